@@ -1,0 +1,612 @@
+"""CPU restatement of torchdiffeq 0.2.x for the latent-motion ODE hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (`gan_ode_b200/`) may
+import this file; only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` do, and there only as
+the checker / the CPU arm.
+
+PARITY UNPINNED: the reference repository (`chechaohp/gan-ode`) holds no tests,
+seeds, golden vectors or saved tensors for this path, and its
+arithmetic lives in the third-party packages `torchdiffeq` (requirements.txt:4,
+unpinned; only version evidence: 0.2.2 in stage1/stage_1_ODE_block.ipynb cell 1)
+and `torchsde` (requirements.txt:13), neither of which is vendored, installed or
+installable in this image.  This file therefore restates torchdiffeq's published
+algorithm (module paths cited per function) in plain PyTorch on CPU tensors, op
+for op, and is pinned by analytic / known-answer tests in
+`tests/test_oracle_pins.py` (expm, order-of-convergence slopes, Butcher order
+conditions, scipy RK45 cross-check, fp64 finite differences) — not by the real
+package.  If `import torchdiffeq` ever succeeds, `tests/test_oracle_vs_real.py`
+compares the two and should be preferred.
+
+Reference call sites this restates the callee of:
+  models/mocogan_ode.py:48-50,105-107,142-144   odeint_adjoint(..., method='rk4')
+  models/mocogan_ode_rnn.py:47-48               odeint_adjoint(ode_fn, h, [0,1]) (dopri5 default)
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+__all__ = ["odeint", "odeint_adjoint", "StepLog", "DOPRI5", "last_step_log"]
+
+
+# ----------------------------------------------------------------------------------------------
+# torchdiffeq/_impl/misc.py
+# ----------------------------------------------------------------------------------------------
+
+def _rms_norm(tensor: torch.Tensor) -> torch.Tensor:
+    """misc.py::_rms_norm — sqrt(mean(|x|^2)) over ALL elements (batch-global)."""
+    return tensor.abs().pow(2).mean().sqrt()
+
+
+def _mixed_norm(tensor_tuple: Sequence[torch.Tensor]) -> torch.Tensor:
+    """misc.py::_mixed_norm — max over components of the rms norm."""
+    if len(tensor_tuple) == 0:
+        return torch.tensor(0.0)
+    return max([_rms_norm(tensor) for tensor in tensor_tuple])
+
+
+def _flat_to_shape(tensor: torch.Tensor, length: Tuple[int, ...], shapes) -> Tuple[torch.Tensor, ...]:
+    """misc.py::_flat_to_shape."""
+    tensor_list = []
+    total = 0
+    for shape in shapes:
+        next_total = total + shape.numel()
+        tensor_list.append(tensor[..., total:next_total].view((*length, *shape)))
+        total = next_total
+    return tuple(tensor_list)
+
+
+class _TupleFunc(torch.nn.Module):
+    """misc.py::_TupleFunc — run a tuple-state vector field on the flattened state."""
+
+    def __init__(self, base_func, shapes):
+        super().__init__()
+        self.base_func = base_func
+        self.shapes = shapes
+
+    def forward(self, t, y):
+        f = self.base_func(t, _flat_to_shape(y, (), self.shapes))
+        return torch.cat([f_.reshape(-1) for f_ in f])
+
+
+class _ReverseFunc(torch.nn.Module):
+    """misc.py::_ReverseFunc — decreasing t is handled by negating time."""
+
+    def __init__(self, base_func, mul=1.0):
+        super().__init__()
+        self.base_func = base_func
+        self.mul = mul
+
+    def forward(self, t, y):
+        return self.mul * self.base_func(-t, y)
+
+
+class _CastTimeFunc(torch.nn.Module):
+    """misc.py::_PerturbFunc minus the one-ulp perturbation (irrelevant for an autonomous field):
+    the time argument is cast to the state dtype before the user function sees it."""
+
+    def __init__(self, base_func):
+        super().__init__()
+        self.base_func = base_func
+
+    def forward(self, t, y):
+        return self.base_func(t.to(y.dtype), y)
+
+
+def _select_initial_step(func, t0, y0, order, rtol, atol, norm, f0=None):
+    """misc.py::_select_initial_step (Hairer, Norsett & Wanner II.4)."""
+    dtype = y0.dtype
+    device = y0.device
+    t_dtype = t0.dtype
+    t0 = t0.to(t_dtype)
+
+    if f0 is None:
+        f0 = func(t0, y0)
+
+    scale = atol + torch.abs(y0) * rtol
+
+    d0 = norm(y0 / scale).abs()
+    d1 = norm(f0 / scale).abs()
+
+    if d0 < 1e-5 or d1 < 1e-5:
+        h0 = torch.tensor(1e-6, dtype=dtype, device=device)
+    else:
+        h0 = 0.01 * d0 / d1
+    h0 = h0.abs()
+
+    y1 = y0 + h0 * f0
+    f1 = func(t0 + h0, y1)
+
+    d2 = torch.abs(norm((f1 - f0) / scale) / h0)
+
+    if d1 <= 1e-15 and d2 <= 1e-15:
+        h1 = torch.max(torch.tensor(1e-6, dtype=dtype, device=device), h0 * 1e-3)
+    else:
+        h1 = (0.01 / max(d1, d2)) ** (1.0 / float(order + 1))
+    h1 = h1.abs()
+
+    return torch.min(100 * h0, h1).to(t_dtype)
+
+
+def _compute_error_ratio(error_estimate, rtol, atol, y0, y1, norm):
+    """misc.py::_compute_error_ratio."""
+    error_tol = atol + rtol * torch.max(y0.abs(), y1.abs())
+    return norm(error_estimate / error_tol).abs()
+
+
+@torch.no_grad()
+def _optimal_step_size(last_step, error_ratio, safety, ifactor, dfactor, order):
+    """misc.py::_optimal_step_size."""
+    if error_ratio == 0:
+        return last_step * ifactor
+    if error_ratio < 1:
+        dfactor = torch.ones((), dtype=last_step.dtype, device=last_step.device)
+    error_ratio = error_ratio.type_as(last_step)
+    exponent = torch.tensor(order, dtype=last_step.dtype, device=last_step.device).reciprocal()
+    factor = torch.min(ifactor, torch.max(safety / error_ratio ** exponent, dfactor))
+    return last_step * factor
+
+
+def _assert_increasing(name, t):
+    assert (t[1:] > t[:-1]).all(), "{} must be strictly increasing or decreasing".format(name)
+
+
+def _check_inputs(func, y0, t, rtol, atol, method, options):
+    """misc.py::_check_inputs — tuple flattening, time reversal, defaults, norm selection."""
+    shapes = None
+    is_tuple = not isinstance(y0, torch.Tensor)
+    if is_tuple:
+        assert isinstance(y0, tuple), "y0 must be either a torch.Tensor or a tuple"
+        shapes = [y0_.shape for y0_ in y0]
+        y0 = torch.cat([y0_.reshape(-1) for y0_ in y0])
+        func = _TupleFunc(func, shapes)
+    if not torch.is_floating_point(y0):
+        raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0.type()))
+
+    if options is None:
+        options = {}
+    else:
+        options = options.copy()
+    if method is None:
+        method = "dopri5"
+    if method not in ("rk4", "dopri5", "euler"):
+        raise ValueError('Invalid method "{}" (oracle restates rk4, dopri5, euler only)'.format(method))
+
+    if is_tuple:
+        if "norm" in options:
+            user_norm = options["norm"]
+            options["norm"] = lambda tensor: user_norm(_flat_to_shape(tensor, (), shapes))
+        else:
+            options["norm"] = lambda tensor: _mixed_norm(_flat_to_shape(tensor, (), shapes))
+    else:
+        options.setdefault("norm", _rms_norm)
+
+    assert t.ndimension() == 1, "t must be one dimensional"
+    if not torch.is_floating_point(t):
+        raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
+    t_is_reversed = False
+    if len(t) > 1 and t[0] > t[1]:
+        t_is_reversed = True
+    if t_is_reversed:
+        t = -t
+        func = _ReverseFunc(func, mul=-1.0)
+    _assert_increasing("t", t)
+
+    if t.device != y0.device:
+        warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
+        t = t.to(y0.device)
+
+    func = _CastTimeFunc(func)
+    return shapes, func, y0, t, rtol, atol, method, options, t_is_reversed
+
+
+# ----------------------------------------------------------------------------------------------
+# torchdiffeq/_impl/rk_common.py, fixed_grid.py, solvers.py  (fixed grid)
+# ----------------------------------------------------------------------------------------------
+
+_one_third = 1 / 3
+_two_thirds = 2 / 3
+
+
+def rk4_alt_step_func(func, t0, dt, t1, y0, f0=None):
+    """rk_common.py::rk4_alt_step_func — the 3/8 rule ("smaller error with slightly more compute").
+    torchdiffeq's method='rk4' uses THIS, not the classic tableau (fixed_grid.py::RK4._step_func)."""
+    k1 = f0
+    if k1 is None:
+        k1 = func(t0, y0)
+    k2 = func(t0 + dt * _one_third, y0 + dt * k1 * _one_third)
+    k3 = func(t0 + dt * _two_thirds, y0 + dt * (k2 - k1 * _one_third))
+    k4 = func(t1, y0 + dt * (k1 - k2 + k3))
+    return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
+
+
+def _euler_step_func(func, t0, dt, t1, y0):
+    """fixed_grid.py::Euler._step_func."""
+    return dt * func(t0, y0)
+
+
+def _linear_interp(t0, t1, y0, y1, t):
+    """solvers.py::FixedGridODESolver._linear_interp."""
+    if t == t0:
+        return y0
+    if t == t1:
+        return y1
+    slope = (t - t0) / (t1 - t0)
+    return y0 + slope * (y1 - y0)
+
+
+def _grid_constructor_from_step_size(step_size):
+    """solvers.py::FixedGridODESolver._grid_constructor_from_step_size."""
+
+    def _grid_constructor(func, y0, t):
+        start_time = t[0]
+        end_time = t[-1]
+        niters = torch.ceil((end_time - start_time) / step_size + 1).item()
+        t_infer = torch.arange(0, niters, dtype=t.dtype, device=t.device) * step_size + start_time
+        t_infer[-1] = t[-1]
+        return t_infer
+
+    return _grid_constructor
+
+
+def _fixed_grid_integrate(func, y0, t, method, options):
+    """solvers.py::FixedGridODESolver.integrate with step function `method`."""
+    step_size = options.get("step_size", None)
+    if step_size is None:
+        time_grid = t
+    else:
+        time_grid = _grid_constructor_from_step_size(step_size)(func, y0, t)
+    assert time_grid[0] == t[0] and time_grid[-1] == t[-1]
+
+    solution = torch.empty(len(t), *y0.shape, dtype=y0.dtype, device=y0.device)
+    solution[0] = y0
+
+    j = 1
+    for t0, t1 in zip(time_grid[:-1], time_grid[1:]):
+        dt = t1 - t0
+        if method == "rk4":
+            dy = rk4_alt_step_func(func, t0, dt, t1, y0)
+        else:
+            dy = _euler_step_func(func, t0, dt, t1, y0)
+        y1 = y0 + dy
+        while j < len(t) and t1 >= t[j]:
+            solution[j] = _linear_interp(t0, t1, y0, y1, t[j])
+            j += 1
+        y0 = y1
+    return solution
+
+
+# ----------------------------------------------------------------------------------------------
+# torchdiffeq/_impl/dopri5.py, rk_common.py, interp.py  (adaptive)
+# ----------------------------------------------------------------------------------------------
+
+class DOPRI5:
+    """dopri5.py — Dormand–Prince 5(4) tableau with Shampine's error weights, built in fp64."""
+
+    alpha = torch.tensor([1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0], dtype=torch.float64)
+    beta = [
+        torch.tensor([1 / 5], dtype=torch.float64),
+        torch.tensor([3 / 40, 9 / 40], dtype=torch.float64),
+        torch.tensor([44 / 45, -56 / 15, 32 / 9], dtype=torch.float64),
+        torch.tensor([19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729], dtype=torch.float64),
+        torch.tensor([9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656], dtype=torch.float64),
+        torch.tensor([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84], dtype=torch.float64),
+    ]
+    c_sol = torch.tensor([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0], dtype=torch.float64)
+    c_error = torch.tensor(
+        [
+            35 / 384 - 1951 / 21600,
+            0,
+            500 / 1113 - 22642 / 50085,
+            125 / 192 - 451 / 720,
+            -2187 / 6784 - -12231 / 42400,
+            11 / 84 - 649 / 6300,
+            -1.0 / 60.0,
+        ],
+        dtype=torch.float64,
+    )
+    c_mid = torch.tensor(
+        [
+            6025192743 / 30085553152 / 2,
+            0,
+            51252292925 / 65400821598 / 2,
+            -2691868925 / 45128329728 / 2,
+            187940372067 / 1594534317056 / 2,
+            -1776094331 / 19743644256 / 2,
+            11237099 / 235043384 / 2,
+        ],
+        dtype=torch.float64,
+    )
+    order = 5
+
+
+class StepLog:
+    """What the adaptive driver did — one entry per ATTEMPTED step (accepted or not)."""
+
+    def __init__(self):
+        self.t0: List[float] = []
+        self.dt: List[float] = []
+        self.error_ratio: List[float] = []
+        self.accepted: List[bool] = []
+        self.dt0: Optional[float] = None
+        self.nfe = 0
+
+    @property
+    def n_accepted(self):
+        return sum(self.accepted)
+
+    @property
+    def n_rejected(self):
+        return len(self.accepted) - sum(self.accepted)
+
+
+_LAST_LOG: List[Optional[StepLog]] = [None]
+
+
+def last_step_log() -> Optional[StepLog]:
+    """Step log of the most recent adaptive solve run through this oracle (test convenience)."""
+    return _LAST_LOG[0]
+
+
+def _runge_kutta_step(func, y0, f0, t0, dt, t1, tab):
+    """rk_common.py::_runge_kutta_step.  `tab` holds the tableau already cast to y0.dtype."""
+    t0 = t0.to(y0.dtype)
+    dt = dt.to(y0.dtype)
+    t1 = t1.to(y0.dtype)
+    ks = [f0]
+    yi = y0
+    for alpha_i, beta_i in zip(tab["alpha"], tab["beta"]):
+        ti = t1 if alpha_i == 1.0 else t0 + alpha_i * dt
+        k = torch.stack(ks, dim=-1)
+        yi = y0 + torch.sum(k * (beta_i * dt), dim=-1).view_as(f0)
+        ks.append(func(ti, yi))
+    k = torch.stack(ks, dim=-1)
+    # c_sol[-1] == 0 and c_sol[:-1] == beta[-1]  (FSAL): y1 is the last stage input, f1 the last k.
+    y1 = yi
+    f1 = ks[-1]
+    y1_error = k.matmul(dt * tab["c_error"])
+    return y1, f1, y1_error, k
+
+
+def _interp_fit(y0, y1, y_mid, f0, f1, dt):
+    """interp.py::_interp_fit — quartic through (y0, y_mid, y1) with end slopes."""
+    a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+    b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+    c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+    d = dt * f0
+    e = y0
+    return [e, d, c, b, a]
+
+
+def _interp_evaluate(coefficients, t0, t1, t):
+    """interp.py::_interp_evaluate."""
+    assert (t0 <= t) & (t <= t1), "invalid interpolation, fails `t0 <= t <= t1`: {}, {}, {}".format(t0, t, t1)
+    x = (t - t0) / (t1 - t0)
+    x = x.to(coefficients[0].dtype)
+    total = coefficients[0] + x * coefficients[1]
+    x_power = x
+    for coefficient in coefficients[2:]:
+        x_power = x_power * x
+        total = total + x_power * coefficient
+    return total
+
+
+def _dopri5_integrate(func, y0, t, rtol, atol, options):
+    """solvers.py::AdaptiveStepsizeODESolver.integrate +
+    rk_common.py::RKAdaptiveStepsizeODESolver.{_before_integrate,_advance,_adaptive_step}.
+
+    Mixed precision as upstream: state and k in y0.dtype; t, dt, rtol, atol, safety, ifactor,
+    dfactor in promote(float64, y0.dtype)."""
+    norm = options["norm"]
+    tdtype = torch.promote_types(torch.float64, y0.dtype)
+    device = y0.device
+    rtol = torch.as_tensor(rtol, dtype=tdtype, device=device)
+    atol = torch.as_tensor(atol, dtype=tdtype, device=device)
+    min_step = torch.as_tensor(options.get("min_step", 0), dtype=tdtype, device=device)
+    max_step = torch.as_tensor(options.get("max_step", float("inf")), dtype=tdtype, device=device)
+    first_step = options.get("first_step", None)
+    safety = torch.as_tensor(options.get("safety", 0.9), dtype=tdtype, device=device)
+    ifactor = torch.as_tensor(options.get("ifactor", 10.0), dtype=tdtype, device=device)
+    dfactor = torch.as_tensor(options.get("dfactor", 0.2), dtype=tdtype, device=device)
+    max_num_steps = options.get("max_num_steps", 2 ** 31 - 1)
+    tab = {
+        "alpha": DOPRI5.alpha.to(device=device, dtype=y0.dtype),
+        "beta": [b.to(device=device, dtype=y0.dtype) for b in DOPRI5.beta],
+        "c_error": DOPRI5.c_error.to(device=device, dtype=y0.dtype),
+    }
+    mid = DOPRI5.c_mid.to(device=device, dtype=y0.dtype)
+    log = StepLog()
+    _LAST_LOG[0] = log
+
+    def counted(tt, yy):
+        log.nfe += 1
+        return func(tt, yy)
+
+    solution = torch.empty(len(t), *y0.shape, dtype=y0.dtype, device=device)
+    solution[0] = y0
+    t = t.to(tdtype)
+
+    # _before_integrate
+    f0 = counted(t[0], y0)
+    if first_step is None:
+        dt = _select_initial_step(counted, t[0], y0, DOPRI5.order - 1, rtol, atol, norm, f0=f0)
+    else:
+        dt = torch.as_tensor(first_step, dtype=tdtype, device=device)
+    if options.get("_detach_dt0", False):
+        # Upstream leaves the initial-step heuristic inside the autograd graph, which leaks an
+        # O(tol) term into backprop-through-solver gradients.  The CUDA path treats every dt as data; tests
+        # that compare gradients set this private flag and say so.
+        dt = dt.detach()
+    log.dt0 = float(dt.detach())
+    rk_t0, rk_t1 = t[0], t[0]
+    rk_y1, rk_f1 = y0, f0
+    interp_coeff = [y0] * 5
+
+    for i in range(1, len(t)):
+        next_t = t[i]
+        n_steps = 0
+        while next_t > rk_t1:
+            assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
+            # _adaptive_step
+            ys, fs, ts = rk_y1, rk_f1, rk_t1
+            t1 = ts + dt
+            assert ts + dt > ts, "underflow in dt {}".format(dt.item())
+            assert torch.isfinite(ys).all(), "non-finite values in state `y`: {}".format(ys)
+            y1, f1, y1_error, k = _runge_kutta_step(counted, ys, fs, ts, dt, t1, tab)
+            error_ratio = _compute_error_ratio(y1_error, rtol, atol, ys, y1, norm)
+            accept_step = bool(error_ratio <= 1)
+            if dt > max_step:
+                accept_step = False
+            if dt <= min_step:
+                accept_step = True
+            log.t0.append(float(ts.detach()))
+            log.dt.append(float(dt.detach()))
+            log.error_ratio.append(float(error_ratio.detach()))
+            log.accepted.append(accept_step)
+            if accept_step:
+                dt32 = dt.type_as(ys)
+                y_mid = ys + k.matmul(dt32 * mid).view_as(ys)
+                interp_coeff = _interp_fit(ys, y1, y_mid, k[..., 0], k[..., -1], dt32)
+                rk_t0, rk_t1 = ts, t1
+                rk_y1, rk_f1 = y1, f1
+            else:
+                rk_t0, rk_t1 = ts, ts
+            dt = _optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, DOPRI5.order)
+            dt = dt.clamp(min_step, max_step)
+            n_steps += 1
+        solution[i] = _interp_evaluate(interp_coeff, rk_t0, rk_t1, next_t)
+    return solution
+
+
+# ----------------------------------------------------------------------------------------------
+# torchdiffeq/_impl/odeint.py
+# ----------------------------------------------------------------------------------------------
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """odeint.py::odeint — same signature; differentiable by ordinary autograd (A.5:
+    backprop-through-solver).  The adaptive controller's dt sequence is data (no_grad) except
+    the initial-step heuristic, exactly as upstream."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not on the gan-ode hot path")
+    shapes, func, y0, t, rtol, atol, method, options, t_is_reversed = _check_inputs(
+        func, y0, t, rtol, atol, method, options
+    )
+    if method == "dopri5":
+        solution = _dopri5_integrate(func, y0, t, rtol, atol, options)
+    else:
+        solution = _fixed_grid_integrate(func, y0, t, method, options)
+    if shapes is not None:
+        solution = _flat_to_shape(solution, (len(t),), shapes)
+    return solution
+
+
+# ----------------------------------------------------------------------------------------------
+# torchdiffeq/_impl/adjoint.py
+# ----------------------------------------------------------------------------------------------
+
+class _OdeintAdjointMethod(torch.autograd.Function):
+    """adjoint.py::OdeintAdjointMethod (tensor state, no event function, t.requires_grad False —
+    the only way the reference calls it)."""
+
+    @staticmethod
+    def forward(ctx, func, y0, t, rtol, atol, method, options, adjoint_rtol, adjoint_atol,
+                adjoint_method, adjoint_options, *adjoint_params):
+        ctx.func = func
+        ctx.adjoint_rtol = adjoint_rtol
+        ctx.adjoint_atol = adjoint_atol
+        ctx.adjoint_method = adjoint_method
+        ctx.adjoint_options = adjoint_options
+        with torch.no_grad():
+            y = odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+        ctx.save_for_backward(t, y, *adjoint_params)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        with torch.no_grad():
+            func = ctx.func
+            t, y, *adjoint_params = ctx.saved_tensors
+            adjoint_params = tuple(adjoint_params)
+
+            aug_state = [torch.zeros((), dtype=y.dtype, device=y.device), y[-1], grad_y[-1]]
+            aug_state.extend([torch.zeros_like(param) for param in adjoint_params])
+
+            def augmented_dynamics(t_, y_aug):
+                y_ = y_aug[1]
+                adj_y = y_aug[2]
+                with torch.enable_grad():
+                    t_d = t_.detach()
+                    t_g = t_d.requires_grad_(True)
+                    y_g = y_.detach().requires_grad_(True)
+                    func_eval = func(t_d, y_g)
+                    vjp_t, vjp_y, *vjp_params = torch.autograd.grad(
+                        func_eval, (t_g, y_g) + adjoint_params, -adj_y,
+                        allow_unused=True, retain_graph=True,
+                    )
+                vjp_t = torch.zeros_like(t_g) if vjp_t is None else vjp_t
+                vjp_y = torch.zeros_like(y_g) if vjp_y is None else vjp_y
+                vjp_params = [torch.zeros_like(p) if g is None else g for p, g in zip(adjoint_params, vjp_params)]
+                return (vjp_t, func_eval, vjp_y, *vjp_params)
+
+            for i in range(len(t) - 1, 0, -1):
+                aug_state = odeint(
+                    augmented_dynamics, tuple(aug_state), t[i - 1:i + 1].flip(0),
+                    rtol=ctx.adjoint_rtol, atol=ctx.adjoint_atol, method=ctx.adjoint_method,
+                    options=ctx.adjoint_options,
+                )
+                aug_state = [a[1] for a in aug_state]
+                aug_state[1] = y[i - 1]
+                aug_state[2] += grad_y[i - 1]
+
+            adj_y = aug_state[2]
+            adj_params = aug_state[3:]
+        return (None, adj_y, None, None, None, None, None, None, None, None, None, *adj_params)
+
+
+def _default_adjoint_norm(state_norm):
+    """adjoint.py::handle_adjoint_norm_::default_adjoint_norm."""
+
+    def default_adjoint_norm(tensor_tuple):
+        t, y, adj_y, *adj_params = tensor_tuple
+        return max(t.abs(), state_norm(y), state_norm(adj_y), _mixed_norm(adj_params))
+
+    return default_adjoint_norm
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None):
+    """adjoint.py::odeint_adjoint — same signature and defaulting rules."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not on the gan-ode hot path")
+    if adjoint_params is None and not isinstance(func, torch.nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they "
+                         "can be specified explicitly via the `adjoint_params` argument. If there are no parameters "
+                         "then it is allowable to set `adjoint_params=()`.")
+    if adjoint_rtol is None:
+        adjoint_rtol = rtol
+    if adjoint_atol is None:
+        adjoint_atol = atol
+    if adjoint_method is None:
+        adjoint_method = method
+    if adjoint_options is None:
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    else:
+        adjoint_options = adjoint_options.copy()
+    if adjoint_params is None:
+        adjoint_params = tuple(p for p in func.parameters() if p.requires_grad)
+    else:
+        adjoint_params = tuple(p for p in adjoint_params if p.requires_grad)
+    if not isinstance(y0, torch.Tensor):
+        raise NotImplementedError("tuple y0 through the adjoint is not on the gan-ode hot path")
+
+    state_norm = options["norm"] if (options is not None and "norm" in options) else _rms_norm
+    if "norm" not in adjoint_options:
+        adjoint_options["norm"] = _default_adjoint_norm(state_norm)
+
+    return _OdeintAdjointMethod.apply(func, y0, t, rtol, atol, method, options, adjoint_rtol, adjoint_atol,
+                                      adjoint_method, adjoint_options, *adjoint_params)

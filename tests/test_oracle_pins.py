@@ -1,0 +1,347 @@
+"""Pins for the CPU oracle (SURVEY.md §8c "pins the new repo must create").
+
+The reference holds no golden vectors for this path and torchdiffeq/torchsde are absent, so the
+oracle is anchored on analytic answers, order conditions, an independent DP5 (scipy), finite
+differences, nn.GRUCell and Random123's Philox known-answer vectors.
+"""
+from fractions import Fraction as Fr
+
+import numpy as np
+import pytest
+import scipy.integrate
+import scipy.linalg
+import torch
+
+from oracle import torchdiffeq_restatement as tdq
+from oracle import torchsde_restatement as tsde
+from oracle.latent_motion import ODEFunc, SDEFunc, sample_z_m_odernn
+from oracle.philox import philox4x32_10, normals
+
+
+class Lin(torch.nn.Module):
+    def __init__(self, A):
+        super().__init__()
+        self.A = A
+
+    def forward(self, t, y):
+        return y @ self.A.T
+
+
+def _expm_traj(A, y0, t):
+    return torch.stack([y0 @ torch.tensor(scipy.linalg.expm(A.numpy() * float(tt))).T for tt in t])
+
+
+# ---- (1) analytic -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("method,tol", [("rk4", 1e-6), ("dopri5", 1e-8)])
+def test_linear_ode_matches_expm(method, tol):
+    torch.manual_seed(0)
+    A = torch.randn(4, 4, dtype=torch.float64) * 0.5
+    y0 = torch.randn(3, 4, dtype=torch.float64)
+    t = torch.linspace(0, 1, 16, dtype=torch.float64)
+    sol = tdq.odeint(Lin(A), y0, t, method=method, rtol=1e-9, atol=1e-11)
+    assert torch.equal(sol[0], y0)
+    assert (sol - _expm_traj(A, y0, t)).abs().max() < tol
+
+
+def test_decreasing_time_is_time_reversal():
+    torch.manual_seed(1)
+    A = torch.randn(3, 3, dtype=torch.float64) * 0.3
+    y0 = torch.randn(2, 3, dtype=torch.float64)
+    t = torch.linspace(1, 0, 9, dtype=torch.float64)
+    for method in ("rk4", "dopri5"):
+        sol = tdq.odeint(Lin(A), y0, t, method=method, rtol=1e-10, atol=1e-12)
+        ex = torch.stack([y0 @ torch.tensor(scipy.linalg.expm(A.numpy() * (float(tt) - 1.0))).T for tt in t])
+        assert (sol - ex).abs().max() < 1e-6
+
+
+# ---- (2) order of convergence --------------------------------------------------------------------
+
+def test_rk4_38_rule_is_order_4():
+    torch.manual_seed(2)
+    A = torch.randn(4, 4, dtype=torch.float64)
+    y0 = torch.randn(1, 4, dtype=torch.float64)
+    errs = []
+    for n in (8, 16, 32, 64):
+        t = torch.linspace(0, 1, n + 1, dtype=torch.float64)
+        sol = tdq.odeint(Lin(A), y0, t, method="rk4")
+        errs.append(float((sol[-1] - _expm_traj(A, y0, t[-1:])[0]).abs().max()))
+    slopes = [np.log2(errs[i] / errs[i + 1]) for i in range(3)]
+    assert all(3.7 < s < 4.4 for s in slopes), slopes
+
+
+def test_rk4_is_the_38_rule_not_classic():
+    """One step of y' = y: 3/8 rule and classic RK4 agree to O(h^5) but differ in rounding-free rational
+    arithmetic for a nonlinear field; check the stage times 1/3, 2/3 are what the field sees."""
+    seen = []
+
+    class F(torch.nn.Module):
+        def forward(self, t, y):
+            seen.append(float(t))
+            return -y * y
+
+    y0 = torch.ones(1, 1, dtype=torch.float64)
+    tdq.odeint(F(), y0, torch.tensor([0.0, 0.3], dtype=torch.float64), method="rk4")
+    assert np.allclose(seen, [0.0, 0.1, 0.2, 0.3])
+
+
+def test_dopri5_local_order_5():
+    torch.manual_seed(3)
+    A = torch.randn(3, 3, dtype=torch.float64)
+    y0 = torch.randn(1, 3, dtype=torch.float64)
+    errs = []
+    for h in (0.2, 0.1, 0.05):
+        # a single forced step of size h: first_step=h, tolerances so loose it is accepted, output at t=h
+        sol = tdq.odeint(Lin(A), y0, torch.tensor([0.0, h], dtype=torch.float64), method="dopri5",
+                         rtol=1e3, atol=1e3, options={"first_step": h})
+        assert tdq.last_step_log().accepted == [True]
+        errs.append(float((sol[-1] - _expm_traj(A, y0, torch.tensor([h], dtype=torch.float64))[0]).abs().max()))
+    slopes = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert all(5.5 < s < 6.5 for s in slopes), slopes  # local error O(h^6)
+
+
+# ---- (3) Butcher / interpolation identities -------------------------------------------
+
+def test_dopri5_tableau_order_conditions():
+    c = [Fr(0), Fr(1, 5), Fr(3, 10), Fr(4, 5), Fr(8, 9), Fr(1), Fr(1)]
+    beta = [
+        [Fr(1, 5)],
+        [Fr(3, 40), Fr(9, 40)],
+        [Fr(44, 45), Fr(-56, 15), Fr(32, 9)],
+        [Fr(19372, 6561), Fr(-25360, 2187), Fr(64448, 6561), Fr(-212, 729)],
+        [Fr(9017, 3168), Fr(-355, 33), Fr(46732, 5247), Fr(49, 176), Fr(-5103, 18656)],
+        [Fr(35, 384), Fr(0), Fr(500, 1113), Fr(125, 192), Fr(-2187, 6784), Fr(11, 84)],
+    ]
+    for i, row in enumerate(beta):
+        assert sum(row) == c[i + 1]
+        assert np.allclose([float(x) for x in row], tdq.DOPRI5.beta[i].numpy())
+    b = beta[-1] + [Fr(0)]
+    assert sum(b) == 1
+    assert sum(bi * ci for bi, ci in zip(b, c)) == Fr(1, 2)
+    assert sum(bi * ci ** 2 for bi, ci in zip(b, c)) == Fr(1, 3)
+    assert sum(bi * ci ** 3 for bi, ci in zip(b, c)) == Fr(1, 4)
+    assert sum(bi * ci ** 4 for bi, ci in zip(b, c)) == Fr(1, 5)
+    bstar = [Fr(1951, 21600), Fr(0), Fr(22642, 50085), Fr(451, 720), Fr(-12231, 42400), Fr(649, 6300), Fr(1, 60)]
+    assert sum(bstar) == 1
+    for p in (1, 2, 3):
+        assert sum(bi * ci ** p for bi, ci in zip(bstar, c)) == Fr(1, p + 1)
+    assert sum(bi * ci ** 4 for bi, ci in zip(bstar, c)) != Fr(1, 5)
+    cerr = [float(x - y) for x, y in zip(b, bstar)]
+    assert np.allclose(cerr, tdq.DOPRI5.c_error.numpy(), atol=1e-16)
+    cmid = [Fr(6025192743, 30085553152), Fr(0), Fr(51252292925, 65400821598), Fr(-2691868925, 45128329728),
+            Fr(187940372067, 1594534317056), Fr(-1776094331, 19743644256), Fr(11237099, 235043384)]
+    cmid = [x / 2 for x in cmid]
+    assert np.allclose([float(x) for x in cmid], tdq.DOPRI5.c_mid.numpy())
+    assert abs(float(sum(cmid)) - 0.5) < 1e-12
+    assert abs(float(sum(m * ci for m, ci in zip(cmid, c))) - 1 / 8) < 1e-12
+    assert abs(float(sum(m * ci ** 2 for m, ci in zip(cmid, c))) - 1 / 24) < 1e-12
+    assert abs(float(sum(m * ci ** 3 for m, ci in zip(cmid, c))) - 1 / 64) < 1e-12
+
+
+def test_38_rule_order_conditions():
+    c = [Fr(0), Fr(1, 3), Fr(2, 3), Fr(1)]
+    b = [Fr(1, 8), Fr(3, 8), Fr(3, 8), Fr(1, 8)]
+    a = [[], [Fr(1, 3)], [Fr(-1, 3), Fr(1)], [Fr(1), Fr(-1), Fr(1)]]
+    for i in range(1, 4):
+        assert sum(a[i]) == c[i]
+    for p in range(4):
+        assert sum(bi * ci ** p for bi, ci in zip(b, c)) == Fr(1, p + 1)
+    assert sum(b[i] * sum(a[i][j] * c[j] for j in range(i)) for i in range(4)) == Fr(1, 6)
+    assert sum(b[i] * c[i] * sum(a[i][j] * c[j] for j in range(i)) for i in range(4)) == Fr(1, 8)
+    assert sum(b[i] * sum(a[i][j] * c[j] ** 2 for j in range(i)) for i in range(4)) == Fr(1, 12)
+    assert sum(b[i] * sum(a[i][j] * sum(a[j][k] * c[k] for k in range(j)) for j in range(i)) for i in range(4)) == Fr(1, 24)
+
+
+def test_quartic_interpolant_endpoints_and_slopes():
+    torch.manual_seed(4)
+    y0, y1, ym, f0, f1 = (torch.randn(5, dtype=torch.float64) for _ in range(5))
+    dt = torch.tensor(0.37, dtype=torch.float64)
+    co = tdq._interp_fit(y0, y1, ym, f0, f1, dt)
+    t0, t1 = torch.tensor(1.0, dtype=torch.float64), torch.tensor(1.37, dtype=torch.float64)
+    ev = lambda t: tdq._interp_evaluate(co, t0, t1, torch.tensor(t, dtype=torch.float64))
+    assert torch.allclose(ev(1.0), y0) and torch.allclose(ev(1.37), y1) and torch.allclose(ev(1.185), ym)
+    eps = 1e-7  # one-sided difference: error ~ eps/2 * |p''|, p'' = O(1e2) for random data
+    assert torch.allclose((ev(1.0 + eps) - ev(1.0)) / eps, f0, atol=1e-3)
+    assert torch.allclose((ev(1.37) - ev(1.37 - eps)) / eps, f1, atol=1e-3)
+
+
+# ---- (4) independent DP5 ----------------------------------------------------------------------------
+
+def test_dopri5_vs_scipy_rk45_on_odefunc():
+    torch.manual_seed(5)
+    f = ODEFunc(16, 16).double()
+    with torch.no_grad():
+        for p in f.parameters():
+            p.mul_(3.0)
+    y0 = torch.randn(8, 16, dtype=torch.float64)
+    t = torch.linspace(0, 1, 16, dtype=torch.float64)
+    sol = tdq.odeint(f, y0, t, method="dopri5", rtol=1e-9, atol=1e-11)
+
+    def rhs(tt, y):
+        with torch.no_grad():
+            return f(None, torch.from_numpy(y).view(8, 16)).reshape(-1).numpy()
+
+    ref = scipy.integrate.solve_ivp(rhs, (0, 1), y0.reshape(-1).numpy(), method="RK45", t_eval=t.numpy(),
+                                    rtol=1e-11, atol=1e-13)
+    assert np.abs(sol.detach().numpy().reshape(16, -1) - ref.y.T).max() < 1e-6
+
+
+def test_dopri5_step_sequence_is_independent_of_output_times():
+    torch.manual_seed(6)
+    f = ODEFunc(16, 16)
+    y0 = torch.randn(32, 16)
+    with torch.no_grad():
+        for p in f.parameters():
+            p.mul_(4.0)
+        tdq.odeint(f, y0, torch.linspace(0, 1, 16), method="dopri5", rtol=1e-5, atol=1e-5)
+        a = tdq.last_step_log()
+        tdq.odeint(f, y0, torch.tensor([0.0, 1.0]), method="dopri5", rtol=1e-5, atol=1e-5)
+        b = tdq.last_step_log()
+    assert a.accepted == b.accepted and a.dt == b.dt
+    assert a.n_rejected > 0  # the stiffer variant exercises rejections
+    assert a.nfe == 2 + 6 * len(a.accepted)
+
+
+# ---- (5) adjoint vs autograd-through-solver vs finite differences -----------------------------------
+
+def _loss(solve, f, y0, t, g, **kw):
+    return (solve(f, y0, t, **kw) * g).sum()
+
+
+@pytest.mark.parametrize("method,kw", [("rk4", {}), ("dopri5", dict(rtol=1e-9, atol=1e-11))])
+def test_gradients_adjoint_autograd_fd(method, kw):
+    torch.manual_seed(7)
+    f = ODEFunc(6, 5).double()
+    y0 = torch.randn(4, 6, dtype=torch.float64, requires_grad=True)
+    t = torch.linspace(0, 1, 6 if method == "rk4" else 4, dtype=torch.float64)
+    if method == "rk4":
+        t = torch.linspace(0, 1, 41, dtype=torch.float64)  # fine grid so the continuous adjoint ~ discrete gradient
+    g = torch.randn(len(t), 4, 6, dtype=torch.float64)
+    params = list(f.parameters())
+
+    ga = torch.autograd.grad(_loss(tdq.odeint_adjoint, f, y0, t, g, method=method, **kw), [y0] + params)
+    gb = torch.autograd.grad(_loss(tdq.odeint, f, y0, t, g, method=method, **kw), [y0] + params)
+    for a, b in zip(ga, gb):
+        assert (a - b).abs().max() < 2e-5 * max(1.0, float(b.abs().max()))
+
+    # fp64 central finite differences on a few coordinates against autograd-through-solver
+    eps = 1e-6
+    with torch.no_grad():
+        for tensor, grad in zip([y0] + params, gb):
+            flat = tensor.view(-1)
+            for idx in (0, flat.numel() // 2, flat.numel() - 1):
+                old = flat[idx].item()
+                flat[idx] = old + eps
+                lp = _loss(tdq.odeint, f, y0, t, g, method=method, **kw)
+                flat[idx] = old - eps
+                lm = _loss(tdq.odeint, f, y0, t, g, method=method, **kw)
+                flat[idx] = old
+                fd = float(lp - lm) / (2 * eps)
+                assert abs(fd - float(grad.view(-1)[idx])) < 1e-5 * max(1.0, abs(fd))
+
+
+def test_rk4_adjoint_is_one_38_step_per_interval_on_augmented_state():
+    """A.4: with method='rk4' every backward interval is ONE 3/8-rule step of the augmented system, so the
+    adjoint's parameter gradient equals this closed-form restatement (A.4 last bullet)."""
+    torch.manual_seed(8)
+    f = ODEFunc(16, 16)
+    y0 = torch.randn(32, 16, requires_grad=True)
+    t = torch.linspace(0, 1, 16)
+    g = torch.randn(16, 32, 16)
+    sol = tdq.odeint_adjoint(f, y0, t, method="rk4")
+    grads = torch.autograd.grad((sol * g).sum(), [y0] + list(f.parameters()))
+
+    W1, b1, W2, b2 = [p.detach() for p in f.parameters()]
+
+    def F(y, a):
+        h = torch.tanh(y @ W1.T + b1)
+        fe = h @ W2.T + b2
+        gh = a @ W2
+        delta = gh * (1 - h * h)
+        return -fe, delta @ W1, (delta.T @ y, delta.sum(0), a.T @ h, a.sum(0))
+
+    sol = sol.detach()
+    a = g[-1].clone()
+    acc = [torch.zeros_like(p) for p in (W1, b1, W2, b2)]
+    for i in range(15, 0, -1):
+        dt = (-t[i - 1]) - (-t[i])
+        y = sol[i]
+        k1y, k1a, k1p = F(y, a)
+        k2y, k2a, k2p = F(y + dt * k1y / 3, a + dt * k1a / 3)
+        k3y, k3a, k3p = F(y + dt * (k2y - k1y / 3), a + dt * (k2a - k1a / 3))
+        k4y, k4a, k4p = F(y + dt * (k1y - k2y + k3y), a + dt * (k1a - k2a + k3a))
+        a = a + (k1a + 3 * (k2a + k3a) + k4a) * dt * 0.125 + g[i - 1]
+        acc = [A + (p1 + 3 * (p2 + p3) + p4) * dt * 0.125 for A, p1, p2, p3, p4 in zip(acc, k1p, k2p, k3p, k4p)]
+    for mine, ref in zip([a] + acc, grads):
+        assert (mine - ref).abs().max() <= 2e-5 * float(ref.abs().max())
+
+
+# ---- (6) GRU jump ------------------------------------------------------------------------------------
+
+def test_odernn_loop_shapes_and_gru_formula():
+    torch.manual_seed(9)
+    f = ODEFunc(16, 16)
+    gru = torch.nn.GRUCell(16, 16)
+    h0 = torch.randn(3, 16)
+    eps = torch.randn(4, 3, 16)
+    with torch.no_grad():
+        z = sample_z_m_odernn(f, gru, h0, eps, adjoint=False, rtol=1e-5, atol=1e-5)
+        assert z.shape == (12, 16)
+        hp = tdq.odeint(f, h0, torch.tensor([0.0, 1.0]), rtol=1e-5, atol=1e-5)[-1]
+        Wi, Wh, bi, bh = gru.weight_ih, gru.weight_hh, gru.bias_ih, gru.bias_hh
+        gi = eps[0] @ Wi.T + bi
+        gh = hp @ Wh.T + bh
+        r = torch.sigmoid(gi[:, :16] + gh[:, :16])
+        zz = torch.sigmoid(gi[:, 16:32] + gh[:, 16:32])
+        n = torch.tanh(gi[:, 32:] + r * gh[:, 32:])
+        h1 = (1 - zz) * n + zz * hp
+    assert torch.allclose(z.view(3, 4, 16)[:, 0], h1, atol=1e-6)
+
+
+# ---- (7) Philox + SDE grid -----------------------------------------------------------------------------
+
+def test_philox4x32_10_random123_known_answers():
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, out in kat:
+        r = philox4x32_10(np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert [int(x) for x in r] == out
+
+
+def test_philox_normals_moments():
+    z = normals(1234, np.arange(200000), step=3, d_block=1)
+    assert abs(z.mean()) < 5e-3 and abs(z.std() - 1) < 5e-3
+    assert abs((z ** 4).mean() - 3) < 0.05
+
+
+def test_sde_euler_grid_is_41_steps_with_fp32_time():
+    ts = torch.linspace(0, 1, 16).float()
+    pairs = tsde.step_grid(ts, 2.5e-2)
+    assert len(pairs) == 41  # SURVEY Appendix B (measured upstream behaviour: fp32 accumulation)
+    assert float(pairs[-1][1]) == 1.0 and float(pairs[-1][1] - pairs[-1][0]) < 1e-6
+
+
+def test_sde_euler_given_increments_matches_hand_loop():
+    torch.manual_seed(10)
+    sde = SDEFunc(16, 16)
+    y0 = torch.randn(5, 16)
+    ts = torch.linspace(0, 1, 16).float()
+    pairs = tsde.step_grid(ts, 2.5e-2)
+    dW = torch.stack([torch.randn(5, 16) * float(b - a) ** 0.5 for a, b in pairs])
+    with torch.no_grad():
+        sol = tsde.sdeint(sde, y0, ts, bm=tsde.TableBrownian(dW), method="euler", dt=2.5e-2)
+        y = y0
+        for k, (a, b) in enumerate(pairs[:2]):
+            y = y + sde.f(a, y) * (b - a) + sde.g(a, y) * dW[k]
+    assert sol.shape == (16, 5, 16) and torch.equal(sol[0], y0)
+    # frame 1 (t=1/15) lies between step 2 (t=.05) and step 3 (t=.075)
+    with torch.no_grad():
+        y2 = y
+        a, b = pairs[2]
+        y3 = y2 + sde.f(a, y2) * (b - a) + sde.g(a, y2) * dW[2]
+        w = (ts[1] - a) / (b - a)
+    assert torch.allclose(sol[1], (1 - w) * y2 + w * y3, atol=1e-6)
