@@ -1,0 +1,84 @@
+"""ctypes binding of libgode.so (the C ABI in include/gode.h).
+
+The product path has NO fallback: if the shared library is missing or a kernel is not compiled for the
+requested shape, callers get an exception, never a silent PyTorch/CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
+
+PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+LAYOUT_TBD, LAYOUT_BTD = 0, 1
+NORM_BATCH, NORM_TRAJ = 0, 1
+MAX_HOST_STEPS = 255
+
+ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_CKPT_OVERFLOW = 1, 2, 4, 8
+
+
+class GodeStepLog(C.Structure):
+    _fields_ = [("status", C.c_int32), ("n_attempts", C.c_int32), ("n_accepted", C.c_int32), ("nfe", C.c_int32),
+                ("dt0", C.c_double), ("t_final", C.c_double)]
+
+
+class GodeAdaptiveOpts(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("first_step", C.c_double), ("safety", C.c_double),
+                ("ifactor", C.c_double), ("dfactor", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double),
+                ("max_num_steps", C.c_int32), ("norm_scope", C.c_int32), ("log_capacity", C.c_int32),
+                ("ckpt_capacity", C.c_int32), ("fsign", C.c_float), ("_pad", C.c_int32)]
+
+
+class GodeError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_I = C.c_int
+_SIGS = {
+    "gode_strerror": (C.c_char_p, [_I]),
+    "gode_version": (C.c_char_p, []),
+    "gode_supported": (_I, [_I, _I, _I]),
+    "gode_param_count": (_I, [_I, _I]),
+    "gode_rk4_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "gode_bwd_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "gode_rk4_adjoint_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
+    "gode_rk4_backprop_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
+    "gode_dopri5_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "gode_dopri5_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 + [C.c_size_t, _P]),
+    "gode_dopri5_backprop_bwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P, C.c_size_t, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libgode.so once.  Raises loudly if it has not been built (python -m gan_ode_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GodeError("libgode.so not found at {} — build it with `python -m gan_ode_b200.build`; "
+                            "there is no CPU/PyTorch fallback for this path".format(LIB_PATH))
+        h = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise GodeError("{} failed: {} (code {})".format(what, lib().gode_strerror(rc).decode(), rc))
+
+
+def declared_symbols():
+    """Every function name declared in include/gode.h (used by the CPU test that the library exports them all)."""
+    import re
+    hdr = os.path.join(os.path.dirname(HERE), "include", "gode.h")
+    src = open(hdr).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gode_[a-z0-9_]+)\s*\(", src)))

@@ -1,0 +1,111 @@
+// capi.cu — the extern "C" boundary declared in include/gode.h.  Argument checking and dispatch only.
+#include "launch.h"
+
+using namespace gode;
+
+extern "C" {
+
+const char* gode_version(void) { return "gode 0.1 (sm_100a)"; }
+
+const char* gode_strerror(int code) {
+  switch (code) {
+    case GODE_OK: return "ok";
+    case GODE_ERR_SHAPE: return "no kernel compiled for this (D, H) at this precision";
+    case GODE_ERR_ARG: return "invalid argument (null pointer, B <= 0, T < 2, bad layout)";
+    case GODE_ERR_T_TOO_LONG: return "host dt table longer than GODE_MAX_HOST_STEPS; pass dt on the device";
+    case GODE_ERR_WORKSPACE: return "workspace too small";
+    case GODE_ERR_COOP: return "batch-global adaptive solve needs every CTA co-resident: batch too large";
+    case GODE_ERR_PRECISION: return "precision mode not available for this entry point";
+    default: return code <= -1000 ? cudaGetErrorString((cudaError_t)(-code - 1000)) : "unknown gode error";
+  }
+}
+
+int gode_param_count(int D, int H) { return H * D + H + D * H + D; }
+
+int gode_supported(int D, int H, int precision) {
+  if (precision == GODE_PREC_FP32) return small_field_shape(D, H) ? 1 : 0;
+  return 0;
+}
+
+static bool bad_common(const void* a, const void* b, const void* c, const void* d, const void* e, int B, int T, int layout) {
+  return !a || !b || !c || !d || !e || B <= 0 || T < 2 || (layout != GODE_LAYOUT_TBD && layout != GODE_LAYOUT_BTD);
+}
+
+int gode_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+                 int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,
+                 gode_stream_t stream) {
+  if (bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !dt || !traj) return GODE_ERR_ARG;
+  if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, out_layout, traj, (cudaStream_t)stream);
+}
+
+size_t gode_bwd_workspace_bytes(int B, int D, int H) {
+  (void)B;
+  return bwd_workspace_bytes(gode_param_count(D, H));
+}
+
+static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                          const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H,
+                          int T, int precision, int layout, float* grad_y0, float* grad_params, void* workspace,
+                          size_t ws_bytes, gode_stream_t stream) {
+  if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !dt || !grad_y0 || !grad_params || !workspace)
+    return GODE_ERR_ARG;
+  if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_bwd(adjoint, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
+                       grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int gode_rk4_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                         const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int precision,
+                         int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                         gode_stream_t stream) {
+  return rk4_bwd_common(true, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, precision, layout,
+                        grad_y0, grad_params, workspace, ws_bytes, stream);
+}
+
+int gode_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                          const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int precision,
+                          int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                          gode_stream_t stream) {
+  return rk4_bwd_common(false, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, precision, layout,
+                        grad_y0, grad_params, workspace, ws_bytes, stream);
+}
+
+size_t gode_dopri5_workspace_bytes(int B, int D, int H) {
+  const size_t a = dopri5_small_workspace_bytes(B, D, H), b = bwd_workspace_bytes(gode_param_count(D, H));
+  return a > b ? a : b;
+}
+
+int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                    float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
+                    float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes,
+                    gode_stream_t stream) {
+  if (bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !t_host || !opts || !traj || !log || !workspace)
+    return GODE_ERR_ARG;
+  if (opts->log_capacity > 0 && (!att_t0 || !att_dt || !att_er || !att_acc)) return GODE_ERR_ARG;
+  if (opts->ckpt_capacity > 0 && (!ckpt || !acc_t0 || !acc_dt)) return GODE_ERR_ARG;
+  if (opts->norm_scope != GODE_NORM_BATCH) return GODE_ERR_ARG;
+  for (int i = 1; i < T; ++i)
+    if (!(t_host[i] > t_host[i - 1])) return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_small_fwd(y0, W1, b1, W2, b2, t_host, B, D, H, T, opts, out_layout, traj, log, att_t0, att_dt, att_er,
+                          att_acc, ckpt, acc_t0, acc_dt, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                             const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                             int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                             size_t ws_bytes, gode_stream_t stream) {
+  if (bad_common(grad_traj, W1, b1, W2, b2, B, T, layout) || !t_host || !log || !ckpt || !acc_t0 || !acc_dt ||
+      ckpt_capacity <= 0 || !grad_y0 || !grad_params || !workspace)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_small_backprop_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, ckpt, acc_t0, acc_dt,
+                                   ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

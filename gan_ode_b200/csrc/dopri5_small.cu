@@ -1,0 +1,536 @@
+// dopri5_small.cu — adaptive Dormand–Prince 5(4) for the small-field shapes, FP32 state / FP64 time.
+//   dopri5_fwd_kernel           torchdiffeq RKAdaptiveStepsizeODESolver, batch-global RMS error norm:
+//                               ONE (t, dt) for the whole batch, so every attempted step ends in a grid-wide
+//                               reduction.  The kernel is launched cooperatively (all CTAs co-resident), keeps every
+//                               trajectory's y0/f0/k1..k7 in registers for the whole solve and replaces torchdiffeq's
+//                               per-attempt device->host sync (`if error_ratio <= 1`) by an in-kernel barrier.
+//   dopri5_backprop_bwd_kernel  reverse-mode through the accepted steps + dense-output interpolation,
+//                               dt sequence read from the device-side step log (no host round trip).
+#include "small_field.cuh"
+#include "launch.h"
+
+namespace gode {
+
+// dopri5.py tableau, built in fp64 and cast to fp32 exactly as torchdiffeq casts it to y0.dtype
+#define F32(x) ((float)(x))
+__device__ constexpr float kBeta[6][6] = {
+    {F32(1.0 / 5), 0, 0, 0, 0, 0},
+    {F32(3.0 / 40), F32(9.0 / 40), 0, 0, 0, 0},
+    {F32(44.0 / 45), F32(-56.0 / 15), F32(32.0 / 9), 0, 0, 0},
+    {F32(19372.0 / 6561), F32(-25360.0 / 2187), F32(64448.0 / 6561), F32(-212.0 / 729), 0, 0},
+    {F32(9017.0 / 3168), F32(-355.0 / 33), F32(46732.0 / 5247), F32(49.0 / 176), F32(-5103.0 / 18656), 0},
+    {F32(35.0 / 384), 0, F32(500.0 / 1113), F32(125.0 / 192), F32(-2187.0 / 6784), F32(11.0 / 84)}};
+__device__ constexpr float kCErr[7] = {F32(35.0 / 384 - 1951.0 / 21600),
+                                        0,
+                                        F32(500.0 / 1113 - 22642.0 / 50085),
+                                        F32(125.0 / 192 - 451.0 / 720),
+                                        F32(-2187.0 / 6784 - -12231.0 / 42400),
+                                        F32(11.0 / 84 - 649.0 / 6300),
+                                        F32(-1.0 / 60)};
+__device__ constexpr float kCMid[7] = {F32(6025192743.0 / 30085553152.0 / 2),
+                                        0,
+                                        F32(51252292925.0 / 65400821598.0 / 2),
+                                        F32(-2691868925.0 / 45128329728.0 / 2),
+                                        F32(187940372067.0 / 1594534317056.0 / 2),
+                                        F32(-1776094331.0 / 19743644256.0 / 2),
+                                        F32(11237099.0 / 235043384.0 / 2)};
+#undef F32
+
+constexpr int kMaxT = 256;  // output times passed by value
+
+struct Dp5Args {
+  const float *y0, *W1, *b1, *W2, *b2;
+  const float* grad_traj;
+  float* traj;
+  float* grad_y0;
+  float* grad_params;
+  ReduceWs ws;
+  GodeStepLog* log;
+  double* att_t0; double* att_dt; float* att_er; uint8_t* att_acc;
+  float* ckpt; double* acc_t0; double* acc_dt;
+  unsigned int* bar_counter;  // grid barrier, zeroed by the host wrapper
+  double* partials;           // [2][gridDim.x][4]
+  GodeAdaptiveOpts o;
+  int B, T, layout;
+  double t[kMaxT];
+};
+
+__device__ __forceinline__ size_t toff(int layout, int s, int b, int B, int T, int D) {
+  return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
+}
+
+// ---- grid-wide deterministic sum of NV doubles --------------------------------------------------------------
+// Every CTA publishes its partial, all CTAs meet at a monotone-counter barrier, then every warp re-reads all
+// partials and adds them in the same fixed order, so all threads of the grid hold bit-identical totals and the
+// accept/reject branch is uniform without a broadcast.
+template <int NV, int WARPS>
+__device__ __forceinline__ void grid_sum(double (&v)[NV], double* s_part /* [WARPS][NV] */, const Dp5Args& p,
+                                         unsigned int& epoch, int& parity, int lane, int warp, int tid) {
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_part[warp * NV + k] = v[k];
+  }
+  __syncthreads();
+  double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * 4;
+  if (tid == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      double s = s_part[k];
+      for (int w = 1; w < WARPS; ++w) s += s_part[w * NV + k];
+      __stcg(mine + k, s);
+    }
+    epoch += gridDim.x;
+    __threadfence();
+    atomicAdd(p.bar_counter, 1u);
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.bar_counter) : "memory");
+    } while ((int)(seen - epoch) < 0);
+  }
+  __syncthreads();
+  const double* all = p.partials + (size_t)parity * gridDim.x * 4;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    double s = 0.0;
+    for (int c = lane; c < (int)gridDim.x; c += 32) s += __ldcg(all + (size_t)c * 4 + k);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    v[k] = s;
+  }
+  parity ^= 1;
+}
+
+// misc.py::_optimal_step_size in fp64
+__device__ __forceinline__ double optimal_step(double dt, float er32, const GodeAdaptiveOpts& o) {
+  if (er32 == 0.f) return dt * o.ifactor;
+  const double dfactor = er32 < 1.f ? 1.0 : o.dfactor;
+  const double er = (double)er32;
+  const double factor = fmin(o.ifactor, fmax(o.safety / pow(er, 0.2), dfactor));
+  // torch.min/max propagate NaN; fmin/fmax do not
+  return (er != er) ? er : dt * factor;
+}
+
+// the (possibly time-reversed) field: out = fsign * f(u)
+template <int D, int H, int L, class Lines>
+__device__ __forceinline__ void field(const RowWeights<D, H, L>& w, const Lines& ln, int l, float fsign,
+                                      const float (&u)[Shape<D, H, L>::DL], float (&out)[Shape<D, H, L>::DL],
+                                      float (&hk)[Shape<D, H, L>::HL]) {
+  mlp_forward<D, H, L>(w, ln, l, u, out, hk);
+#pragma unroll
+  for (int c = 0; c < Shape<D, H, L>::DL; ++c) out[c] *= fsign;
+}
+
+template <int D, int H, int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_constant__ Dp5Args p) {
+  using S = Shape<D, H, L>;
+  __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
+  __shared__ double s_part[WARPS * 4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  FwdLines<D, H, L> ln;
+  ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
+  RowWeights<D, H, L> w;
+  w.load(p.W1, p.b1, p.W2, p.b2, l);
+  const int b = (blockIdx.x * WARPS + warp) * S::G + g;
+  const bool valid = b < p.B;
+  const bool logger = (blockIdx.x == 0 && tid == 0);
+  const double n_elem = (double)p.B * (double)D;
+  const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
+  unsigned int epoch = 0;
+  int parity = 0;
+
+  float y0[S::DL], k[7][S::DL], hk[S::HL];
+#pragma unroll
+  for (int c = 0; c < S::DL; ++c) y0[c] = 0.f;
+  if (valid) {
+    load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y0);
+    store_frag<S::DL>(p.traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y0);
+  }
+  field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], hk);  // f0
+  int nfe = 1, status = 0;
+  double t0 = p.t[0];
+  double dt;
+
+  // ---- misc.py::_select_initial_step (order = 4) -------------------------------------------------------------
+  {
+    float scale[S::DL];
+    double v[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) {
+      scale[c] = atol32 + fabsf(y0[c]) * rtol32;
+      const float r0 = y0[c] / scale[c], r1 = k[0][c] / scale[c];
+      if (valid) {
+        v[0] += (double)r0 * (double)r0;
+        v[1] += (double)r1 * (double)r1;
+        if (!isfinite(y0[c])) v[2] += 1.0;
+      }
+    }
+    grid_sum<3, WARPS>(v, s_part, p, epoch, parity, lane, warp, tid);
+    if (v[2] > 0.0) status |= GODE_ST_NONFINITE;
+    if (p.o.first_step > 0.0) {
+      dt = p.o.first_step;
+    } else {
+      const float d0 = (float)sqrt(v[0] / n_elem), d1 = (float)sqrt(v[1] / n_elem);
+      const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+      float u[S::DL], f1[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) u[c] = y0[c] + h0 * k[0][c];
+      field<D, H, L>(w, ln, l, p.o.fsign, u, f1, hk);
+      nfe++;
+      double v2[1] = {0.0};
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) {
+        const float r = (f1[c] - k[0][c]) / scale[c];
+        if (valid) v2[0] += (double)r * (double)r;
+      }
+      grid_sum<1, WARPS>(v2, s_part, p, epoch, parity, lane, warp, tid);
+      const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
+      float h1;
+      if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+      else h1 = powf(0.01f / fmaxf(d1, d2), 0.2f);
+      dt = (double)fminf(100.f * h0, h1);
+    }
+  }
+  if (logger) p.log->dt0 = dt;
+
+  // ---- solvers.py::AdaptiveStepsizeODESolver.integrate / rk_common.py::_adaptive_step ---------------------------
+  int iout = 1, n_att = 0, n_acc = 0, n_steps = 0;
+  while (iout < p.T && status == 0) {
+    if (n_steps >= p.o.max_num_steps) { status |= GODE_ST_MAX_STEPS; break; }
+    if (!(t0 + dt > t0)) { status |= GODE_ST_DT_UNDERFLOW; break; }
+    const double t1 = t0 + dt;
+    const float dt32 = (float)dt;
+    float u[S::DL];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) {
+        float s = k[0][c] * (kBeta[i][0] * dt32);
+#pragma unroll
+        for (int j = 1; j <= i; ++j) s = fmaf(k[j][c], kBeta[i][j] * dt32, s);
+        u[c] = y0[c] + s;
+      }
+      field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], hk);
+    }
+    nfe += 6;
+    // u is y1 (FSAL: c_sol == beta[5]), k[6] is f1
+    double v[1] = {0.0};
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) {
+      float e = k[0][c] * (dt32 * kCErr[0]);
+#pragma unroll
+      for (int j = 2; j < 7; ++j) e = fmaf(k[j][c], dt32 * kCErr[j], e);
+      const float tol = atol32 + rtol32 * fmaxf(fabsf(y0[c]), fabsf(u[c]));
+      const float r = e / tol;
+      if (valid) v[0] += (double)r * (double)r;
+    }
+    grid_sum<1, WARPS>(v, s_part, p, epoch, parity, lane, warp, tid);
+    const float er = (float)sqrt(v[0] / n_elem);
+    bool accept = er <= 1.f;
+    if (dt > p.o.max_step) accept = false;
+    if (dt <= p.o.min_step) accept = true;
+    if (logger && n_att < p.o.log_capacity) {
+      p.att_t0[n_att] = t0; p.att_dt[n_att] = dt; p.att_er[n_att] = er; p.att_acc[n_att] = accept ? 1 : 0;
+    }
+    if (accept) {
+      if (p.o.ckpt_capacity > 0) {
+        if (n_acc < p.o.ckpt_capacity) {
+          if (valid) store_frag<S::DL>(p.ckpt + ((size_t)n_acc * p.B + b) * D + l * S::DL, y0);
+          if (logger) { p.acc_t0[n_acc] = t0; p.acc_dt[n_acc] = dt; }
+        } else {
+          status |= GODE_ST_CKPT_OVERFLOW;
+        }
+      }
+      if (iout < p.T && p.t[iout] <= t1) {
+        // interp.py::_interp_fit (dense output), only when an output lands in this step
+        float ca[S::DL], cb[S::DL], cc[S::DL], cd[S::DL];
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) {
+          float m = k[0][c] * (dt32 * kCMid[0]);
+#pragma unroll
+          for (int j = 2; j < 7; ++j) m = fmaf(k[j][c], dt32 * kCMid[j], m);
+          const float ymid = y0[c] + m, f0 = k[0][c], f1 = k[6][c], y1 = u[c];
+          ca[c] = 2.f * dt32 * (f1 - f0) - 8.f * (y1 + y0[c]) + 16.f * ymid;
+          cb[c] = dt32 * (5.f * f0 - 3.f * f1) + 18.f * y0[c] + 14.f * y1 - 32.f * ymid;
+          cc[c] = dt32 * (f1 - 4.f * f0) - 11.f * y0[c] - 5.f * y1 + 16.f * ymid;
+          cd[c] = dt32 * f0;
+        }
+        while (iout < p.T && p.t[iout] <= t1) {
+          const float x = (float)((p.t[iout] - t0) / (t1 - t0));
+          float o[S::DL];
+#pragma unroll
+          for (int c = 0; c < S::DL; ++c) {
+            float tot = y0[c] + x * cd[c];
+            float xp = x * x;
+            tot = tot + xp * cc[c];
+            xp = xp * x;
+            tot = tot + xp * cb[c];
+            xp = xp * x;
+            tot = tot + xp * ca[c];
+            o[c] = tot;
+          }
+          if (valid) store_frag<S::DL>(p.traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, o);
+          ++iout;
+          n_steps = -1;  // max_num_steps is counted per output interval (per _advance call)
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { y0[c] = u[c]; k[0][c] = k[6][c]; }
+      t0 = t1;
+      ++n_acc;
+    }
+    dt = optimal_step(dt, er, p.o);
+    dt = fmin(fmax(dt, p.o.min_step), p.o.max_step);
+    ++n_att;
+    ++n_steps;
+  }
+  if (logger) {
+    p.log->status = status;
+    p.log->n_attempts = n_att;
+    p.log->n_accepted = n_acc;
+    p.log->nfe = nfe;
+    p.log->t_final = t0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int D, int H, int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const __grid_constant__ Dp5Args p) {
+  using S = Shape<D, H, L>;
+  using BL = BwdLines<D, H, L>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_lines = smem;
+  float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;
+  float* s_red = s_cw + ColWeights<D, H, L>::kFloats;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  BL ln;
+  ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
+  ColWeights<D, H, L> cw;
+  cw.bind(s_cw);
+  cw.stage(p.W1, p.W2, tid, WARPS * 32);
+  RowWeights<D, H, L> w;
+  w.load(p.W1, p.b1, p.W2, p.b2, l);
+  GradAcc<D, H, L> acc;
+  acc.zero();
+  __syncthreads();
+  const int n_acc = min(p.log->n_accepted, p.o.ckpt_capacity);
+  const int stride = gridDim.x * WARPS * S::G;
+  for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
+    const int b = base + g;
+    const bool valid = b < p.B;
+    const float sc = valid ? 1.f : 0.f;
+    float ybar[S::DL], fbar[S::DL];  // cotangents of the next step's (y0, f0) == this step's (y1, f1)
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) { ybar[c] = 0.f; fbar[c] = 0.f; }
+    int iout = p.T - 1;
+    for (int s = n_acc - 1; s >= 0; --s) {
+      const double t0 = p.acc_t0[s], dtd = p.acc_dt[s], t1 = t0 + dtd;
+      const float dt32 = (float)dtd;
+      float y0[S::DL], k[7][S::DL], h[7][S::HL], u[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) y0[c] = 0.f;
+      if (valid) load_frag<S::DL>(p.ckpt + ((size_t)s * p.B + b) * D + l * S::DL, y0);
+      // recompute the step exactly as the forward did
+      field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], h[0]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) {
+          float sum = k[0][c] * (kBeta[i][0] * dt32);
+#pragma unroll
+          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], kBeta[i][j] * dt32, sum);
+          u[c] = y0[c] + sum;
+        }
+        field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], h[i + 1]);
+      }
+      // cotangents of the interpolation inputs (y0, y1, ymid, f0, f1) from every output inside (t0, t1]
+      float y0b[S::DL], ymb[S::DL], f0b[S::DL], kb[7][S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { y0b[c] = 0.f; ymb[c] = 0.f; f0b[c] = 0.f; }
+      while (iout >= 1 && p.t[iout] > t0) {
+        float gout[S::DL];
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) gout[c] = 0.f;
+        if (valid) load_frag<S::DL>(p.grad_traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, gout);
+        const float x = (float)((p.t[iout] - t0) / (t1 - t0));
+        const float p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+        const float cy0 = 1.f - 11.f * p2 + 18.f * p3 - 8.f * p4;
+        const float cy1 = -5.f * p2 + 14.f * p3 - 8.f * p4;
+        const float cym = 16.f * p2 - 32.f * p3 + 16.f * p4;
+        const float cf0 = dt32 * (x - 4.f * p2 + 5.f * p3 - 2.f * p4);
+        const float cf1 = dt32 * (p2 - 3.f * p3 + 2.f * p4);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) {
+          y0b[c] = fmaf(cy0, gout[c], y0b[c]);
+          ybar[c] = fmaf(cy1, gout[c], ybar[c]);
+          ymb[c] = fmaf(cym, gout[c], ymb[c]);
+          f0b[c] = fmaf(cf0, gout[c], f0b[c]);
+          fbar[c] = fmaf(cf1, gout[c], fbar[c]);
+        }
+        --iout;
+      }
+      // ymid = y0 + sum_j k_j dt cmid_j ; f1 = k7 ; f0 = k1
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) {
+        y0b[c] += ymb[c];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kb[j][c] = (dt32 * kCMid[j]) * ymb[c];
+        kb[6][c] += fbar[c];
+        kb[0][c] += f0b[c];
+      }
+      // stage 7: k7 = f(u7), u7 == y1 (lines still hold u7 / h7 from the recompute)
+      // k_j = fsign * f(u_j): the cotangent reaching f is fsign * kb_j
+      float ub[S::DL], cot[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) cot[c] = p.o.fsign * kb[6][c];
+      mlp_vjp<D, H, L>(cw, ln, l, h[6], cot, sc, ub, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) {
+        ub[c] += ybar[c];
+        y0b[c] += ub[c];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) kb[j][c] = fmaf(kBeta[5][j] * dt32, ub[c], kb[j][c]);
+      }
+      // stages 6..2
+#pragma unroll
+      for (int i = 4; i >= 0; --i) {
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) {
+          float sum = k[0][c] * (kBeta[i][0] * dt32);
+#pragma unroll
+          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], kBeta[i][j] * dt32, sum);
+          u[c] = y0[c] + sum;
+        }
+        regather<D, H, L>(ln, l, u, h[i + 1]);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) cot[c] = p.o.fsign * kb[i + 1][c];
+        mlp_vjp<D, H, L>(cw, ln, l, h[i + 1], cot, sc, ub, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) {
+          y0b[c] += ub[c];
+#pragma unroll
+          for (int j = 0; j <= i; ++j) kb[j][c] = fmaf(kBeta[i][j] * dt32, ub[c], kb[j][c]);
+        }
+      }
+      if (s > 0) {
+        // FSAL: k1 of this step IS f1 of the previous step (same autograd node) -> hand its cotangent back
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) { ybar[c] = y0b[c]; fbar[c] = kb[0][c]; }
+      } else {
+        regather<D, H, L>(ln, l, y0, h[0]);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) cot[c] = p.o.fsign * kb[0][c];
+        mlp_vjp<D, H, L>(cw, ln, l, h[0], cot, sc, ub, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) ybar[c] = y0b[c] + ub[c];
+      }
+    }
+    float g0[S::DL];
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) g0[c] = 0.f;
+    if (valid) {
+      load_frag<S::DL>(p.grad_traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, g0);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) g0[c] += ybar[c];
+      store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
+    }
+  }
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kDp5Warps = 4;
+
+static size_t dp5_partials_bytes(int grid) { return sizeof(double) * 2 * 4 * (size_t)grid; }
+
+template <int D, int H, int L>
+static int dp5_fwd_grid(int B) {
+  const int per_cta = kDp5Warps * Shape<D, H, L>::G;
+  return (B + per_cta - 1) / per_cta;
+}
+
+size_t dopri5_small_workspace_bytes(int B, int D, int H) {
+  (void)D; (void)H;
+  // barrier counter (256 B) + double-buffered per-CTA partials; sized for the L=8 mapping (the densest we launch)
+  const int grid = dp5_fwd_grid<16, 16, 8>(B);
+  return 256 + dp5_partials_bytes(grid);
+}
+
+template <int D, int H, int L>
+static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  const int grid = dp5_fwd_grid<D, H, L>(a.B);
+  if (ws_bytes < 256 + dp5_partials_bytes(grid)) return GODE_ERR_WORKSPACE;
+  auto kern = dopri5_fwd_kernel<D, H, L, kDp5Warps>;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDp5Warps * 32, 0);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  if (grid > per_sm * sm_count()) return GODE_ERR_COOP;
+  a.bar_counter = reinterpret_cast<unsigned int*>(workspace);
+  a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+  e = cudaMemsetAsync(workspace, 0, 256, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  void* args[] = {(void*)&a};
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDp5Warps * 32), args, 0, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  return launch_status();
+}
+
+template <int D, int H, int L>
+static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  using S = Shape<D, H, L>;
+  constexpr int WARPS = 4;
+  const int per_cta = WARPS * S::G;
+  int grid = (a.B + per_cta - 1) / per_cta;
+  const int cap = bwd_grid_cap();
+  if (grid > cap) grid = cap;
+  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
+  a.ws.counter = reinterpret_cast<unsigned int*>(workspace);
+  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P);
+  auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS>;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(1000 + (int)e);
+  }
+  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  return launch_status();
+}
+
+int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                     const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                     float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
+                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
+  Dp5Args a{};
+  a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.log = log;
+  a.att_t0 = att_t0; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
+  a.ckpt = ckpt; a.acc_t0 = acc_t0; a.acc_dt = acc_dt;
+  a.o = *opts; a.B = B; a.T = T; a.layout = out_layout;
+  for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
+  if (D == 16 && H == 16) return launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
+  return GODE_ERR_SHAPE;
+}
+
+int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                              const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                              const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                              int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                              size_t ws_bytes, cudaStream_t st) {
+  if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
+  Dp5Args a{};
+  a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.grad_traj = grad_traj; a.log = const_cast<GodeStepLog*>(log);
+  a.ckpt = const_cast<float*>(ckpt); a.acc_t0 = const_cast<double*>(acc_t0); a.acc_dt = const_cast<double*>(acc_dt);
+  a.o.ckpt_capacity = ckpt_capacity; a.o.fsign = fsign; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+  a.B = B; a.T = T; a.layout = layout;
+  for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
+  if (D == 16 && H == 16) return launch_dp5_bwd<16, 16, 8>(a, workspace, ws_bytes, st);
+  return GODE_ERR_SHAPE;
+}
+
+}  // namespace gode

@@ -1,0 +1,54 @@
+// launch.h — host-side helpers shared by the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include "../../include/gode.h"
+
+namespace gode {
+
+// Device properties are queried per call (cached per device id in a small immutable table; no mutable
+// global state that a second thread could observe half-written: entries are written once with the same value).
+inline int sm_count() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int cached[64] = {0};
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
+inline int launch_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? GODE_OK : -(1000 + (int)e);
+}
+
+// backward kernels keep parameter-gradient accumulators in registers and loop over their trajectories;
+// two 128-thread CTAs per SM.
+inline int bwd_grid_cap() { return sm_count() * 2; }
+
+inline size_t bwd_workspace_bytes(int P) { return 256 + sizeof(float) * (size_t)P * (size_t)bwd_grid_cap(); }
+
+// entry points of the per-family translation units
+int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st);
+int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                  const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+
+size_t dopri5_small_workspace_bytes(int B, int D, int H);
+int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                     const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                     float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
+                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st);
+int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                              const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                              const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                              int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                              size_t ws_bytes, cudaStream_t st);
+
+inline bool small_field_shape(int D, int H) { return D == 16 && H == 16; }
+
+}  // namespace gode

@@ -1,0 +1,298 @@
+// rk4_small.cu — fixed-grid RK4 (3/8 rule) for the small-field shapes, FP32.
+//   rk4_fwd_kernel          torchdiffeq FixedGridODESolver.integrate + rk4_alt_step_func        
+//   rk4_adjoint_bwd_kernel  torchdiffeq OdeintAdjointMethod.backward with method='rk4'          
+//   rk4_backprop_bwd_kernel autograd through the same forward (discretise-then-optimise)        
+// One launch per call: every trajectory's whole time loop runs inside the kernel.
+#include "small_field.cuh"
+#include "launch.h"
+
+namespace gode {
+
+constexpr float kOneThird = 0.33333334f;  // float(1/3): torchdiffeq multiplies fp32 tensors by the Python double 1/3
+
+struct Rk4Args {
+  const float *y0, *W1, *b1, *W2, *b2;
+  const float* traj_in;     // bwd: stored forward trajectory
+  const float* grad_traj;   // bwd: upstream gradient, same layout as traj
+  float* traj;              // fwd output
+  float* grad_y0;           // bwd output (B,D)
+  float* grad_params;       // bwd output flat [W1|b1|W2|b2]
+  ReduceWs ws;
+  const float* dt_dev;      // device dt table, or nullptr -> dt_val
+  int B, T, layout;
+  float dt_val[GODE_MAX_HOST_STEPS];
+};
+
+__device__ __forceinline__ size_t traj_off(int layout, int s, int b, int B, int T, int D) {
+  return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+template <int D, int H, int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_constant__ Rk4Args p) {
+  using S = Shape<D, H, L>;
+  __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / L, l = lane % L;
+  FwdLines<D, H, L> ln;
+  ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
+  RowWeights<D, H, L> w;
+  w.load(p.W1, p.b1, p.W2, p.b2, l);
+  const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
+  const int stride = gridDim.x * WARPS * S::G;
+  for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
+    const int b = base + g;
+    const bool valid = b < p.B;
+    float y[S::DL];
+    if (valid) load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y);
+    else {
+#pragma unroll
+      for (int i = 0; i < S::DL; ++i) y[i] = 0.f;
+    }
+    if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y);
+    for (int s = 0; s + 1 < p.T; ++s) {
+      const float dt = dtp[s];
+      float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u[S::DL], hk[S::HL];
+      mlp_forward<D, H, L>(w, ln, l, y, k1, hk);
+#pragma unroll
+      for (int i = 0; i < S::DL; ++i) u[i] = y[i] + dt * k1[i] * kOneThird;
+      mlp_forward<D, H, L>(w, ln, l, u, k2, hk);
+#pragma unroll
+      for (int i = 0; i < S::DL; ++i) u[i] = y[i] + dt * (k2[i] - k1[i] * kOneThird);
+      mlp_forward<D, H, L>(w, ln, l, u, k3, hk);
+#pragma unroll
+      for (int i = 0; i < S::DL; ++i) u[i] = y[i] + dt * (k1[i] - k2[i] + k3[i]);
+      mlp_forward<D, H, L>(w, ln, l, u, k4, hk);
+#pragma unroll
+      for (int i = 0; i < S::DL; ++i) y[i] = y[i] + (k1[i] + 3.f * (k2[i] + k3[i]) + k4[i]) * dt * 0.125f;
+      if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Continuous adjoint, one 3/8-rule step of the augmented system (y, a, theta_bar) per output interval, in
+// reversed time: dy/ds = -f, da/ds = +a^T df/dy, dtheta_bar/ds = +a^T df/dtheta.  y is reset to the stored forward
+// value at the start of every interval and grad_traj[i-1] is added to a at its end, exactly as adjoint.py does.
+// theta_bar is linear in the stage contributions, so each lane keeps its rows of theta_bar in registers across ALL
+// intervals and ALL its trajectories and the grid reduces once at the end.
+template <int D, int H, int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __grid_constant__ Rk4Args p) {
+  using S = Shape<D, H, L>;
+  using BL = BwdLines<D, H, L>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_lines = smem;                                          // WARPS * BL::kFloatsPerWarp
+  float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;             // ColWeights::kFloats
+  float* s_red = s_cw + ColWeights<D, H, L>::kFloats;             // WARPS * P
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  BL ln;
+  ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
+  ColWeights<D, H, L> cw;
+  cw.bind(s_cw);
+  cw.stage(p.W1, p.W2, tid, WARPS * 32);
+  RowWeights<D, H, L> w;
+  w.load(p.W1, p.b1, p.W2, p.b2, l);
+  GradAcc<D, H, L> acc;
+  acc.zero();
+  __syncthreads();
+  const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
+  const int stride = gridDim.x * WARPS * S::G;
+  for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
+    const int b = base + g;
+    const bool valid = b < p.B;
+    float a[S::DL];
+#pragma unroll
+    for (int i = 0; i < S::DL; ++i) a[i] = 0.f;
+    if (valid) load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, a);
+    for (int i = p.T - 1; i >= 1; --i) {
+      const float dt = dtp[i - 1];
+      float y[S::DL], gprev[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { y[c] = 0.f; gprev[c] = 0.f; }
+      if (valid) {
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i, b, p.B, p.T, D) + l * S::DL, y);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 1, b, p.B, p.T, D) + l * S::DL, gprev);
+      }
+      const float c18 = dt * 0.125f, c38 = 3.f * c18;
+      const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
+      float f[S::DL], v[S::DL], hk[S::HL], uy[S::DL], ua[S::DL];
+      float k1y[S::DL], k1a[S::DL], k2y[S::DL], k2a[S::DL], k3y[S::DL], k3a[S::DL];
+      // stage 1
+      mlp_forward<D, H, L>(w, ln, l, y, f, hk);
+      mlp_vjp<D, H, L>(cw, ln, l, hk, a, sc * c18, v, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { k1y[c] = -f[c]; k1a[c] = v[c]; uy[c] = y[c] + dt * k1y[c] * kOneThird; ua[c] = a[c] + dt * k1a[c] * kOneThird; }
+      // stage 2
+      mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
+      mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * c38, v, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { k2y[c] = -f[c]; k2a[c] = v[c]; uy[c] = y[c] + dt * (k2y[c] - k1y[c] * kOneThird); ua[c] = a[c] + dt * (k2a[c] - k1a[c] * kOneThird); }
+      // stage 3
+      mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
+      mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * c38, v, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { k3y[c] = -f[c]; k3a[c] = v[c]; uy[c] = y[c] + dt * (k1y[c] - k2y[c] + k3y[c]); ua[c] = a[c] + dt * (k1a[c] - k2a[c] + k3a[c]); }
+      // stage 4
+      mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
+      mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * c18, v, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) a[c] = a[c] + (k1a[c] + 3.f * (k2a[c] + k3a[c]) + v[c]) * dt * 0.125f + gprev[c];
+    }
+    if (valid) store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, a);
+  }
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Exact reverse-mode through the forward's arithmetic.  Per step the four stage inputs u_s and tanh vectors are
+// recomputed from the stored y_s (bit-identical to the forward), then the stages are walked 4..1.
+template <int D, int H, int L, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __grid_constant__ Rk4Args p) {
+  using S = Shape<D, H, L>;
+  using BL = BwdLines<D, H, L>;
+  extern __shared__ __align__(16) float smem[];
+  float* s_lines = smem;
+  float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;
+  float* s_red = s_cw + ColWeights<D, H, L>::kFloats;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  BL ln;
+  ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
+  ColWeights<D, H, L> cw;
+  cw.bind(s_cw);
+  cw.stage(p.W1, p.W2, tid, WARPS * 32);
+  RowWeights<D, H, L> w;
+  w.load(p.W1, p.b1, p.W2, p.b2, l);
+  GradAcc<D, H, L> acc;
+  acc.zero();
+  __syncthreads();
+  const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
+  const int stride = gridDim.x * WARPS * S::G;
+  for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
+    const int b = base + g;
+    const bool valid = b < p.B;
+    const float sc = valid ? 1.f : 0.f;
+    float yb[S::DL];  // cotangent of y_{s+1}
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) yb[c] = 0.f;
+    if (valid) load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yb);
+    for (int s = p.T - 2; s >= 0; --s) {
+      const float dt = dtp[s];
+      float y[S::DL], gs[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { y[c] = 0.f; gs[c] = 0.f; }
+      if (valid) {
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, s, b, p.B, p.T, D) + l * S::DL, y);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, s, b, p.B, p.T, D) + l * S::DL, gs);
+      }
+      // recompute (same expressions as the forward kernel)
+      float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u2[S::DL], u3[S::DL], u4[S::DL];
+      float h1[S::HL], h2[S::HL], h3[S::HL], h4[S::HL];
+      mlp_forward<D, H, L>(w, ln, l, y, k1, h1);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) u2[c] = y[c] + dt * k1[c] * kOneThird;
+      mlp_forward<D, H, L>(w, ln, l, u2, k2, h2);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) u3[c] = y[c] + dt * (k2[c] - k1[c] * kOneThird);
+      mlp_forward<D, H, L>(w, ln, l, u3, k3, h3);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) u4[c] = y[c] + dt * (k1[c] - k2[c] + k3[c]);
+      mlp_forward<D, H, L>(w, ln, l, u4, k4, h4);  // leaves u4 / h4 in the lines
+      // reverse
+      const float c18 = dt * 0.125f, c38 = 3.f * c18, dt3 = dt * kOneThird;
+      float kb1[S::DL], kb2[S::DL], kb3[S::DL], kb4[S::DL], ub[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { kb1[c] = c18 * yb[c]; kb2[c] = c38 * yb[c]; kb3[c] = c38 * yb[c]; kb4[c] = c18 * yb[c]; }
+      mlp_vjp<D, H, L>(cw, ln, l, h4, kb4, sc, ub, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { yb[c] += ub[c]; kb1[c] += dt * ub[c]; kb2[c] -= dt * ub[c]; kb3[c] += dt * ub[c]; }
+      regather<D, H, L>(ln, l, u3, h3);
+      mlp_vjp<D, H, L>(cw, ln, l, h3, kb3, sc, ub, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { yb[c] += ub[c]; kb2[c] += dt * ub[c]; kb1[c] -= dt3 * ub[c]; }
+      regather<D, H, L>(ln, l, u2, h2);
+      mlp_vjp<D, H, L>(cw, ln, l, h2, kb2, sc, ub, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { yb[c] += ub[c]; kb1[c] += dt3 * ub[c]; }
+      regather<D, H, L>(ln, l, y, h1);
+      mlp_vjp<D, H, L>(cw, ln, l, h1, kb1, sc, ub, acc);
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) yb[c] += ub[c] + gs[c];
+      (void)k4;
+    }
+    if (valid) store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, yb);
+  }
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+template <int D, int H, int L, int WARPS>
+static size_t bwd_smem_bytes() {
+  return sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * Shape<D, H, L>::P);
+}
+
+static int fill_dt(Rk4Args& a, const float* dt, int dt_on_device, int T) {
+  if (dt_on_device) { a.dt_dev = dt; return GODE_OK; }
+  if (T - 1 > GODE_MAX_HOST_STEPS) return GODE_ERR_T_TOO_LONG;
+  a.dt_dev = nullptr;
+  for (int i = 0; i < T - 1; ++i) a.dt_val[i] = dt[i];
+  return GODE_OK;
+}
+
+template <int D, int H, int L>
+static int launch_rk4_fwd(Rk4Args& a, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  using S = Shape<D, H, L>;
+  const int per_cta = WARPS * S::G;
+  int grid = (a.B + per_cta - 1) / per_cta;
+  const int cap = sm_count() * 16;  // 16 CTAs of 128 threads fill an SM; beyond that, loop
+  if (grid > cap) grid = cap;
+  rk4_fwd_kernel<D, H, L, WARPS><<<grid, WARPS * 32, 0, st>>>(a);
+  return launch_status();
+}
+
+template <int D, int H, int L, bool ADJOINT>
+static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  constexpr int WARPS = 4;
+  using S = Shape<D, H, L>;
+  const int per_cta = WARPS * S::G;
+  int grid = (a.B + per_cta - 1) / per_cta;
+  const int cap = bwd_grid_cap();
+  if (grid > cap) grid = cap;
+  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
+  a.ws.counter = reinterpret_cast<unsigned int*>(workspace);
+  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  const size_t smem = bwd_smem_bytes<D, H, L, WARPS>();
+  auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS> : rk4_backprop_bwd_kernel<D, H, L, WARPS>;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return -(1000 + (int)e);
+  }
+  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  return launch_status();
+}
+
+int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st) {
+  Rk4Args a{};
+  a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.B = B; a.T = T; a.layout = out_layout;
+  if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
+  if (D == 16 && H == 16) return launch_rk4_fwd<16, 16, 8>(a, st);
+  return GODE_ERR_SHAPE;
+}
+
+int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                  const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  Rk4Args a{};
+  a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj_in = traj; a.grad_traj = grad_traj; a.grad_y0 = grad_y0;
+  a.grad_params = grad_params; a.B = B; a.T = T; a.layout = layout;
+  if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
+  if (D == 16 && H == 16)
+    return adjoint ? launch_rk4_bwd<16, 16, 8, true>(a, workspace, ws_bytes, st)
+                   : launch_rk4_bwd<16, 16, 8, false>(a, workspace, ws_bytes, st);
+  return GODE_ERR_SHAPE;
+}
+
+}  // namespace gode

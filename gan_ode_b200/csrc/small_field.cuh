@@ -1,0 +1,354 @@
+// small_field.cuh — "small-field" FP32 device code shared by the rk4 / dopri5 / ODE-RNN / SDE kernels.
+//
+// The reference's vector field is ODEFunc (models/mocogan_ode.py:6-17): f(x) = W2 tanh(W1 x + b1) + b2 with
+// D = H = 16 in every shipped script (mnist_moco_ode.py:78, ucf_moco_ode.py:80 ...).  At that size one
+// trajectory is far too little work for a thread block and too much latency for one thread, so a trajectory
+// is split over L lanes of a warp ("lane-split"): lane l owns D/L state components and H/L hidden units,
+// keeps its rows of W1/W2 in REGISTERS for the whole kernel (no weight traffic at all after the prologue),
+// and the two all-gathers per MLP evaluation (state -> all lanes, hidden -> all lanes) go through a
+// per-warp padded shared-memory line (1 STS + D/4 broadcast LDS.128, bank-conflict free) with __syncwarp only.
+// All Runge–Kutta algebra, error norms and adjoint accumulators stay in registers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gode {
+
+constexpr int kPad = 4;  // floats of padding per gather row: stride D+4 keeps float4 alignment and spreads banks
+
+template <int D, int H, int L>
+struct Shape {
+  static_assert(L >= 1 && L <= 32 && (32 % L) == 0, "L must divide the warp");
+  static_assert(D % L == 0 && H % L == 0, "D and H must split evenly over L lanes");
+  static_assert(D % 4 == 0 && H % 4 == 0, "D and H must be multiples of 4 (float4 gathers)");
+  static constexpr int DL = D / L;   // state components per lane (contiguous: d = l*DL + dl)
+  static constexpr int HL = H / L;   // hidden units per lane      (contiguous: j = l*HL + jl)
+  static constexpr int G = 32 / L;   // trajectories per warp
+  static constexpr int YS = D + kPad;
+  static constexpr int HS = H + kPad;
+  static constexpr int P = H * D + H + D * H + D;  // flat [W1|b1|W2|b2]
+};
+
+// ---- fragment <-> memory ---------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void load_frag(const float* __restrict__ p, float (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) {
+      float4 q = *reinterpret_cast<const float4*>(p + i);
+      v[i] = q.x; v[i + 1] = q.y; v[i + 2] = q.z; v[i + 3] = q.w;
+    }
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      float2 q = *reinterpret_cast<const float2*>(p + i);
+      v[i] = q.x; v[i + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = p[i];
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void store_frag(float* __restrict__ p, const float (&v)[N]) {
+  if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(v[i], v[i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = v[i];
+  }
+}
+
+// ---- weights ---------------------------------------------------------------------------------------------
+// Row-owned weights in registers: W1 rows of the lane's hidden units, W2 rows of the lane's state components.
+template <int D, int H, int L>
+struct RowWeights {
+  using S = Shape<D, H, L>;
+  float w1[S::HL][D];
+  float b1[S::HL];
+  float w2[S::DL][H];
+  float b2[S::DL];
+
+  __device__ __forceinline__ void load(const float* __restrict__ W1, const float* __restrict__ B1,
+                                       const float* __restrict__ W2, const float* __restrict__ B2, int l) {
+#pragma unroll
+    for (int jl = 0; jl < S::HL; ++jl) {
+      const int j = l * S::HL + jl;
+      load_frag<D>(W1 + (size_t)j * D, w1[jl]);
+      b1[jl] = B1[j];
+    }
+#pragma unroll
+    for (int dl = 0; dl < S::DL; ++dl) {
+      const int d = l * S::DL + dl;
+      load_frag<H>(W2 + (size_t)d * H, w2[dl]);
+      b2[dl] = B2[d];
+    }
+  }
+};
+
+// Column-owned weights for the VJP, in shared memory (one copy per CTA):
+//   w2t: column j of W2 (length D) for the lane's hidden units   g_h[j]   = sum_d a[d]     W2[d][j]
+//   w1t: column i of W1 (length H) for the lane's components     vjp_y[i] = sum_j delta[j] W1[j][i]
+// Physical row order is (jl*L + l) so that the L lanes of a trajectory read consecutive padded rows
+// (stride D+4 / H+4 floats -> conflict-free LDS.128), while lanes of other trajectories broadcast.
+template <int D, int H, int L>
+struct ColWeights {
+  using S = Shape<D, H, L>;
+  static constexpr int kFloats = H * S::YS + D * S::HS;
+  float* w2t;  // [H][YS]
+  float* w1t;  // [D][HS]
+
+  __device__ __forceinline__ void bind(float* smem) { w2t = smem; w1t = smem + H * S::YS; }
+  __device__ __forceinline__ static int row_h(int j) { return (j % S::HL) * L + j / S::HL; }
+  __device__ __forceinline__ static int row_d(int d) { return (d % S::DL) * L + d / S::DL; }
+
+  // all threads of the CTA cooperate; caller must __syncthreads() afterwards
+  __device__ __forceinline__ void stage(const float* __restrict__ W1, const float* __restrict__ W2, int tid, int nthreads) {
+    for (int e = tid; e < D * H; e += nthreads) {
+      { const int d = e / H, j = e % H; w2t[row_h(j) * S::YS + d] = W2[e]; }   // W2[d][j]
+      { const int j = e / D, i = e % D; w1t[row_d(i) * S::HS + j] = W1[e]; }   // W1[j][i]
+    }
+  }
+};
+
+// ---- per-warp gather lines --------------------------------------------------------------------------------
+template <int D, int H, int L>
+struct FwdLines {   // what mlp_forward needs
+  using S = Shape<D, H, L>;
+  static constexpr int kFloatsPerWarp = S::G * (S::YS + S::HS);
+  float* y;  // this trajectory's padded line of D floats
+  float* h;  // this trajectory's padded line of H floats
+  __device__ __forceinline__ void bind(float* warp_base, int g) {
+    y = warp_base + g * S::YS;
+    h = warp_base + S::G * S::YS + g * S::HS;
+  }
+};
+
+template <int D, int H, int L>
+struct BwdLines {   // mlp_forward + VJP
+  using S = Shape<D, H, L>;
+  static constexpr int kFloatsPerWarp = 2 * S::G * (S::YS + S::HS);
+  float *y, *h, *a, *dl;
+  __device__ __forceinline__ void bind(float* warp_base, int g) {
+    y = warp_base + g * S::YS;
+    h = warp_base + S::G * S::YS + g * S::HS;
+    a = warp_base + S::G * (S::YS + S::HS) + g * S::YS;
+    dl = warp_base + S::G * (2 * S::YS + S::HS) + g * S::HS;
+  }
+};
+
+// dot of a register row with a padded shared line, two partial sums for ILP
+template <int N>
+__device__ __forceinline__ float dot_line(const float (&w)[N], const float* __restrict__ line, float init) {
+  float s0 = init, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(line + i);
+    s0 = fmaf(w[i], v.x, s0); s0 = fmaf(w[i + 1], v.y, s0); s0 = fmaf(w[i + 2], v.z, s0); s0 = fmaf(w[i + 3], v.w, s0);
+    if (i + 4 < N) {
+      const float4 u = *reinterpret_cast<const float4*>(line + i + 4);
+      s1 = fmaf(w[i + 4], u.x, s1); s1 = fmaf(w[i + 5], u.y, s1); s1 = fmaf(w[i + 6], u.z, s1); s1 = fmaf(w[i + 7], u.w, s1);
+    }
+  }
+  return s0 + s1;
+}
+
+// dot of a shared weight row with a shared line (both padded, float4)
+template <int N>
+__device__ __forceinline__ float dot_smem(const float* __restrict__ wrow, const float* __restrict__ line) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; i += 8) {
+    const float4 w = *reinterpret_cast<const float4*>(wrow + i);
+    const float4 v = *reinterpret_cast<const float4*>(line + i);
+    s0 = fmaf(w.x, v.x, s0); s0 = fmaf(w.y, v.y, s0); s0 = fmaf(w.z, v.z, s0); s0 = fmaf(w.w, v.w, s0);
+    if (i + 4 < N) {
+      const float4 w2 = *reinterpret_cast<const float4*>(wrow + i + 4);
+      const float4 v2 = *reinterpret_cast<const float4*>(line + i + 4);
+      s1 = fmaf(w2.x, v2.x, s1); s1 = fmaf(w2.y, v2.y, s1); s1 = fmaf(w2.z, v2.z, s1); s1 = fmaf(w2.w, v2.w, s1);
+    }
+  }
+  return s0 + s1;
+}
+
+// ---- the vector field --------------------------------------------------------------------------------------
+// out = W2 tanh(W1 u + b1) + b2 for the lane's components; hk receives the lane's tanh activations.
+// Leaves the full u in lines.y and the full tanh vector in lines.h.
+template <int D, int H, int L, class Lines>
+__device__ __forceinline__ void mlp_forward(const RowWeights<D, H, L>& w, const Lines& ln, int l,
+                                            const float (&u)[Shape<D, H, L>::DL], float (&out)[Shape<D, H, L>::DL],
+                                            float (&hk)[Shape<D, H, L>::HL]) {
+  using S = Shape<D, H, L>;
+  store_frag<S::DL>(ln.y + l * S::DL, u);
+  __syncwarp();
+#pragma unroll
+  for (int jl = 0; jl < S::HL; ++jl) hk[jl] = tanhf(dot_line<D>(w.w1[jl], ln.y, w.b1[jl]));
+  store_frag<S::HL>(ln.h + l * S::HL, hk);
+  __syncwarp();
+#pragma unroll
+  for (int dl = 0; dl < S::DL; ++dl) out[dl] = dot_line<H>(w.w2[dl], ln.h, w.b2[dl]);
+}
+
+// ---- parameter-gradient accumulators (registers, row-owned like RowWeights) ------------------------------------
+template <int D, int H, int L>
+struct GradAcc {
+  using S = Shape<D, H, L>;
+  float w1[S::HL][D];
+  float b1[S::HL];
+  float w2[S::DL][H];
+  float b2[S::DL];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int jl = 0; jl < S::HL; ++jl) {
+      b1[jl] = 0.f;
+#pragma unroll
+      for (int i = 0; i < D; ++i) w1[jl][i] = 0.f;
+    }
+#pragma unroll
+    for (int dl = 0; dl < S::DL; ++dl) {
+      b2[dl] = 0.f;
+#pragma unroll
+      for (int j = 0; j < H; ++j) w2[dl][j] = 0.f;
+    }
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void axpy_line(float (&acc)[N], float s, const float* __restrict__ line) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(line + i);
+    acc[i] = fmaf(s, v.x, acc[i]); acc[i + 1] = fmaf(s, v.y, acc[i + 1]);
+    acc[i + 2] = fmaf(s, v.z, acc[i + 2]); acc[i + 3] = fmaf(s, v.w, acc[i + 3]);
+  }
+}
+
+// VJP of the field at a point whose full input is in lines.y and full tanh vector in lines.h
+// (i.e. right after mlp_forward, or after regather()).  `a` is the lane's slice of the cotangent on f's output.
+//   vjp[i]   = sum_j delta[j] W1[j][i],  delta = (a W2) ⊙ (1 - h^2)
+//   acc     += scale * (dW1 = delta^T u, db1 = delta, dW2 = a^T h, db2 = a)
+template <int D, int H, int L>
+__device__ __forceinline__ void mlp_vjp(const ColWeights<D, H, L>& cw, const BwdLines<D, H, L>& ln, int l,
+                                        const float (&hk)[Shape<D, H, L>::HL], const float (&a)[Shape<D, H, L>::DL],
+                                        float scale, float (&vjp)[Shape<D, H, L>::DL], GradAcc<D, H, L>& acc) {
+  using S = Shape<D, H, L>;
+  store_frag<S::DL>(ln.a + l * S::DL, a);
+  __syncwarp();
+  float delta[S::HL];
+#pragma unroll
+  for (int jl = 0; jl < S::HL; ++jl) {
+    const float gh = dot_smem<D>(cw.w2t + (jl * L + l) * S::YS, ln.a);
+    delta[jl] = gh * (1.f - hk[jl] * hk[jl]);
+    const float sd = scale * delta[jl];
+    acc.b1[jl] += sd;
+    axpy_line<D>(acc.w1[jl], sd, ln.y);
+  }
+  store_frag<S::HL>(ln.dl + l * S::HL, delta);
+#pragma unroll
+  for (int dl = 0; dl < S::DL; ++dl) {
+    const float sa = scale * a[dl];
+    acc.b2[dl] += sa;
+    axpy_line<H>(acc.w2[dl], sa, ln.h);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int dl = 0; dl < S::DL; ++dl) vjp[dl] = dot_smem<H>(cw.w1t + (dl * L + l) * S::HS, ln.dl);
+}
+
+// Put a stage's full input and tanh vector back into lines.y / lines.h (backprop kernels recompute all
+// stages first and walk them in reverse).  mlp_vjp's first __syncwarp orders these stores before the reads.
+template <int D, int H, int L>
+__device__ __forceinline__ void regather(const BwdLines<D, H, L>& ln, int l, const float (&u)[Shape<D, H, L>::DL],
+                                         const float (&hk)[Shape<D, H, L>::HL]) {
+  using S = Shape<D, H, L>;
+  __syncwarp();  // every lane is done reading the previous stage's lines
+  store_frag<S::DL>(ln.y + l * S::DL, u);
+  store_frag<S::HL>(ln.h + l * S::HL, hk);
+}
+
+// ---- deterministic reduction of GradAcc over the whole grid ---------------------------------------------------
+// 1. lanes with equal l (different trajectories of a warp): xor-shuffle tree
+// 2. warps of a CTA: shared memory, fixed order
+// 3. CTAs: per-CTA partial rows in the workspace; the last CTA to arrive sums them in CTA order and overwrites
+//    grad_params.  The order of every floating-point addition is fixed by (grid, block) alone -> bit-reproducible.
+struct ReduceWs {
+  unsigned int* counter;  // zeroed by the host wrapper before launch
+  float* partials;        // [gridDim.x][P]
+};
+
+template <int D, int H, int L, int WARPS>
+__device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float* smem_red /* [WARPS][P] */,
+                                                   const ReduceWs& ws, float* __restrict__ grad_params, int lane,
+                                                   int warp, int tid) {
+  using S = Shape<D, H, L>;
+  constexpr int P = S::P;
+  const int l = lane % L;
+#pragma unroll
+  for (int off = L; off < 32; off <<= 1) {
+#pragma unroll
+    for (int jl = 0; jl < S::HL; ++jl) {
+      acc.b1[jl] += __shfl_xor_sync(0xffffffffu, acc.b1[jl], off);
+#pragma unroll
+      for (int i = 0; i < D; ++i) acc.w1[jl][i] += __shfl_xor_sync(0xffffffffu, acc.w1[jl][i], off);
+    }
+#pragma unroll
+    for (int dl = 0; dl < S::DL; ++dl) {
+      acc.b2[dl] += __shfl_xor_sync(0xffffffffu, acc.b2[dl], off);
+#pragma unroll
+      for (int j = 0; j < H; ++j) acc.w2[dl][j] += __shfl_xor_sync(0xffffffffu, acc.w2[dl][j], off);
+    }
+  }
+  if (lane < L) {
+    float* r = smem_red + warp * P;
+#pragma unroll
+    for (int jl = 0; jl < S::HL; ++jl) {
+      const int j = l * S::HL + jl;
+      store_frag<D>(r + j * D, acc.w1[jl]);
+      r[H * D + j] = acc.b1[jl];
+    }
+#pragma unroll
+    for (int dl = 0; dl < S::DL; ++dl) {
+      const int d = l * S::DL + dl;
+      store_frag<H>(r + H * D + H + d * H, acc.w2[dl]);
+      r[H * D + H + D * H + d] = acc.b2[dl];
+    }
+  }
+  __syncthreads();
+  float* mine = ws.partials + (size_t)blockIdx.x * P;
+  for (int p = tid; p < P; p += WARPS * 32) {
+    float s = smem_red[p];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
+    mine[p] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_is_last;
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(ws.counter, 1u);
+    s_is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_is_last) {
+    __threadfence();
+    const int nb = gridDim.x;
+    for (int p4 = tid; p4 < P / 4; p4 += WARPS * 32) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
+#pragma unroll 8
+      for (int b = 0; b < nb; ++b) {
+        const float4 v = __ldcg(col + (size_t)b * (P / 4));
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(grad_params)[p4] = s;
+    }
+    if (tid == 0) *ws.counter = 0u;  // leave the workspace reusable
+  }
+}
+
+}  // namespace gode

@@ -1,0 +1,428 @@
+"""torchdiffeq-signature boundary over the fused sm_100a kernels.
+
+Mirrors the interface the reference imports (`from torchdiffeq import odeint_adjoint as odeint`,
+models/mocogan_ode.py:4, models/mocogan_ode_rnn.py:4) so `sample_z_m` (models/mocogan_ode.py:133-148) runs
+unchanged: same argument names, defaults (method=None -> dopri5, rtol=1e-7, atol=1e-9), error behaviour
+(TypeError for non-floating y0 / t, AssertionError texts of torchdiffeq's solver asserts) and return value
+((len(t), *y0.shape), sol[0] == y0 bit-exact, gradients to y0 and to func.parameters()).
+
+What is NOT generic: `func` must be the reference's ODEFunc structure (models/mocogan_ode.py:6-17) —
+`func.fn == Sequential(Linear(D,H), Tanh(), Linear(H,D))`, autonomous — because the whole solve (all steps, all
+stages, the MLP inside each stage) is ONE kernel launch.  Anything else raises NotImplementedError; there is no
+eager/CPU fallback.
+
+Extra keys accepted in `options` (ignored by torchdiffeq, so reference code never passes them):
+  precision : 'fp32' (default) | 'tf32' | 'bf16'      arithmetic of the MLP contractions
+  layout    : 'tbd' (default) | 'btd'                 memory order of the returned (T,B,D) tensor; 'btd' makes the
+                                                      caller's .transpose(0,1).reshape(-1,D) a free view
+  check     : bool (default False)                    synchronise and raise solver asserts eagerly
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import GodeAdaptiveOpts, GodeError, GodeStepLog
+
+__all__ = ["odeint", "odeint_adjoint", "last_step_log", "StepLog", "recognise_field", "config"]
+
+
+class _Config:
+    """Process-wide defaults for reference code that cannot pass `options` (it calls odeint(func, x, t, method=...))."""
+    layout = "tbd"
+    precision = "fp32"
+    ckpt_capacity = 64      # accepted dopri5 steps kept for backprop before GODE_ST_CKPT_OVERFLOW
+    log_capacity = 1024
+
+
+config = _Config()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def recognise_field(func):
+    """Return (W1, b1, W2, b2) if `func` is the reference's ODEFunc structure, else raise NotImplementedError."""
+    fn = getattr(func, "fn", None)
+    ok = (isinstance(fn, nn.Sequential) and len(fn) == 3 and isinstance(fn[0], nn.Linear)
+          and isinstance(fn[1], nn.Tanh) and isinstance(fn[2], nn.Linear)
+          and fn[0].bias is not None and fn[2].bias is not None
+          and fn[0].out_features == fn[2].in_features and fn[0].in_features == fn[2].out_features)
+    if not ok:
+        raise NotImplementedError(
+            "gan_ode_b200 fuses the solver with the reference's ODEFunc (models/mocogan_ode.py:6-17): func.fn must be "
+            "nn.Sequential(nn.Linear(D,H), nn.Tanh(), nn.Linear(H,D)); got {!r}. There is no generic fallback."
+            .format(type(func).__name__))
+    return fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32, contiguous, 16-byte aligned (kernels use 128-bit accesses)."""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _check_common(y0, t):
+    if not isinstance(y0, torch.Tensor):
+        raise NotImplementedError("tuple-valued y0 is not on the gan-ode hot path")
+    if not torch.is_floating_point(y0):
+        raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0.type()))
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("`t` must be a torch.Tensor")
+    assert t.ndimension() == 1, "t must be one dimensional"
+    if not torch.is_floating_point(t):
+        raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
+    if y0.dtype != torch.float32:
+        raise NotImplementedError("the fused path computes in float32 state (reference dtype); got {}".format(y0.dtype))
+    if y0.dim() != 2:
+        raise NotImplementedError("y0 must be (B, D) as in models/mocogan_ode.py:136-140; got {}".format(tuple(y0.shape)))
+    if not y0.is_cuda:
+        raise GodeError("y0 is on {}: the B200 path has no CPU fallback".format(y0.device))
+    if len(t) < 2:
+        raise NotImplementedError("len(t) must be >= 2")
+
+
+def _signed_times(t: torch.Tensor):
+    """torchdiffeq _check_inputs: decreasing t is integrated as increasing -t with the field negated.
+    Returns (t_inc_cpu_or_dev, fsign).  Monotonicity is asserted like upstream (needs the values on the host when
+    t is a CPU tensor — the reference's case — and is skipped for device tensors unless options['check'])."""
+    fsign = 1.0
+    if not t.is_cuda:
+        if len(t) > 1 and bool(t[0] > t[1]):
+            t = -t
+            fsign = -1.0
+        assert bool((t[1:] > t[:-1]).all()), "t must be strictly increasing or decreasing"
+    return t, fsign
+
+
+def _layout_code(name):
+    if name not in ("tbd", "btd"):
+        raise ValueError("options['layout'] must be 'tbd' or 'btd'")
+    return _lib.LAYOUT_TBD if name == "tbd" else _lib.LAYOUT_BTD
+
+
+def _alloc_traj(T, B, D, layout, like):
+    if layout == _lib.LAYOUT_TBD:
+        buf = torch.empty((T, B, D), dtype=torch.float32, device=like.device)
+        return buf, buf
+    buf = torch.empty((B, T, D), dtype=torch.float32, device=like.device)
+    return buf, buf.transpose(0, 1)
+
+
+def _grad_in_layout(g: torch.Tensor, layout):
+    """Upstream gradient as a contiguous buffer in the kernel's layout (zero-copy when it already is)."""
+    g = g.detach()
+    if g.dtype != torch.float32:
+        g = g.float()
+    if layout == _lib.LAYOUT_BTD:
+        g = g.transpose(0, 1)
+    g = g.contiguous()
+    if g.data_ptr() % 16:
+        g = g.clone()
+    return g
+
+
+def _split_params(flat, D, H, needs):
+    n1 = H * D
+    outs = (flat[:n1].view(H, D), flat[n1:n1 + H], flat[n1 + H:n1 + H + D * H].view(D, H), flat[n1 + H + D * H:])
+    return tuple(o if need else None for o, need in zip(outs, needs))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# fixed-grid rk4
+class _Rk4(torch.autograd.Function):
+    """forward: gode_rk4_fwd (one launch).  backward: gode_rk4_adjoint_bwd (torchdiffeq odeint_adjoint semantics) or
+    gode_rk4_backprop_bwd (autograd-through-odeint semantics), one launch."""
+
+    @staticmethod
+    def forward(ctx, y0, dt, meta, W1, b1, W2, b2):
+        L = _lib.lib()
+        B, D = y0.shape
+        H = W1.shape[0]
+        T = meta["T"]
+        y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
+        buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
+        dt_dev = 1 if dt.is_cuda else 0
+        _lib.check(L.gode_rk4_fwd(_ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), _ptr(dt), dt_dev, B, D, H, T,
+                                  meta["precision"], meta["layout"], _ptr(buf), _stream()), "gode_rk4_fwd")
+        ctx.meta = meta
+        ctx.dt = dt
+        ctx.save_for_backward(buf, W1c, b1c, W2c, b2c)
+        return view
+
+    @staticmethod
+    def backward(ctx, grad_traj):
+        L = _lib.lib()
+        buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
+        meta, dt = ctx.meta, ctx.dt
+        T = meta["T"]
+        if meta["layout"] == _lib.LAYOUT_TBD:
+            _, B, D = buf.shape
+        else:
+            B, _, D = buf.shape
+        H = W1c.shape[0]
+        g = _grad_in_layout(grad_traj, meta["layout"])
+        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=buf.device)
+        grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=buf.device)
+        ws_bytes = L.gode_bwd_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
+        fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
+        _lib.check(fn(_ptr(buf), _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), _ptr(dt), 1 if dt.is_cuda else 0,
+                      B, D, H, T, meta["precision"], meta["layout"], _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes,
+                      _stream()), "gode_rk4_bwd")
+        needs = ctx.needs_input_grad
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[3:7])
+        return (grad_y0 if needs[0] else None), None, None, gW1, gb1, gW2, gb2
+
+
+def _rk4_dt(t: torch.Tensor, options) -> torch.Tensor:
+    """Step table of torchdiffeq's fixed-grid driver: grid == t when no step_size is given, dt_j = t[j+1]-t[j] in t's
+    dtype, multiplied into fp32 state (=> rounded to fp32).  Decreasing t gives negative dt, which is bit-identical
+    to upstream's (-t, -f) rewrite for the 3/8 rule (negation is exact)."""
+    if options.get("step_size") is not None or options.get("grid_constructor") is not None:
+        raise NotImplementedError("step_size / grid_constructor sub-stepping is not on the gan-ode hot path (SURVEY §8f-4)")
+    return (t[1:] - t[:-1]).to(torch.float32).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# adaptive dopri5
+class StepLog:
+    """Host view of a device-side GodeStepLog (+ attempt arrays).  Reading any attribute synchronises."""
+
+    def __init__(self, raw: torch.Tensor, cap: int):
+        self._raw, self._cap, self._host = raw, cap, None
+
+    def _load(self):
+        if self._host is None:
+            h = self._raw.cpu().numpy().tobytes()
+            hdr = GodeStepLog.from_buffer_copy(h[:C.sizeof(GodeStepLog)])
+            import numpy as np
+            cap = self._cap
+            off = 64
+            n = min(hdr.n_attempts, cap)
+            t0 = np.frombuffer(h, dtype=np.float64, count=cap, offset=off)[:n]
+            dt = np.frombuffer(h, dtype=np.float64, count=cap, offset=off + 8 * cap)[:n]
+            er = np.frombuffer(h, dtype=np.float32, count=cap, offset=off + 16 * cap)[:n]
+            acc = np.frombuffer(h, dtype=np.uint8, count=cap, offset=off + 20 * cap)[:n]
+            self._host = dict(status=hdr.status, n_attempts=hdr.n_attempts, n_accepted=hdr.n_accepted, nfe=hdr.nfe,
+                              dt0=hdr.dt0, t_final=hdr.t_final, t0=t0.tolist(), dt=dt.tolist(),
+                              error_ratio=er.tolist(), accepted=[bool(a) for a in acc])
+        return self._host
+
+    def __getattr__(self, k):
+        if k.startswith("_"):
+            raise AttributeError(k)
+        return self._load()[k]
+
+    @property
+    def n_rejected(self):
+        return self.n_attempts - self.n_accepted
+
+
+_LAST_LOG = [None]
+
+
+def last_step_log() -> Optional[StepLog]:
+    """Step log of the most recent adaptive solve on this process (synchronises when read)."""
+    return _LAST_LOG[0]
+
+
+def raise_for_status(status: int):
+    """torchdiffeq's solver asserts, raised from the device status word."""
+    if status & _lib.ST_NONFINITE:
+        raise AssertionError("non-finite values in state `y`")
+    if status & _lib.ST_DT_UNDERFLOW:
+        raise AssertionError("underflow in dt")
+    if status & _lib.ST_MAX_STEPS:
+        raise AssertionError("max_num_steps exceeded")
+    if status & _lib.ST_CKPT_OVERFLOW:
+        raise GodeError("more accepted steps than options['ckpt_capacity']; raise gan_ode_b200.config.ckpt_capacity")
+
+
+def _log_layout(cap):
+    # [GodeStepLog (64 B slot)] [att_t0: cap f64] [att_dt: cap f64] [att_er: cap f32] [att_acc: cap u8]
+    return 64 + 8 * cap + 8 * cap + 4 * cap + cap
+
+
+class _Dopri5(torch.autograd.Function):
+    """forward: gode_dopri5_fwd (one cooperative launch, batch-global error norm).
+    backward: gode_dopri5_backprop_bwd — reverse-mode through the accepted steps recorded on the device."""
+
+    @staticmethod
+    def forward(ctx, y0, meta, W1, b1, W2, b2):
+        L = _lib.lib()
+        B, D = y0.shape
+        H = W1.shape[0]
+        T = meta["T"]
+        dev = y0.device
+        y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
+        buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
+        o = meta["opts"]
+        cap = o.log_capacity
+        raw = torch.empty(_log_layout(cap), dtype=torch.uint8, device=dev)
+        base = raw.data_ptr()
+        keep = meta["keep_ckpt"]
+        kc = o.ckpt_capacity if keep else 0
+        opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
+        opts.ckpt_capacity = kc
+        ckpt = torch.empty((max(kc, 1), B, D), dtype=torch.float32, device=dev) if keep else None
+        acc = torch.empty(2 * max(kc, 1), dtype=torch.float64, device=dev) if keep else None
+        ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        tarr = (C.c_double * T)(*meta["t_list"])
+        _lib.check(L.gode_dopri5_fwd(
+            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), C.cast(tarr, C.c_void_p), B, D, H, T, C.byref(opts),
+            meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
+            _ptr(ckpt), _ptr(acc), (acc.data_ptr() + 8 * max(kc, 1)) if keep else None, _ptr(ws), ws_bytes, _stream()),
+            "gode_dopri5_fwd")
+        log = StepLog(raw, cap)
+        _LAST_LOG[0] = log
+        if meta["check"]:
+            raise_for_status(log.status)
+        ctx.meta, ctx.log, ctx.kc, ctx.tarr = meta, log, kc, tarr
+        ctx.save_for_backward(raw, ckpt, acc, W1c, b1c, W2c, b2c)
+        return view
+
+    @staticmethod
+    def backward(ctx, grad_traj):
+        L = _lib.lib()
+        raw, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors
+        meta, kc = ctx.meta, ctx.kc
+        if ckpt is None:
+            raise GodeError("dopri5 forward ran without checkpoints (inputs did not require grad)")
+        # the only host<->device sync of the backward: solver status (checkpoint overflow would silently truncate)
+        raise_for_status(ctx.log.status)
+        T = meta["T"]
+        _, B, D = ckpt.shape
+        H = W1c.shape[0]
+        g = _grad_in_layout(grad_traj, meta["layout"])
+        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=ckpt.device)
+        grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
+        ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
+        _lib.check(L.gode_dopri5_backprop_bwd(
+            _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), C.cast(ctx.tarr, C.c_void_p), B, D, H, T,
+            meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
+            C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes, _stream()),
+            "gode_dopri5_backprop_bwd")
+        needs = ctx.needs_input_grad
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6])
+        return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
+
+
+def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
+    if isinstance(rtol, torch.Tensor) or isinstance(atol, torch.Tensor):
+        rtol, atol = float(rtol), float(atol)
+    o = GodeAdaptiveOpts()
+    o.rtol, o.atol = float(rtol), float(atol)
+    fs = options.get("first_step", None)
+    o.first_step = float(fs) if fs is not None else 0.0
+    o.safety = float(options.get("safety", 0.9))
+    o.ifactor = float(options.get("ifactor", 10.0))
+    o.dfactor = float(options.get("dfactor", 0.2))
+    o.min_step = float(options.get("min_step", 0.0))
+    o.max_step = float(options.get("max_step", float("inf")))
+    o.max_num_steps = int(min(options.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
+    norm = options.get("norm", None)
+    if norm is not None and norm not in ("batch", "rms"):
+        raise NotImplementedError("custom error norms are not supported by the fused dopri5 kernel (batch-global RMS only)")
+    o.norm_scope = _lib.NORM_BATCH
+    o.log_capacity = int(options.get("log_capacity", config.log_capacity))
+    o.ckpt_capacity = int(options.get("ckpt_capacity", config.ckpt_capacity))
+    o.fsign = fsign
+    return o
+
+
+# ------------------------------------------------------------------------------------------------------------
+def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
+    W1, b1, W2, b2 = recognise_field(func)
+    _check_common(y0, t)
+    options = {} if options is None else dict(options)
+    if method is None:
+        method = "dopri5"
+    D, H = W1.shape[1], W1.shape[0]
+    if y0.shape[1] != D:
+        raise ValueError("y0 has {} features but func expects {}".format(y0.shape[1], D))
+    prec_name = options.get("precision", config.precision)
+    if prec_name not in _lib.PREC:
+        raise ValueError("options['precision'] must be one of {}".format(sorted(_lib.PREC)))
+    prec = _lib.PREC[prec_name]
+    if not _lib.lib().gode_supported(D, H, prec):
+        raise NotImplementedError("no sm_100a kernel compiled for ODEFunc(dim={}, dim_hidden={}) at precision {}; "
+                                  "there is no fallback".format(D, H, prec_name))
+    layout = _layout_code(options.get("layout", config.layout))
+    if t.device != y0.device and t.is_cuda:
+        warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
+        t = t.to(y0.device)
+    meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)))
+
+    if method == "rk4":
+        t_inc, _ = _signed_times(t)  # asserts monotonicity; rk4 uses signed dt directly
+        dt = _rk4_dt(t, options)
+        if len(t) - 1 > _lib.MAX_HOST_STEPS and not dt.is_cuda:
+            dt = dt.to(y0.device)
+        return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
+
+    if method == "dopri5":
+        if prec != _lib.PREC["fp32"]:
+            raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
+        if adjoint:
+            raise NotImplementedError("dopri5 continuous adjoint is not built yet; use odeint (backprop-through-solver)")
+        th = t.detach().to("cpu", torch.float64)  # torchdiffeq: t -> float64 for adaptive solvers (syncs iff t on GPU)
+        th, fsign = _signed_times(th)
+        meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
+        meta["t_list"] = th.tolist()
+        meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
+        return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
+
+    raise NotImplementedError('method "{}" is not on the gan-ode hot path (rk4 and dopri5 are; SURVEY §8f-4)'.format(method))
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """torchdiffeq.odeint for the reference's ODEFunc.  Gradients are those of autograd through the solver
+    (backprop-through-solver; the adaptive dt sequence is treated as data)."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not on the gan-ode hot path")
+    return _solve(func, y0, t, rtol, atol, method, options, adjoint=False)
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
+                   adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
+                   adjoint_params=None):
+    """torchdiffeq.odeint_adjoint for the reference's ODEFunc: the backward pass is the continuous adjoint re-solved
+    per output interval with the same method (adjoint.py), fused into one kernel."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not on the gan-ode hot path")
+    if adjoint_params is None and not isinstance(func, nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they "
+                         "can be specified explicitly via the `adjoint_params` argument. If there are no parameters "
+                         "then it is allowable to set `adjoint_params=()`.")
+    if adjoint_method is not None and adjoint_method != (method or "dopri5"):
+        raise NotImplementedError("adjoint_method must equal method on the fused path")
+    for name, val, fwd in (("adjoint_rtol", adjoint_rtol, rtol), ("adjoint_atol", adjoint_atol, atol)):
+        if val is not None and val != fwd:
+            raise NotImplementedError("{} different from the forward tolerance is not supported".format(name))
+    if adjoint_options:
+        raise NotImplementedError("adjoint_options are not supported on the fused path")
+    if adjoint_params is not None:
+        mine = [p for p in recognise_field(func)]
+        given = [p for p in adjoint_params]
+        if len(given) != len(mine) or any(a is not b for a, b in zip(given, mine)):
+            raise NotImplementedError("adjoint_params must be func's own parameters (or None)")
+    return _solve(func, y0, t, rtol, atol, method, options, adjoint=True)

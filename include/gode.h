@@ -1,0 +1,166 @@
+/* gode.h — C ABI of the B200-native latent-motion ODE hot path (libgode.so).
+ *
+ * Drop-in boundary for chechaohp/gan-ode: these entry points are what a binding of the
+ * reference's solver calls would bind.  The reference is pure Python and reaches its solver
+ * through two third-party call signatures:
+ *
+ *   torchdiffeq.odeint_adjoint(func, y0, t, method='rk4')      models/mocogan_ode.py:48-50,105-107,142-144
+ *   torchdiffeq.odeint_adjoint(func, h, [0,1])  (dopri5)       models/mocogan_ode_rnn.py:47-48
+ *   nn.GRUCell(e_t, h')  jump after each solve                 models/mocogan_ode_rnn.py:49
+ *   torchsde.sdeint_adjoint(sde, x, ts, method='euler', dt)    models/mocogan_sde.py:57-59
+ *
+ * with func = ODEFunc (models/mocogan_ode.py:6-17): f(t,x) = W2 tanh(W1 x + b1) + b2.
+ * The Python host side (gan_ode_b200/odeint.py …) keeps those signatures and calls the
+ * functions below through ctypes.  INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.  All tensors fp32, row-major,
+ *    contiguous.  Weights use nn.Linear layout: W1 (H,D), b1 (H), W2 (D,H), b2 (D).
+ *  - pointers are DEVICE pointers unless the name ends in _host.
+ *  - every call is asynchronous on `stream` (a cudaStream_t), holds no global mutable state,
+ *    never synchronises the device, and allocates nothing: outputs and workspaces come from
+ *    the caller (PyTorch's caching allocator on the Python side).
+ *  - return value: 0 OK; <0 argument / capability error (gode_strerror); launch failures are
+ *    returned as -(1000 + cudaError_t).  Solver conditions that are only known on the device
+ *    (dt underflow, non-finite state, step budget exhausted, checkpoint overflow) are written
+ *    to the int status word of the GodeStepLog the caller passed.
+ */
+#ifndef GODE_H_
+#define GODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gode_stream_t; /* cudaStream_t */
+
+/* arithmetic of the MLP contractions */
+enum {
+  GODE_PREC_FP32 = 0, /* CUDA-core FFMA, <=1e-5 rel vs torchdiffeq                      */
+  GODE_PREC_TF32 = 1, /* tcgen05 kind::tf32, fp32 accumulate in TMEM, <=2e-3 rel        */
+  GODE_PREC_BF16 = 2  /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate, <=2e-3 rel */
+};
+
+/* trajectory layout */
+enum {
+  GODE_LAYOUT_TBD = 0, /* (T,B,D): what odeint returns                                   */
+  GODE_LAYOUT_BTD = 1  /* (B,T,D): == traj.transpose(0,1).reshape(-1,D) of models/mocogan_ode.py:146 */
+};
+
+/* error-norm scope of the adaptive controller */
+enum {
+  GODE_NORM_BATCH = 0, /* one RMS norm over all B*D elements, one (t,dt) for the batch — torchdiffeq */
+  GODE_NORM_TRAJ = 1   /* per-trajectory RMS over D, per-trajectory (t,dt) — opt-in                 */
+};
+
+/* error codes (<0) */
+enum {
+  GODE_OK = 0,
+  GODE_ERR_SHAPE = -1,       /* (D,H) has no compiled kernel for this precision            */
+  GODE_ERR_ARG = -2,         /* null pointer, B<=0, T<2 ...                                */
+  GODE_ERR_T_TOO_LONG = -3,  /* host-side dt table longer than GODE_MAX_HOST_STEPS         */
+  GODE_ERR_WORKSPACE = -4,   /* workspace smaller than gode_*_workspace_bytes()            */
+  GODE_ERR_COOP = -5,        /* batch-global dopri5 needs all CTAs co-resident; B too big  */
+  GODE_ERR_PRECISION = -6    /* precision mode not available for this entry point          */
+};
+
+/* device-side solver status bits (GodeStepLog.status) */
+enum {
+  GODE_ST_DT_UNDERFLOW = 1, /* torchdiffeq: assert t0 + dt > t0, 'underflow in dt'         */
+  GODE_ST_NONFINITE = 2,    /* torchdiffeq: assert isfinite(y0), 'non-finite values in state' */
+  GODE_ST_MAX_STEPS = 4,    /* torchdiffeq: 'max_num_steps exceeded'                       */
+  GODE_ST_CKPT_OVERFLOW = 8 /* more accepted steps than checkpoint / log capacity          */
+};
+
+#define GODE_MAX_HOST_STEPS 255
+
+/* Step log of one adaptive solve, device resident, written by the forward kernel and read by the
+ * backward kernel (no host round trip).  One entry per ATTEMPTED step in attempt order. */
+typedef struct GodeStepLog {
+  int32_t status;      /* OR of GODE_ST_*                                                  */
+  int32_t n_attempts;  /* attempted steps                                                  */
+  int32_t n_accepted;  /* accepted steps                                                   */
+  int32_t nfe;         /* vector-field evaluations per trajectory                          */
+  double dt0;          /* result of the initial-step heuristic                             */
+  double t_final;      /* t1 of the last accepted step                                     */
+} GodeStepLog;
+
+/* adaptive controller options — torchdiffeq RKAdaptiveStepsizeODESolver defaults in comments */
+typedef struct GodeAdaptiveOpts {
+  double rtol;         /* 1e-7 */
+  double atol;         /* 1e-9 */
+  double first_step;   /* <=0: use the initial-step heuristic */
+  double safety;       /* 0.9  */
+  double ifactor;      /* 10   */
+  double dfactor;      /* 0.2  */
+  double min_step;     /* 0    */
+  double max_step;     /* inf  */
+  int32_t max_num_steps; /* per output interval; 2^31-1 */
+  int32_t norm_scope;    /* GODE_NORM_BATCH */
+  int32_t log_capacity;  /* entries in the attempt arrays (t0/dt/er/accepted)              */
+  int32_t ckpt_capacity; /* accepted steps the checkpoint buffer can hold (0: none kept)   */
+  float fsign;           /* +1, or -1 when the caller negated a decreasing time grid (torchdiffeq _ReverseFunc) */
+  int32_t _pad;
+} GodeAdaptiveOpts;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+const char* gode_strerror(int code);
+const char* gode_version(void);
+/* 1 if a kernel exists for (D,H) at this precision, else 0 */
+int gode_supported(int D, int H, int precision);
+/* number of floats in the flat parameter vector [W1|b1|W2|b2] = H*D + H + D*H + D */
+int gode_param_count(int D, int H);
+
+/* ---- a3: fixed-grid rk4 (3/8 rule) forward -------------------------------------------------- */
+/* dt: T-1 step sizes dt_j = t[j+1]-t[j] rounded as torchdiffeq does (in t's dtype, then fp32).
+ * dt_on_device=0: dt is a HOST array, passed by value in the launch (T-1 <= GODE_MAX_HOST_STEPS).
+ * traj: (T,B,D) or (B,T,D); traj[0] = y0 bit-exact. */
+int gode_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                 const float* dt, int dt_on_device, int B, int D, int H, int T, int precision,
+                 int out_layout, float* traj, gode_stream_t stream);
+
+/* ---- a4: rk4 continuous adjoint (torchdiffeq OdeintAdjointMethod.backward with method='rk4') -- */
+/* grad_params: flat [W1|b1|W2|b2], OVERWRITTEN with this call's gradient (may be an NCCL buffer).
+ * workspace: gode_bwd_workspace_bytes(B,D,H) bytes, contents undefined on entry. */
+size_t gode_bwd_workspace_bytes(int B, int D, int H);
+int gode_rk4_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                         const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D,
+                         int H, int T, int precision, int layout, float* grad_y0, float* grad_params,
+                         void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* ---- A.5: rk4 backprop-through-solver (== autograd through torchdiffeq.odeint, method='rk4') -- */
+int gode_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                          const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D,
+                          int H, int T, int precision, int layout, float* grad_y0, float* grad_params,
+                          void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* ---- a5: adaptive dopri5 forward ------------------------------------------------------------- */
+/* t_host: T output times (fp64, increasing; the caller negates decreasing grids as torchdiffeq does).
+ * log: device GodeStepLog; att_t0/att_dt (double), att_er (float), att_acc (uint8): device arrays of
+ * opts->log_capacity entries (may be NULL when log_capacity==0).
+ * ckpt: (ckpt_capacity,B,D) state at the START of each accepted step, for backprop (NULL if capacity 0).
+ * acc_t0/acc_dt: (ckpt_capacity) doubles, (t0,dt) of each accepted step.
+ * workspace: gode_dopri5_workspace_bytes(B,D,H) bytes. */
+size_t gode_dopri5_workspace_bytes(int B, int D, int H);
+int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts,
+                    int out_layout, float* traj, GodeStepLog* log, double* att_t0, double* att_dt,
+                    float* att_er, uint8_t* att_acc, float* ckpt, double* acc_t0, double* acc_dt,
+                    void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* ---- A.5: dopri5 backprop-through-solver ------------------------------------------------------ */
+/* Replays the accepted steps recorded by gode_dopri5_fwd in reverse (dt sequence treated as data),
+ * including the dense-output interpolation of every requested time. */
+int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                             const GodeStepLog* log, const float* ckpt, const double* acc_t0,
+                             const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
+                             void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GODE_H_ */
