@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — ODE trajectory-steps/s (fwd+bwd) of the latent-motion hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): the reference's ODEFunc
+(models/mocogan_ode.py:6-17, D = H = 16, default nn.Linear init under torch.manual_seed(0)), B = 4096 trajectories
+PER GPU (weak scaling), output grid t = linspace(0,1,16), dopri5 with rtol = atol = 1e-5, forward + backprop through
+the solver, upstream gradient supplied as a resident N(0,1) tensor.  One "step" = one forward + one
+backward of that batch.  trajectory-steps = B x ATTEMPTED dopri5 steps (accepted + rejected), read from the device log.
+
+value     inputs resident in HBM; the step (2 kernels + 2 memsets) replayed from a CUDA graph; per-step CUDA events,
+          L2 flushed (256 MiB write) between steps outside the event pairs.
+e2e       the same metric through the public API the reference calls (gan_ode_b200.odeint), eager, with the
+          batch's noise y0 in pinned HOST memory: H2D copy of y0 and D2H read of loss + parameter gradients are
+          inside the timed region, every step.
+roofline  dominant kernel, algorithmic HBM bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+--impl reference   the CPU arm: the torchdiffeq-restatement oracle (the real torchdiffeq is neither vendored by the
+          reference nor installable here) on all host threads, same config / metric / unit.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+B_PER_GPU, D, H, T = 4096, 16, 16, 16
+RTOL = ATOL = 1e-5
+METRIC = "ode_trajectory_steps_per_s_fwd_bwd"
+UNIT = "trajectory-steps/s"
+CONFIG = {
+    "workload": "configs[1]: ODEFunc D=H=16, B=4096 trajectories per GPU, t=linspace(0,1,16), dopri5 rtol=atol=1e-5, "
+                "fwd + backprop-through-solver",
+    "B_per_gpu": B_PER_GPU, "D": D, "H": H, "T": T, "rtol": RTOL, "atol": ATOL, "method": "dopri5",
+    "backward": "backprop-through-solver", "weights": "nn.Linear default init, torch.manual_seed(0)",
+    "l2": "flushed between steps (256 MiB write outside the per-step CUDA-event pairs)",
+    "parallelism": "dp",
+}
+
+
+def make_inputs(seed=0, device="cpu"):
+    from tests.helpers import make_field
+    f = make_field(D, H, seed=0)
+    g = torch.Generator().manual_seed(1000 + seed)
+    y0 = torch.randn(B_PER_GPU, D, generator=g)
+    grad = torch.randn(T, B_PER_GPU, D, generator=g)
+    t = torch.linspace(0, 1, T).float()
+    return f.to(device), y0.to(device), grad.to(device), t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_arm_time(steps, warmup, threads):
+    """One step = the full workload (B=4096, dopri5 fwd + backprop) through the CPU oracle."""
+    from oracle import torchdiffeq_restatement as tdq
+    torch.set_num_threads(threads)
+    f, y0, grad, t = make_inputs()
+    params = list(f.parameters())
+
+    def step():
+        y = y0.clone().requires_grad_(True)
+        sol = tdq.odeint(f, y, t, method="dopri5", rtol=RTOL, atol=ATOL)
+        torch.autograd.grad(sol, [y] + params, grad)
+        return len(tdq.last_step_log().accepted)
+
+    for _ in range(warmup):
+        n_att = step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        n_att = step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return B_PER_GPU * n_att / med, med, n_att
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 20))
+    val, sec, n_att = cpu_arm_time(steps, min(args.warmup, 3), threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "full workload per step (B=4096, {} attempted dopri5 steps), median of {} steps; "
+                                   "torchdiffeq-restatement oracle (real torchdiffeq not installable)".format(n_att, steps)},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, copy bandwidth)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    import gan_ode_b200 as gode
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        gode.config.grad_allreduce = True
+    n_gpus = world
+
+    f, y0, grad, t = make_inputs(seed=rank, device=dev)
+    params = list(f.parameters())
+    kw = dict(method="dopri5", rtol=RTOL, atol=ATOL)
+    y0r = y0.clone().requires_grad_(True)
+
+    def step():
+        sol = gode.odeint(f, y0r, t, **kw)
+        return torch.autograd.grad(sol, [y0r] + params, grad)
+
+    # warm-up (eager), read the step count from the device log
+    for _ in range(max(3, args.warmup)):
+        grads = step()
+    torch.cuda.synchronize()
+    log = gode.last_step_log()
+    n_att, n_acc, status = log.n_attempts, log.n_accepted, log.status
+    assert status == 0, "solver status {}".format(status)
+
+    # capture fwd+bwd (+ the NCCL all-reduce when N>1) in a CUDA graph; fall back to eager launches if refused
+    graph, graphed = None, False
+    try:
+        if args.no_graph:
+            raise RuntimeError("--no-graph")
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_grads = step()
+        graph.replay()
+        torch.cuda.synchronize()
+        ok = all(torch.allclose(a, b, rtol=1e-4, atol=1e-6) for a, b in zip(static_grads, grads))
+        graphed = bool(ok)
+        if not ok:
+            graph = None
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("[bench] CUDA-graph capture unavailable ({}); timing eager launches\n".format(str(e)[:200]))
+        graph = None
+        torch.cuda.synchronize()
+
+    run_step = graph.replay if graph is not None else step
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def timed_region(fn, k):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tot = sum(a.elapsed_time(b) for a, b in evs)  # ms
+        tt = torch.tensor([tot], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(max(3, args.warmup)):
+        run_step()
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms = timed_region(run_step, args.steps)
+    eager_ms = timed_region(step, args.steps) if graph is not None else total_ms
+
+    # ---- e2e through the public API with host buffers -----------------------------------------------------------
+    y0_host = y0.cpu().pin_memory()
+    res_host = torch.empty(1 + sum(p.numel() for p in params), dtype=torch.float32).pin_memory()
+    n_param = res_host.numel() - 1
+
+    def e2e_step():
+        y = y0_host.to(dev, non_blocking=True).requires_grad_(True)
+        sol = gode.odeint(f, y, t, **kw)
+        loss = (sol * grad).sum()
+        gs = torch.autograd.grad(loss, params)
+        res = torch.cat([loss.reshape(1)] + [g.reshape(-1) for g in gs])
+        res_host.copy_(res, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res_host
+
+    for _ in range(3):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-kernel durations for the roofline: events around each launch while the GPU is kept busy -------------
+    roof = None
+    if rank == 0:
+        k = max(10, min(args.steps, 50))
+        ef = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)]
+        prev = gode.config.grad_allreduce
+        gode.config.grad_allreduce = None
+        for e0, e1, e2 in ef:
+            flush.fill_(1)
+            torch.cuda._sleep(400000)  # keep the GPU busy while the host enqueues, so events bracket kernels only
+            e0.record()
+            sol = gode.odeint(f, y0r, t, **kw)
+            e1.record()
+            torch.autograd.grad(sol, [y0r] + params, grad)
+            e2.record()
+        torch.cuda.synchronize()
+        gode.config.grad_allreduce = prev
+        fwd_us = sorted(e0.elapsed_time(e1) for e0, e1, _ in ef)[k // 2] * 1e3
+        bwd_us = sorted(e1.elapsed_time(e2) for _, e1, e2 in ef)[k // 2] * 1e3
+        row = B_PER_GPU * D * 4
+        fwd_bytes = row * (1 + T + n_acc)           # read y0, write T outputs, write n_acc checkpoints
+        bwd_bytes = row * (T + n_acc + 1) + 4 * n_param  # read T upstream grads + n_acc checkpoints, write grad_y0 + params
+        dom, dur, byts = ("dopri5_backprop_bwd_kernel", bwd_us, bwd_bytes) if bwd_us >= fwd_us else \
+                         ("dopri5_fwd_kernel", fwd_us, fwd_bytes)
+        peak, how = peaks()
+        achieved = byts / (dur * 1e-6) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(dom)
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": how,
+                "algorithmic_bytes_per_launch": byts, "kernel_us": dur,
+                "kernels_us": {"dopri5_fwd_kernel": fwd_us, "dopri5_backprop_bwd_kernel": bwd_us},
+                "note": "B=4096 x D=16 is 256 KB of state: the solve is a chain of {} dependent stages with a grid "
+                        "barrier per attempted step, i.e. latency-bound, not bandwidth-bound".format(2 + 6 * n_att)}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    units = B_PER_GPU * n_att * n_gpus
+    ms_per_step = total_ms / args.steps
+    value = units / (ms_per_step * 1e-3)
+    e2e_val = units / (e2e_s / args.steps)
+    h2d = y0_host.numel() * 4
+    d2h = res_host.numel() * 4
+
+    # CPU baseline beside it: the oracle on the host cores, bounded sample (rank 0, N=1 only)
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sec, na = cpu_arm_time(steps=7, warmup=2, threads=threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "full workload (B=4096, {} attempted steps) x 7 timed steps, median {:.3f} s/step; "
+                         "torchdiffeq-restatement oracle (PyTorch CPU)".format(na, sec)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": dict(CONFIG, global_batch=B_PER_GPU * n_gpus, cuda_graph=graphed,
+                                            attempted_steps=n_att, accepted_steps=n_acc,
+                                            parallelism="dp{}".format(n_gpus)),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s / args.steps * 1e3, "api": "gan_ode_b200.odeint (eager, pinned host y0)"},
+        "gpu_launches": 2 * args.steps,
+        "eager_ms_per_step": eager_ms / args.steps,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        sys.exit(subprocess.call(cmd))
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

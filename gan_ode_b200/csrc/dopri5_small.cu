@@ -318,6 +318,10 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   acc.zero();
   __syncthreads();
   const int n_acc = min(p.log->n_accepted, p.o.ckpt_capacity);
+  // A forward that failed (dt underflow, non-finite state, step budget, checkpoint overflow) has no valid replay:
+  // return NaN gradients instead of silently truncated ones (the host does not sync to look at the status).
+  const float poison = p.log->status != 0 ? __int_as_float(0x7fc00000) : 0.f;
+  acc.fill(poison);
   const int stride = gridDim.x * WARPS * S::G;
   for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
     const int b = base + g;
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
     const float sc = valid ? 1.f : 0.f;
     float ybar[S::DL], fbar[S::DL];  // cotangents of the next step's (y0, f0) == this step's (y1, f1)
 #pragma unroll
-    for (int c = 0; c < S::DL; ++c) { ybar[c] = 0.f; fbar[c] = 0.f; }
+    for (int c = 0; c < S::DL; ++c) { ybar[c] = poison; fbar[c] = 0.f; }
     int iout = p.T - 1;
     for (int s = n_acc - 1; s >= 0; --s) {
       const double t0 = p.acc_t0[s], dtd = p.acc_dt[s], t1 = t0 + dtd;

@@ -202,20 +202,21 @@ struct GradAcc {
   float b1[S::HL];
   float w2[S::DL][H];
   float b2[S::DL];
-  __device__ __forceinline__ void zero() {
+  __device__ __forceinline__ void fill(float v) {
 #pragma unroll
     for (int jl = 0; jl < S::HL; ++jl) {
-      b1[jl] = 0.f;
+      b1[jl] = v;
 #pragma unroll
-      for (int i = 0; i < D; ++i) w1[jl][i] = 0.f;
+      for (int i = 0; i < D; ++i) w1[jl][i] = v;
     }
 #pragma unroll
     for (int dl = 0; dl < S::DL; ++dl) {
-      b2[dl] = 0.f;
+      b2[dl] = v;
 #pragma unroll
-      for (int j = 0; j < H; ++j) w2[dl][j] = 0.f;
+      for (int j = 0; j < H; ++j) w2[dl][j] = v;
     }
   }
+  __device__ __forceinline__ void zero() { fill(0.f); }
 };
 
 template <int N>

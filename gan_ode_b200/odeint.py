@@ -21,6 +21,8 @@ from __future__ import annotations
 
 import ctypes as C
 import warnings
+
+import numpy as np
 from typing import Optional
 
 import torch
@@ -38,6 +40,10 @@ class _Config:
     precision = "fp32"
     ckpt_capacity = 64      # accepted dopri5 steps kept for backprop before GODE_ST_CKPT_OVERFLOW
     log_capacity = 1024
+    # Data parallelism: trajectories shard across ranks, weights are replicated, and the flat ODE
+    # parameter-gradient buffer the backward kernel writes is all-reduced (sum) in place on the same stream.
+    # None: off.  True: the default process group.  A ProcessGroup: that group.
+    grad_allreduce = None
 
 
 config = _Config()
@@ -68,12 +74,11 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
-    """fp32, contiguous, 16-byte aligned (kernels use 128-bit accesses)."""
-    t = t.detach()
-    if t.dtype != torch.float32:
-        t = t.float()
-    t = t.contiguous()
-    if t.data_ptr() % 16:
+    """fp32, contiguous, 16-byte aligned (kernels use 128-bit accesses).  The common case returns `t` itself."""
+    if t.dtype is torch.float32 and t.is_contiguous() and not (t.data_ptr() & 15):
+        return t
+    t = t.detach().float().contiguous()
+    if t.data_ptr() & 15:
         t = t.clone()
     return t
 
@@ -98,17 +103,23 @@ def _check_common(y0, t):
         raise NotImplementedError("len(t) must be >= 2")
 
 
-def _signed_times(t: torch.Tensor):
-    """torchdiffeq _check_inputs: decreasing t is integrated as increasing -t with the field negated.
-    Returns (t_inc_cpu_or_dev, fsign).  Monotonicity is asserted like upstream (needs the values on the host when
-    t is a CPU tensor — the reference's case — and is skipped for device tensors unless options['check'])."""
-    fsign = 1.0
-    if not t.is_cuda:
-        if len(t) > 1 and bool(t[0] > t[1]):
-            t = -t
-            fsign = -1.0
-        assert bool((t[1:] > t[:-1]).all()), "t must be strictly increasing or decreasing"
-    return t, fsign
+def _host_steps(t: torch.Tensor):
+    """t on the host (the reference's case: torch.linspace(...) on CPU, models/mocogan_ode.py:143) -> numpy views.
+    Returns (t64_increasing, dt32_signed, fsign).  torchdiffeq _check_inputs: t must be strictly monotone; a
+    decreasing grid is integrated as increasing -t with the field negated (fsign = -1).  dt_j = t[j+1]-t[j] is
+    taken in t's own dtype and then rounded to fp32, which is what multiplying it into fp32 state does upstream."""
+    tn = t.detach().numpy()
+    d = np.diff(tn)
+    if (d > 0).all():
+        fsign = 1.0
+    elif (d < 0).all():
+        fsign = -1.0
+    else:
+        raise AssertionError("t must be strictly increasing or decreasing")
+    t64 = tn.astype(np.float64)
+    if fsign < 0:
+        t64 = -t64
+    return t64, np.ascontiguousarray(d, dtype=np.float32), fsign
 
 
 def _layout_code(name):
@@ -138,7 +149,16 @@ def _grad_in_layout(g: torch.Tensor, layout):
     return g
 
 
+def _maybe_allreduce(flat):
+    g = config.grad_allreduce
+    if g is None or g is False:
+        return
+    import torch.distributed as dist
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=None if g is True else g)
+
+
 def _split_params(flat, D, H, needs):
+    _maybe_allreduce(flat)
     n1 = H * D
     outs = (flat[:n1].view(H, D), flat[n1:n1 + H], flat[n1 + H:n1 + H + D * H].view(D, H), flat[n1 + H + D * H:])
     return tuple(o if need else None for o, need in zip(outs, needs))
@@ -158,9 +178,11 @@ class _Rk4(torch.autograd.Function):
         T = meta["T"]
         y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
         buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
-        dt_dev = 1 if dt.is_cuda else 0
-        _lib.check(L.gode_rk4_fwd(_ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), _ptr(dt), dt_dev, B, D, H, T,
-                                  meta["precision"], meta["layout"], _ptr(buf), _stream()), "gode_rk4_fwd")
+        dt_ptr, dt_dev = _dt_arg(dt)
+        rc = L.gode_rk4_fwd(y0c.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
+                            dt_dev, B, D, H, T, meta["precision"], meta["layout"], buf.data_ptr(), _stream())
+        if rc:
+            _lib.check(rc, "gode_rk4_fwd")
         ctx.meta = meta
         ctx.dt = dt
         ctx.save_for_backward(buf, W1c, b1c, W2c, b2c)
@@ -183,21 +205,41 @@ class _Rk4(torch.autograd.Function):
         ws_bytes = L.gode_bwd_workspace_bytes(B, D, H)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
-        _lib.check(fn(_ptr(buf), _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), _ptr(dt), 1 if dt.is_cuda else 0,
-                      B, D, H, T, meta["precision"], meta["layout"], _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes,
-                      _stream()), "gode_rk4_bwd")
+        dt_ptr, dt_dev = _dt_arg(dt)
+        rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
+                dt_dev, B, D, H, T, meta["precision"], meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
+                ws.data_ptr(), ws_bytes, _stream())
+        if rc:
+            _lib.check(rc, "gode_rk4_bwd")
         needs = ctx.needs_input_grad
         gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[3:7])
         return (grad_y0 if needs[0] else None), None, None, gW1, gb1, gW2, gb2
 
 
-def _rk4_dt(t: torch.Tensor, options) -> torch.Tensor:
+def _dt_arg(dt):
+    """(pointer, on_device) of a step table held as a host numpy array or a device tensor."""
+    if isinstance(dt, np.ndarray):
+        return dt.ctypes.data, 0
+    return dt.data_ptr(), 1
+
+
+def _rk4_dt(t: torch.Tensor, options, device):
     """Step table of torchdiffeq's fixed-grid driver: grid == t when no step_size is given, dt_j = t[j+1]-t[j] in t's
     dtype, multiplied into fp32 state (=> rounded to fp32).  Decreasing t gives negative dt, which is bit-identical
-    to upstream's (-t, -f) rewrite for the 3/8 rule (negation is exact)."""
+    to upstream's (-t, -f) rewrite for the 3/8 rule (negation is exact).  A host t gives a host table that rides in
+    the kernel launch parameters (no copy, no sync); a device t stays on the device (monotonicity then unchecked
+    unless options['check'])."""
     if options.get("step_size") is not None or options.get("grid_constructor") is not None:
         raise NotImplementedError("step_size / grid_constructor sub-stepping is not on the gan-ode hot path (SURVEY §8f-4)")
-    return (t[1:] - t[:-1]).to(torch.float32).contiguous()
+    if not t.is_cuda:
+        _, dt, _ = _host_steps(t)
+        if len(dt) > _lib.MAX_HOST_STEPS:
+            return torch.from_numpy(dt).to(device)
+        return dt
+    d = t[1:] - t[:-1]
+    if options.get("check", False):
+        assert bool((d > 0).all()) or bool((d < 0).all()), "t must be strictly increasing or decreasing"
+    return d.to(torch.float32).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -285,9 +327,9 @@ class _Dopri5(torch.autograd.Function):
         acc = torch.empty(2 * max(kc, 1), dtype=torch.float64, device=dev) if keep else None
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        tarr = (C.c_double * T)(*meta["t_list"])
+        tarr = meta["t64"]
         _lib.check(L.gode_dopri5_fwd(
-            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), C.cast(tarr, C.c_void_p), B, D, H, T, C.byref(opts),
+            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
             meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
             _ptr(ckpt), _ptr(acc), (acc.data_ptr() + 8 * max(kc, 1)) if keep else None, _ptr(ws), ws_bytes, _stream()),
             "gode_dopri5_fwd")
@@ -306,8 +348,10 @@ class _Dopri5(torch.autograd.Function):
         meta, kc = ctx.meta, ctx.kc
         if ckpt is None:
             raise GodeError("dopri5 forward ran without checkpoints (inputs did not require grad)")
-        # the only host<->device sync of the backward: solver status (checkpoint overflow would silently truncate)
-        raise_for_status(ctx.log.status)
+        # No host sync by default (keeps fwd+bwd CUDA-graph capturable): a failed forward (status != 0, including
+        # checkpoint overflow) makes the backward kernel return NaN gradients; options['check'] raises eagerly.
+        if meta["check"]:
+            raise_for_status(ctx.log.status)
         T = meta["T"]
         _, B, D = ckpt.shape
         H = W1c.shape[0]
@@ -317,7 +361,7 @@ class _Dopri5(torch.autograd.Function):
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
         _lib.check(L.gode_dopri5_backprop_bwd(
-            _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), C.cast(ctx.tarr, C.c_void_p), B, D, H, T,
+            _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
             meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
             C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes, _stream()),
             "gode_dopri5_backprop_bwd")
@@ -367,16 +411,13 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         raise NotImplementedError("no sm_100a kernel compiled for ODEFunc(dim={}, dim_hidden={}) at precision {}; "
                                   "there is no fallback".format(D, H, prec_name))
     layout = _layout_code(options.get("layout", config.layout))
-    if t.device != y0.device and t.is_cuda:
+    if t.is_cuda and t.device != y0.device:
         warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
         t = t.to(y0.device)
     meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)))
 
     if method == "rk4":
-        t_inc, _ = _signed_times(t)  # asserts monotonicity; rk4 uses signed dt directly
-        dt = _rk4_dt(t, options)
-        if len(t) - 1 > _lib.MAX_HOST_STEPS and not dt.is_cuda:
-            dt = dt.to(y0.device)
+        dt = _rk4_dt(t, options, y0.device)
         return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
 
     if method == "dopri5":
@@ -384,10 +425,10 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
             raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
         if adjoint:
             raise NotImplementedError("dopri5 continuous adjoint is not built yet; use odeint (backprop-through-solver)")
-        th = t.detach().to("cpu", torch.float64)  # torchdiffeq: t -> float64 for adaptive solvers (syncs iff t on GPU)
-        th, fsign = _signed_times(th)
+        # torchdiffeq: t -> float64 for adaptive solvers; the grid rides in the launch parameters (syncs iff t is on GPU)
+        t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
-        meta["t_list"] = th.tolist()
+        meta["t64"] = t64
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
         return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
 

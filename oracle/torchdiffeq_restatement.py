@@ -446,11 +446,19 @@ def _dopri5_integrate(func, y0, t, rtol, atol, options):
     rk_y1, rk_f1 = y0, f0
     interp_coeff = [y0] * 5
 
+    # Test-only: replay a prescribed attempt-by-attempt dt sequence (e.g. the CUDA path's device log) so that
+    # gradient comparisons are made on the SAME discretisation.  The first attempt after the initial-step
+    # heuristic has an error estimate at fp32 rounding level, so its error_ratio (hence the next dt, through
+    # er^-1/5) is reduction-order noise and two correct implementations legitimately differ by a few percent.
+    replay = options.get("_replay_dt", None)
+
     for i in range(1, len(t)):
         next_t = t[i]
         n_steps = 0
         while next_t > rk_t1:
             assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
+            if replay is not None:
+                dt = torch.as_tensor(replay[len(log.dt)], dtype=tdtype, device=device)
             # _adaptive_step
             ys, fs, ts = rk_y1, rk_f1, rk_t1
             t1 = ts + dt
