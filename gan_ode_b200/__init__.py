@@ -7,6 +7,7 @@ or, without touching the reference files, `gan_ode_b200.install_shims()` registe
 """
 from .odeint import config, last_step_log, odeint, odeint_adjoint, recognise_field  # noqa: F401
 from ._lib import GodeError  # noqa: F401
+from .graphed import GraphedSolveStep  # noqa: F401
 
 __version__ = "0.1.0"
 

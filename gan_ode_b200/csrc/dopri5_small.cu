@@ -48,8 +48,7 @@ struct Dp5Args {
   GodeStepLog* log;
   double* att_t0; double* att_dt; float* att_er; uint8_t* att_acc;
   float* ckpt; double* acc_t0; double* acc_dt;
-  unsigned int* bar_counter;  // grid barrier, zeroed by the host wrapper
-  double* partials;           // [2][gridDim.x][4]
+  GridSyncWs gs;              // grid all-reduce slots, zeroed by the host wrapper
   GodeAdaptiveOpts o;
   int B, T, layout;
   double t[kMaxT];
@@ -57,52 +56,6 @@ struct Dp5Args {
 
 __device__ __forceinline__ size_t toff(int layout, int s, int b, int B, int T, int D) {
   return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
-}
-
-// ---- grid-wide deterministic sum of NV doubles --------------------------------------------------------------
-// Every CTA publishes its partial, all CTAs meet at a monotone-counter barrier, then every warp re-reads all
-// partials and adds them in the same fixed order, so all threads of the grid hold bit-identical totals and the
-// accept/reject branch is uniform without a broadcast.
-template <int NV, int WARPS>
-__device__ __forceinline__ void grid_sum(double (&v)[NV], double* s_part /* [WARPS][NV] */, const Dp5Args& p,
-                                         unsigned int& epoch, int& parity, int lane, int warp, int tid) {
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) s_part[warp * NV + k] = v[k];
-  }
-  __syncthreads();
-  double* mine = p.partials + ((size_t)parity * gridDim.x + blockIdx.x) * 4;
-  if (tid == 0) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      double s = s_part[k];
-      for (int w = 1; w < WARPS; ++w) s += s_part[w * NV + k];
-      __stcg(mine + k, s);
-    }
-    epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(p.bar_counter, 1u);
-    unsigned int seen;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.bar_counter) : "memory");
-    } while ((int)(seen - epoch) < 0);
-  }
-  __syncthreads();
-  const double* all = p.partials + (size_t)parity * gridDim.x * 4;
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    double s = 0.0;
-    for (int c = lane; c < (int)gridDim.x; c += 32) s += __ldcg(all + (size_t)c * 4 + k);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    v[k] = s;
-  }
-  parity ^= 1;
 }
 
 // misc.py::_optimal_step_size in fp64
@@ -129,7 +82,8 @@ template <int D, int H, int L, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_constant__ Dp5Args p) {
   using S = Shape<D, H, L>;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
-  __shared__ double s_part[WARPS * 4];
+  __shared__ float s_f[WARPS * kGsMaxVals];
+  __shared__ double s_d[kGsMaxVals];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
   FwdLines<D, H, L> ln;
   ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
@@ -141,7 +95,6 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   const double n_elem = (double)p.B * (double)D;
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
   unsigned int epoch = 0;
-  int parity = 0;
 
   float y0[S::DL], k[7][S::DL], hk[S::HL];
 #pragma unroll
@@ -169,7 +122,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         if (!isfinite(y0[c])) v[2] += 1.0;
       }
     }
-    grid_sum<3, WARPS>(v, s_part, p, epoch, parity, lane, warp, tid);
+    grid_allreduce_sum<3, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
     if (v[2] > 0.0) status |= GODE_ST_NONFINITE;
     if (p.o.first_step > 0.0) {
       dt = p.o.first_step;
@@ -187,7 +140,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         const float r = (f1[c] - k[0][c]) / scale[c];
         if (valid) v2[0] += (double)r * (double)r;
       }
-      grid_sum<1, WARPS>(v2, s_part, p, epoch, parity, lane, warp, tid);
+      grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, epoch, lane, warp);
       const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
@@ -228,7 +181,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       const float r = e / tol;
       if (valid) v[0] += (double)r * (double)r;
     }
-    grid_sum<1, WARPS>(v, s_part, p, epoch, parity, lane, warp, tid);
+    grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
     const float er = (float)sqrt(v[0] / n_elem);
     bool accept = er <= 1.f;
     if (dt > p.o.max_step) accept = false;
@@ -449,8 +402,6 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kDp5Warps = 4;
 
-static size_t dp5_partials_bytes(int grid) { return sizeof(double) * 2 * 4 * (size_t)grid; }
-
 template <int D, int H, int L>
 static int dp5_fwd_grid(int B) {
   const int per_cta = kDp5Warps * Shape<D, H, L>::G;
@@ -459,23 +410,20 @@ static int dp5_fwd_grid(int B) {
 
 size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   (void)D; (void)H;
-  // barrier counter (256 B) + double-buffered per-CTA partials; sized for the L=8 mapping (the densest we launch)
-  const int grid = dp5_fwd_grid<16, 16, 8>(B);
-  return 256 + dp5_partials_bytes(grid);
+  // grid all-reduce slots, sized for the L=8 mapping (the densest we launch)
+  return align256(grid_sync_bytes(dp5_fwd_grid<16, 16, 8>(B)));
 }
 
 template <int D, int H, int L>
 static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   const int grid = dp5_fwd_grid<D, H, L>(a.B);
-  if (ws_bytes < 256 + dp5_partials_bytes(grid)) return GODE_ERR_WORKSPACE;
+  if (ws_bytes < grid_sync_bytes(grid)) return GODE_ERR_WORKSPACE;
   auto kern = dopri5_fwd_kernel<D, H, L, kDp5Warps>;
-  int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kDp5Warps * 32, 0);
-  if (e != cudaSuccess) return -(1000 + (int)e);
-  if (grid > per_sm * sm_count()) return GODE_ERR_COOP;
-  a.bar_counter = reinterpret_cast<unsigned int*>(workspace);
-  a.partials = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
-  e = cudaMemsetAsync(workspace, 0, 256, st);
+  static int limit_cache = 0;
+  const int cap = coop_limit(kern, kDp5Warps * 32, 0, limit_cache);
+  if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
+  a.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   void* args[] = {(void*)&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDp5Warps * 32), args, 0, st);
@@ -487,22 +435,29 @@ template <int D, int H, int L>
 static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   using S = Shape<D, H, L>;
   constexpr int WARPS = 4;
-  const int per_cta = WARPS * S::G;
-  int grid = (a.B + per_cta - 1) / per_cta;
-  const int cap = bwd_grid_cap();
-  if (grid > cap) grid = cap;
-  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
-  a.ws.counter = reinterpret_cast<unsigned int*>(workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
-  const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P);
   auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS>;
+  const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P);
+  cudaError_t e;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(1000 + (int)e);
   }
-  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  static int limit_cache = 0;
+  int cap = coop_limit(kern, WARPS * 32, smem, limit_cache);
+  if (cap <= 0) return GODE_ERR_COOP;
+  if (cap > bwd_grid_cap()) cap = bwd_grid_cap();
+  const int per_cta = WARPS * S::G;
+  int grid = (a.B + per_cta - 1) / per_cta;
+  if (grid > cap) grid = cap;
+  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
+  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
+  a.ws.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
+  e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  void* args[] = {(void*)&a};
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }
 

@@ -25,11 +25,27 @@ inline int launch_status() {
   return e == cudaSuccess ? GODE_OK : -(1000 + (int)e);
 }
 
-// backward kernels keep parameter-gradient accumulators in registers and loop over their trajectories;
-// two 128-thread CTAs per SM.
+// backward kernels keep parameter-gradient accumulators in registers and loop over their trajectories; they are
+// launched cooperatively (grid barrier before the final cross-CTA reduction), at most two 128-thread CTAs per SM.
 inline int bwd_grid_cap() { return sm_count() * 2; }
 
-inline size_t bwd_workspace_bytes(int P) { return 256 + sizeof(float) * (size_t)P * (size_t)bwd_grid_cap(); }
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// [grid-sync slots | per-CTA partial rows]
+inline size_t bwd_workspace_bytes(int P) {
+  const int cap = bwd_grid_cap();
+  return align256(sizeof(unsigned long long) * 2 * 4 * (size_t)cap) + sizeof(float) * (size_t)P * (size_t)cap;
+}
+
+// co-resident CTA limit of a kernel (cached per instantiation; racing writers store the same value)
+template <class K>
+inline int coop_limit(K kern, int threads, size_t smem, int& cache) {
+  if (cache > 0) return cache;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem) != cudaSuccess || per_sm <= 0) return 0;
+  cache = per_sm * sm_count();
+  return cache;
+}
 
 // entry points of the per-family translation units
 int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,

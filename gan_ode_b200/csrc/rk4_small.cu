@@ -254,22 +254,29 @@ template <int D, int H, int L, bool ADJOINT>
 static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   constexpr int WARPS = 4;
   using S = Shape<D, H, L>;
-  const int per_cta = WARPS * S::G;
-  int grid = (a.B + per_cta - 1) / per_cta;
-  const int cap = bwd_grid_cap();
-  if (grid > cap) grid = cap;
-  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
-  a.ws.counter = reinterpret_cast<unsigned int*>(workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + 256);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
-  const size_t smem = bwd_smem_bytes<D, H, L, WARPS>();
   auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS> : rk4_backprop_bwd_kernel<D, H, L, WARPS>;
+  const size_t smem = bwd_smem_bytes<D, H, L, WARPS>();
+  cudaError_t e;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return -(1000 + (int)e);
   }
-  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  static int limit_cache = 0;
+  int cap = coop_limit(kern, WARPS * 32, smem, limit_cache);
+  if (cap <= 0) return GODE_ERR_COOP;
+  if (cap > bwd_grid_cap()) cap = bwd_grid_cap();
+  const int per_cta = WARPS * S::G;
+  int grid = (a.B + per_cta - 1) / per_cta;
+  if (grid > cap) grid = cap;
+  if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
+  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
+  a.ws.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
+  e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  void* args[] = {(void*)&a};
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }
 

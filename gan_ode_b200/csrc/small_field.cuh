@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "grid_sync.cuh"
 
 namespace gode {
 
@@ -274,12 +275,14 @@ __device__ __forceinline__ void regather(const BwdLines<D, H, L>& ln, int l, con
 
 // ---- deterministic reduction of GradAcc over the whole grid ---------------------------------------------------
 // 1. lanes with equal l (different trajectories of a warp): xor-shuffle tree
-// 2. warps of a CTA: shared memory, fixed order
-// 3. CTAs: per-CTA partial rows in the workspace; the last CTA to arrive sums them in CTA order and overwrites
-//    grad_params.  The order of every floating-point addition is fixed by (grid, block) alone -> bit-reproducible.
+// 2. warps of a CTA: shared memory, fixed order -> one partial row per CTA in the workspace
+// 3. grid barrier (cooperative launch), then the float4 columns of the partial matrix are dealt out to the CTAs:
+//    each CTA sums its columns over all rows with a fixed tree (thread r takes rows r, r+T, ...; shuffle tree; warps
+//    in order) and writes them.  All CTAs work in parallel, one or two loads per thread, and the order of every
+//    floating-point addition is fixed by (grid, block) alone -> bit-reproducible gradients.
 struct ReduceWs {
-  unsigned int* counter;  // zeroed by the host wrapper before launch
-  float* partials;        // [gridDim.x][P]
+  GridSyncWs gs;    // zeroed by the host wrapper before launch
+  float* partials;  // [gridDim.x][P]
 };
 
 template <int D, int H, int L, int WARPS>
@@ -288,6 +291,7 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
                                                    int warp, int tid) {
   using S = Shape<D, H, L>;
   constexpr int P = S::P;
+  constexpr int NT = WARPS * 32;
   const int l = lane % L;
 #pragma unroll
   for (int off = L; off < 32; off <<= 1) {
@@ -321,34 +325,37 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
   }
   __syncthreads();
   float* mine = ws.partials + (size_t)blockIdx.x * P;
-  for (int p = tid; p < P; p += WARPS * 32) {
+  for (int p = tid; p < P; p += NT) {
     float s = smem_red[p];
 #pragma unroll
     for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
-    mine[p] = s;
+    __stcg(mine + p, s);
   }
-  __threadfence();
-  __syncthreads();
-  __shared__ int s_is_last;
-  if (tid == 0) {
-    const unsigned ticket = atomicAdd(ws.counter, 1u);
-    s_is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (s_is_last) {
-    __threadfence();
-    const int nb = gridDim.x;
-    for (int p4 = tid; p4 < P / 4; p4 += WARPS * 32) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
-#pragma unroll 8
-      for (int b = 0; b < nb; ++b) {
-        const float4 v = __ldcg(col + (size_t)b * (P / 4));
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      reinterpret_cast<float4*>(grad_params)[p4] = s;
+  unsigned int epoch = 0;
+  grid_barrier<WARPS>(ws.gs, epoch, lane, warp);
+  const int nb = gridDim.x;
+  float4* s4 = reinterpret_cast<float4*>(smem_red);  // reuse: [WARPS] float4
+  for (int p4 = blockIdx.x; p4 < P / 4; p4 += nb) {
+    const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = tid; b < nb; b += NT) {
+      const float4 v = __ldcg(col + (size_t)b * (P / 4));
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    if (tid == 0) *ws.counter = 0u;  // leave the workspace reusable
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+    }
+    __syncthreads();
+    if (lane == 0) s4[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float4 t = s4[0];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) { t.x += s4[w].x; t.y += s4[w].y; t.z += s4[w].z; t.w += s4[w].w; }
+      reinterpret_cast<float4*>(grad_params)[p4] = t;
+    }
   }
 }
 

@@ -1,0 +1,96 @@
+"""CUDA-graph replay of one solve step (forward + backward + the host<->device copies around it).
+
+At the reference's shapes (D = H = 16, a few thousand trajectories) one fused solve is tens of microseconds of GPU
+time, so the host-side cost of *issuing* it (Python, autograd bookkeeping, two launches, two memsets, the copies)
+dominates unless the whole step is replayed from a graph.  `GraphedSolveStep` captures, once:
+
+    H2D   y0 (pinned host)  ->  device
+    fwd   odeint / odeint_adjoint (same kernels, same arguments as the eager call)
+    bwd   gradients w.r.t. y0 and the ODEFunc parameters for a given upstream gradient
+    [NCCL all-reduce of the flat parameter gradient when config.grad_allreduce is set]
+    D2H   flat parameter gradient (and optionally grad_y0 / the trajectory)  ->  pinned host
+
+and `run()` replays it with a single cudaGraphLaunch.  Parameters are read through their device addresses at replay
+time, so in-place optimiser updates are picked up; rebuilding is only needed if shapes or the time grid change.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import odeint as _api
+
+__all__ = ["GraphedSolveStep"]
+
+
+class GraphedSolveStep:
+    def __init__(self, func, batch: int, t: torch.Tensor, *, method: Optional[str] = None, rtol=1e-7, atol=1e-9,
+                 adjoint: bool = True, options: Optional[dict] = None, device=None,
+                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3):
+        W1, _, _, _ = _api.recognise_field(func)
+        D = W1.shape[1]
+        dev = torch.device(device) if device is not None else W1.device
+        assert dev.type == "cuda", "GraphedSolveStep needs the ODEFunc on a CUDA device"
+        self.func, self.t, self.device = func, t, dev
+        self.params = [p for p in _api.recognise_field(func)]
+        self._solve = _api.odeint_adjoint if adjoint else _api.odeint
+        self._kw = dict(method=method, rtol=rtol, atol=atol, options=options)
+        T = len(t)
+        n_param = sum(p.numel() for p in self.params)
+        self.read_back = tuple(read_back)
+        for name in self.read_back:
+            if name not in ("param_grads", "grad_y0", "traj"):
+                raise ValueError("read_back entries must be 'param_grads', 'grad_y0' or 'traj'")
+
+        # static buffers: pinned host side and device side
+        self.y0_host = torch.zeros(batch, D, dtype=torch.float32).pin_memory()
+        self.y0 = torch.zeros(batch, D, dtype=torch.float32, device=dev, requires_grad=True)
+        self.grad_traj = torch.zeros(T, batch, D, dtype=torch.float32, device=dev)
+        self.host = {}
+        if "param_grads" in self.read_back:
+            self.host["param_grads"] = torch.zeros(n_param, dtype=torch.float32).pin_memory()
+        if "grad_y0" in self.read_back:
+            self.host["grad_y0"] = torch.zeros(batch, D, dtype=torch.float32).pin_memory()
+        if "traj" in self.read_back:
+            self.host["traj"] = torch.zeros(T, batch, D, dtype=torch.float32).pin_memory()
+        self.traj = None
+        self.grads = None
+        self.log = None
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+        self.stream = torch.cuda.current_stream(dev)
+
+    def _body(self):
+        with torch.no_grad():
+            self.y0.copy_(self.y0_host, non_blocking=True)
+        sol = self._solve(self.func, self.y0, self.t, **self._kw)
+        self.log = _api.last_step_log() if (self._kw["method"] in (None, "dopri5")) else None
+        grads = torch.autograd.grad(sol, [self.y0] + self.params, self.grad_traj)
+        self.traj, self.grads = sol.detach(), grads
+        if "param_grads" in self.host:
+            self.host["param_grads"].copy_(torch.cat([g.reshape(-1) for g in grads[1:]]), non_blocking=True)
+        if "grad_y0" in self.host:
+            self.host["grad_y0"].copy_(grads[0], non_blocking=True)
+        if "traj" in self.host:
+            self.host["traj"].copy_(sol.detach(), non_blocking=True)
+
+    def run(self, y0_host: Optional[torch.Tensor] = None):
+        """Replay the step.  `y0_host` (optional) is copied into the pinned input buffer first; otherwise whatever the
+        caller wrote into `self.y0_host` is used.  Asynchronous: call `sync()` before reading `self.host[...]`."""
+        if y0_host is not None:
+            self.y0_host.copy_(y0_host)
+        self.graph.replay()
+
+    def sync(self):
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.host

@@ -11,11 +11,14 @@ t = torch.linspace(0, 1, 16).float()
 
 
 def timeit(fn, n=20, warm=5):
+    """GPU time of fn's kernels: the device is kept busy by a spin kernel while the host enqueues, so the two
+    events bracket device work only (no host launch gaps)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
     for a, b in evs:
+        torch.cuda._sleep(1000000)
         a.record(); fn(); b.record()
     torch.cuda.synchronize()
     ts = sorted(a.elapsed_time(b) for a, b in evs)

@@ -188,17 +188,20 @@ def _assert_same_steps(glog, rlog):
     assert abs(glog.dt0 - rlog.dt0) <= 1e-5 * abs(rlog.dt0)
     for n in range(len(glog.dt) - 1):
         assert abs(glog.dt[n + 1] - _controller(glog.dt[n], glog.error_ratio[n])) <= 1e-12 * glog.dt[n + 1]
+    # dt_{n+1} = dt_n * factor(er_n) with factor ~ er^-1/5 and er ~ dt^5: a relative difference d in dt shows up as
+    # ~5d in er and comes back as ~d in the next dt, plus 0.2x the relative difference of the error estimates
+    # themselves.  Where er is an fp32-rounding-level number (first step after the initial-step heuristic) that
+    # difference is O(1); everywhere else it is O(1e-4).  Bound the dt mismatch by that first-order propagation.
     tol = 1e-5
     for n, (a, b) in enumerate(zip(glog.dt, rlog.dt)):
-        assert abs(a - b) <= tol * abs(b), (n, a, b, tol)
+        d = abs(a - b) / abs(b)
+        assert d <= tol, (n, a, b, tol)
         eg, er = glog.error_ratio[n], rlog.error_ratio[n]
+        rel_e = abs(eg - er) / max(min(eg, er), 1e-30)
         if max(eg, er) >= ER_NOISE:
-            assert abs(eg - er) <= 1e-3 * er + 2e-4, (n, eg, er)
-            tol += 0.25 * abs(eg - er) / er
-        else:
-            # both are noise; dt_{n+1} ~ er^-1/5 then differs by a bounded factor unless capped at ifactor
-            tol += 0.25 * abs(eg - er) / max(min(eg, er), 1e-30) if min(eg, er) > (0.9 / 10) ** 5 else 0.0
-            tol = min(tol, 0.5)
+            assert rel_e <= 2e-3 + 8 * d, (n, eg, er, d)
+        capped = max(eg, er) <= (0.9 / 10) ** 5  # both hit ifactor = 10: next dt is exactly 10 dt
+        tol = min(0.5, 1e-5 + 1.5 * d + (0.0 if capped else 0.3 * rel_e))
 
 
 @pytest.mark.parametrize("B,scale", [(1, 1.0), (16, 1.0), (37, 4.0), (4096, 1.0), (4096, 4.0), (4096, 8.0)])
@@ -284,3 +287,28 @@ def test_unrecognised_field_raises():
         gode.odeint(clone_to(make_field(), DEV), torch.zeros(4, 16, device=DEV, dtype=torch.long), _t16())
     with pytest.raises(gode.GodeError):
         gode.odeint(make_field(), torch.randn(4, 16), _t16(), method="rk4")  # CPU tensors: no fallback
+
+
+# ---- CUDA-graph replay API -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("method,adjoint", [("rk4", True), ("dopri5", False)])
+def test_graphed_step_matches_eager(method, adjoint):
+    _need_gpu()
+    f = clone_to(make_field(seed=11), DEV)
+    t = _t16()
+    B = 256
+    kw = dict(method=method, rtol=1e-5, atol=1e-5)
+    gs = gode.GraphedSolveStep(f, B, t, adjoint=adjoint, read_back=("param_grads", "grad_y0", "traj"), **kw)
+    solve = gode.odeint_adjoint if adjoint else gode.odeint
+    for seed in (0, 1):  # replay twice with different host inputs
+        torch.manual_seed(seed)
+        y0 = torch.randn(B, 16)
+        g = torch.randn(16, B, 16)
+        gs.grad_traj.copy_(g)
+        gs.run(y0)
+        host = gs.sync()
+        y = y0.to(DEV).requires_grad_(True)
+        sol = solve(f, y, t, **kw)
+        grads = torch.autograd.grad(sol, [y] + list(f.parameters()), g.to(DEV))
+        assert torch.equal(host["traj"], sol.detach().cpu())
+        assert torch.equal(host["grad_y0"], grads[0].cpu())
+        assert torch.equal(host["param_grads"], torch.cat([x.reshape(-1) for x in grads[1:]]).cpu())
