@@ -422,7 +422,7 @@ static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
   static int limit_cache = 0;
   const int cap = coop_limit(kern, kDp5Warps * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
-  a.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  grid_sync_bind(a.gs, workspace);
   cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   void* args[] = {(void*)&a};
@@ -451,7 +451,7 @@ static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
   if (grid > cap) grid = cap;
   if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
   const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
-  a.ws.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  grid_sync_bind(a.ws.gs, workspace);
   a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
   e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);

@@ -34,7 +34,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // [grid-sync slots | per-CTA partial rows]
 inline size_t bwd_workspace_bytes(int P) {
   const int cap = bwd_grid_cap();
-  return align256(sizeof(unsigned long long) * 2 * 4 * (size_t)cap) + sizeof(float) * (size_t)P * (size_t)cap;
+  return align256(256 + sizeof(unsigned long long) * 2 * 4 * (size_t)cap) + sizeof(float) * (size_t)P * (size_t)cap;
 }
 
 // co-resident CTA limit of a kernel (cached per instantiation; racing writers store the same value)

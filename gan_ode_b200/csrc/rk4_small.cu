@@ -270,7 +270,7 @@ static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStre
   if (grid > cap) grid = cap;
   if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
   const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
-  a.ws.gs.slots = reinterpret_cast<unsigned long long*>(workspace);
+  grid_sync_bind(a.ws.gs, workspace);
   a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
   e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);

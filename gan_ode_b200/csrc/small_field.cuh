@@ -276,10 +276,9 @@ __device__ __forceinline__ void regather(const BwdLines<D, H, L>& ln, int l, con
 // ---- deterministic reduction of GradAcc over the whole grid ---------------------------------------------------
 // 1. lanes with equal l (different trajectories of a warp): xor-shuffle tree
 // 2. warps of a CTA: shared memory, fixed order -> one partial row per CTA in the workspace
-// 3. grid barrier (cooperative launch), then the float4 columns of the partial matrix are dealt out to the CTAs:
-//    each CTA sums its columns over all rows with a fixed tree (thread r takes rows r, r+T, ...; shuffle tree; warps
-//    in order) and writes them.  All CTAs work in parallel, one or two loads per thread, and the order of every
-//    floating-point addition is fixed by (grid, block) alone -> bit-reproducible gradients.
+// 3. grid barrier (cooperative launch), then the float4 columns of the partial matrix are dealt out to the warps of
+//    the grid: each warp sums its columns over all rows with a fixed tree and writes them.  All warps work in
+//    parallel and the order of every floating-point addition is fixed by (grid, block) alone -> bit-reproducible.
 struct ReduceWs {
   GridSyncWs gs;    // zeroed by the host wrapper before launch
   float* partials;  // [gridDim.x][P]
@@ -332,13 +331,15 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
     __stcg(mine + p, s);
   }
   unsigned int epoch = 0;
-  grid_barrier<WARPS>(ws.gs, epoch, lane, warp);
+  grid_barrier(ws.gs, epoch);
+  // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
+  // in order, then a shuffle tree.  No block-level synchronisation.
   const int nb = gridDim.x;
-  float4* s4 = reinterpret_cast<float4*>(smem_red);  // reuse: [WARPS] float4
-  for (int p4 = blockIdx.x; p4 < P / 4; p4 += nb) {
+  const int gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
+  for (int p4 = gw; p4 < P / 4; p4 += nw) {
     const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = tid; b < nb; b += NT) {
+    for (int b = lane; b < nb; b += 32) {
       const float4 v = __ldcg(col + (size_t)b * (P / 4));
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
@@ -347,15 +348,7 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
       s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
       s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
     }
-    __syncthreads();
-    if (lane == 0) s4[warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-      float4 t = s4[0];
-#pragma unroll
-      for (int w = 1; w < WARPS; ++w) { t.x += s4[w].x; t.y += s4[w].y; t.z += s4[w].z; t.w += s4[w].w; }
-      reinterpret_cast<float4*>(grad_params)[p4] = t;
-    }
+    if (lane == 0) reinterpret_cast<float4*>(grad_params)[p4] = s;
   }
 }
 

@@ -19,7 +19,9 @@ from typing import Optional, Sequence
 
 import torch
 
-from . import odeint as _api
+import importlib
+
+_api = importlib.import_module(__package__ + ".odeint")  # the module, not the re-exported function
 
 __all__ = ["GraphedSolveStep"]
 
