@@ -14,8 +14,9 @@
 //     single st.relaxed.gpu (8-byte naturally aligned scalar store = single-copy atomic: data and flag cannot be
 //     seen torn or reordered, so no fence and no atomic); warp 0 of every CTA polls all words.  Two L2 round trips,
 //     but the polling is O(CTAs^2) and collapses beyond ~48 CTAs.
-//   * counter: every CTA stores its fp32 partial, then red.release.gpu on one counter; one lane polls that single
-//     word with ld.acquire.gpu; then the partials are read with all loads in flight.
+//   * counter: the same tagged words, plus a relaxed red on one counter that one lane polls as a HINT that everyone
+//     has published; then the tagged words are read with all loads in flight (re-polling any that lag).  No
+//     release/acquire anywhere, so arrivals do not wait for the CTA's outstanding output stores.
 //
 // Both are double-buffered by epoch parity: a CTA can only publish epoch e+2 into the buffer of epoch e after it
 // completed epoch e+1, which needs every CTA's arrival at e+1, which each CTA signals only after it finished reading
@@ -117,27 +118,41 @@ __device__ __forceinline__ void grid_allreduce_sum(double (&v)[NV], float* s_f, 
         if (lane == 0) s_d[k] = s;
       }
     } else {
-      float* buf = reinterpret_cast<float*>(ws.slots) + (size_t)(epoch & 1u) * kGsMaxVals * grid;
-      if (lane < NV) __stcg(buf + (size_t)lane * grid + blockIdx.x, mine);
-      __syncwarp();
+      // Same tagged words, but the O(CTAs^2) polling is replaced by ONE hot word: a relaxed counter that is only a
+      // hint that everybody has probably published.  Correctness still rests on the tags alone, so nothing here is a
+      // release/acquire and the arrival never waits for the CTA's outstanding trajectory/checkpoint stores to drain
+      // (a red.release did, and cost ~3 us per attempt inside the solver).
+      unsigned long long* buf = ws.slots + (size_t)(epoch & 1u) * kGsMaxVals * grid;
+      if (lane < NV)
+        st_relaxed_u64(buf + (size_t)lane * grid + blockIdx.x,
+                       (unsigned long long)__float_as_uint(mine) | ((unsigned long long)epoch << 32));
       if (lane == 0) {
-        arrive_counter(ws.counter);  // release: cumulative over the NV stores above (ordered by __syncwarp)
-        wait_counter(ws.counter, epoch * (unsigned int)grid);
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ws.counter) : "memory");
+        const unsigned int target = epoch * (unsigned int)grid;
+        unsigned int seen;
+        do {
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ws.counter) : "memory");
+        } while ((int)(seen - target) < 0);
       }
       __syncwarp();
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        const float* col = buf + (size_t)k * grid;
-        float x[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int c = u * 32 + lane;
-          x[u] = c < grid ? __ldcg(col + c) : 0.f;
-        }
+        const unsigned long long* col = buf + (size_t)k * grid;
         double s = 0.0;
+        for (int c0 = 0; c0 < grid; c0 += 256) {
+          unsigned long long x[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) s += (double)x[u];
-        for (int c = 256 + lane; c < grid; c += 32) s += (double)__ldcg(col + c);
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            x[u] = c < grid ? ld_relaxed_u64(col + c) : ((unsigned long long)epoch << 32);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + u * 32 + lane;
+            while (c < grid && (unsigned int)(x[u] >> 32) != epoch) x[u] = ld_relaxed_u64(col + c);
+            s += (double)__uint_as_float((unsigned int)x[u]);
+          }
+        }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) s_d[k] = s;
