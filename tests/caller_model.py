@@ -1,0 +1,35 @@
+"""Stand-in for the reference's caller of the hot path, for tests that must run where /root/reference is absent
+(the GPU box).  Restates ONLY the latent-motion part of VideoGeneratorMNISTODE (models/mocogan_ode.py:114-148):
+pre-MLP `linear` (:123-131), `ode_fn` (:118-121) and `sample_z_m` (:133-148), with the solver imported exactly the
+way the reference imports it (`from torchdiffeq import odeint_adjoint as odeint`, models/mocogan_ode.py:4) so the
+shim is what gets exercised.  tests/test_reference_dropin_cpu.py checks this stand-in against the real reference
+file (same state_dict keys, same output for the same seed) whenever /root/reference exists."""
+import torch
+import torch.nn as nn
+
+
+class ODEFunc(nn.Module):  # models/mocogan_ode.py:6-17
+    def __init__(self, dim, dim_hidden):
+        super().__init__()
+        self.fn = nn.Sequential(nn.Linear(dim, dim_hidden), nn.Tanh(), nn.Linear(dim_hidden, dim))
+
+    def forward(self, t, x):
+        return self.fn(x)
+
+
+class LatentMotionODE(nn.Module):
+    def __init__(self, dim_z_motion=16, video_length=16, dim_hidden=None):
+        super().__init__()
+        self.dim_z_motion, self.video_length = dim_z_motion, video_length
+        self.ode_fn = ODEFunc(dim=dim_z_motion, dim_hidden=dim_hidden or dim_z_motion)
+        self.linear = nn.Sequential(nn.Linear(dim_z_motion, 64), nn.LeakyReLU(0.2),
+                                    nn.Linear(64, dim_z_motion), nn.LeakyReLU(0.2))
+
+    def sample_z_m(self, num_samples, video_len=None, noise=None):
+        from torchdiffeq import odeint_adjoint as odeint  # resolved through sys.modules (shim or oracle)
+        video_len = video_len if video_len is not None else self.video_length
+        x = torch.randn(num_samples, self.dim_z_motion) if noise is None else noise
+        x = x.to(next(self.parameters()).device)
+        x = self.linear(x)
+        z_m_t = odeint(self.ode_fn, x, torch.linspace(0, 1, video_len).float(), method='rk4')
+        return z_m_t.transpose(0, 1).reshape(-1, self.dim_z_motion)
