@@ -65,6 +65,11 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
                               size_t ws_bytes, cudaStream_t st);
 
+int tc_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+               int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,
+               cudaStream_t st);
+
 inline bool small_field_shape(int D, int H) { return D == 16 && H == 16; }
+inline bool tc_shape(int D, int H) { return D == 16 && H == 16; }
 
 }  // namespace gode

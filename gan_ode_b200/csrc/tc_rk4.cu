@@ -1,0 +1,274 @@
+// tc_rk4.cu — fixed-grid RK4 (3/8 rule) forward with the MLP contractions on tcgen05 tensor cores.
+//
+// Tile kernel: one CTA = 128 threads = 128 trajectories; thread r owns trajectory row r for the whole time loop, so
+// every Runge–Kutta vector (y, k-combinations) stays in its registers.  Per stage:
+//
+//   u (registers) --cvt--> A1 (smem, canonical K-major)  --tcgen05.mma x W1^T--> TMEM[:, 0:H)  --tcgen05.ld--> registers
+//     +b1, tanh.approx --cvt--> A2 (smem)                --tcgen05.mma x W2^T--> TMEM[:, H:H+D) --tcgen05.ld--> +b2 = k
+//
+// Accumulators live in TMEM (fp32); operands are TF32 (round-to-nearest on store) or BF16.  The weights arrive once
+// per CTA by TMA bulk copies (cp.async.bulk -> mbarrier complete_tx) and are re-tiled/converted in shared memory into
+// the UMMA no-swizzle layout; they stay resident while the CTA walks its tiles (persistent grid-stride loop).
+// Several CTAs share an SM (32 TMEM columns and ~20 KB shared memory each), so one CTA's MMA/TMEM round trip overlaps
+// the others' tanh/pack epilogues.
+// Tolerance of this mode: <= 2e-3 relative vs torchdiffeq (BASELINE.json north_star).
+#include "launch.h"
+#include "tc_common.cuh"
+
+namespace gode {
+
+constexpr float kThird = 0.33333334f;
+
+struct TcRk4Args {
+  const float *y0, *W1, *b1, *W2, *b2;
+  float* traj;
+  const float* dt_dev;
+  int B, T, layout;
+  float dt_val[GODE_MAX_HOST_STEPS];
+};
+
+template <int D, int H, bool TF32>
+struct TcShape {
+  static constexpr int ELT = TF32 ? 4 : 2;      // bytes per operand element
+  static constexpr int TPC = 16 / ELT;          // elements per 16-byte chunk
+  static constexpr int KC1 = D / TPC;           // 16-byte K chunks of layer 1 (K = D)
+  static constexpr int KC2 = H / TPC;           // layer 2 (K = H)
+  static constexpr int NM1 = KC1 / 2, NM2 = KC2 / 2;  // MMAs per layer (each eats 32 bytes of K)
+  static constexpr int TILE = 128;
+  static constexpr int P = H * D + H + D * H + D;
+  static constexpr uint32_t NCOLS = (H + D <= 32) ? 32 : (H + D <= 64) ? 64 : (H + D <= 128) ? 128 : (H + D <= 256) ? 256 : 512;
+  // shared memory carve-up (bytes)
+  static constexpr int OFF_RAW = 0;                               // fp32 [W1|b1|W2|b2] as bulk-copied
+  static constexpr int OFF_B1 = OFF_RAW + ((P * 4 + 127) / 128) * 128;
+  static constexpr int OFF_B2 = OFF_B1 + H * D * ELT;
+  static constexpr int OFF_A1 = OFF_B2 + D * H * ELT;
+  static constexpr int OFF_A2 = OFF_A1 + TILE * D * ELT;
+  static constexpr int OFF_BAR = OFF_A2 + TILE * H * ELT;
+  static constexpr int BYTES = OFF_BAR + 64;
+  static_assert(D % 16 == 0 && H % 16 == 0, "tensor-core tile kernels need D, H multiples of 16");
+  static_assert(H + D <= 512, "TMEM has 512 columns");
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// write one 16-byte K chunk of a row-owned operand row: elements v[0..TPC)
+template <bool TF32>
+__device__ __forceinline__ void store_chunk(unsigned char* dst, const float* v) {
+  uint4 q;
+  if constexpr (TF32) {
+    q = make_uint4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+  } else {
+    q = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                   tc::pack_bf16x2(v[6], v[7]));
+  }
+  *reinterpret_cast<uint4*>(dst) = q;
+}
+
+__device__ __forceinline__ size_t tc_traj_off(int layout, int s, int b, int B, int T, int D) {
+  return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
+}
+
+template <int D, int H, bool TF32>
+__global__ void __launch_bounds__(128) tc_rk4_fwd_kernel(const __grid_constant__ TcRk4Args p) {
+  using S = TcShape<D, H, TF32>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* raw = reinterpret_cast<float*>(smem + S::OFF_RAW);
+  const float* b1s = raw + H * D;
+  const float* b2s = raw + H * D + H + D * H;
+  unsigned char* B1 = smem + S::OFF_B1;
+  unsigned char* B2 = smem + S::OFF_B2;
+  unsigned char* A1 = smem + S::OFF_A1;
+  unsigned char* A2 = smem + S::OFF_A2;
+  uint64_t* mbar_w = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* mbar_m = mbar_w + 1;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_w + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (warp == 0) tc::tmem_alloc(s_tmem, S::NCOLS);
+  if (tid == 0) {
+    tc::mbar_init(mbar_w, 1);
+    tc::mbar_init(mbar_m, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *s_tmem;
+  const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
+
+  // weights: TMA bulk copies, once per CTA
+  if (tid == 0) {
+    tc::mbar_expect_tx(mbar_w, S::P * 4);
+    tc::tma_bulk_g2s(raw, p.W1, H * D * 4, mbar_w);
+    tc::tma_bulk_g2s(raw + H * D, p.b1, H * 4, mbar_w);
+    tc::tma_bulk_g2s(raw + H * D + H, p.W2, D * H * 4, mbar_w);
+    tc::tma_bulk_g2s(raw + H * D + H + D * H, p.b2, D * 4, mbar_w);
+  }
+  tc::mbar_wait(mbar_w, 0);
+  // re-tile into the UMMA layout [k_chunk][n][16 B] (K-major B operands: B1 = W1 (N=H,K=D), B2 = W2 (N=D,K=H))
+  for (int idx = tid; idx < H * S::KC1; idx += 128) {
+    const int n = idx % H, kc = idx / H;
+    store_chunk<TF32>(B1 + (size_t)(kc * H + n) * 16, raw + n * D + kc * S::TPC);
+  }
+  for (int idx = tid; idx < D * S::KC2; idx += 128) {
+    const int n = idx % D, kc = idx / D;
+    store_chunk<TF32>(B2 + (size_t)(kc * D + n) * 16, raw + H * D + H + n * H + kc * S::TPC);
+  }
+  tc::fence_async_smem();
+  __syncthreads();
+
+  constexpr uint32_t kFmt = TF32 ? tc::kFmtTF32 : tc::kFmtBF16;
+  constexpr uint32_t idesc1 = tc::make_idesc(kFmt, 128, H);
+  constexpr uint32_t idesc2 = tc::make_idesc(kFmt, 128, D);
+  const uint64_t dA1 = tc::make_smem_desc(tc::smem_u32(A1), S::TILE * 16, 128);
+  const uint64_t dA2 = tc::make_smem_desc(tc::smem_u32(A2), S::TILE * 16, 128);
+  const uint64_t dB1 = tc::make_smem_desc(tc::smem_u32(B1), H * 16, 128);
+  const uint64_t dB2 = tc::make_smem_desc(tc::smem_u32(B2), D * 16, 128);
+  uint32_t phase = 0;
+
+  auto feval = [&](const float(&u)[D], float(&f)[D]) {
+#pragma unroll
+    for (int c = 0; c < S::KC1; ++c) store_chunk<TF32>(A1 + (size_t)(c * S::TILE + tid) * 16, &u[c * S::TPC]);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < S::NM1; ++j)
+        tc::mma_ss<TF32>(tmem, dA1 + (uint64_t)((2 * j * S::TILE * 16) >> 4), dB1 + (uint64_t)((2 * j * H * 16) >> 4), idesc1, j > 0);
+      tc::mma_commit(mbar_m);
+    }
+    tc::mbar_wait(mbar_m, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int cb = 0; cb < H / 16; ++cb) {
+      float z[16];
+      tc::tmem_ld16(my_tmem + cb * 16, z);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(b1s + cb * 16 + i);
+        z[i] = tc::tanh_approx(z[i] + b.x); z[i + 1] = tc::tanh_approx(z[i + 1] + b.y);
+        z[i + 2] = tc::tanh_approx(z[i + 2] + b.z); z[i + 3] = tc::tanh_approx(z[i + 3] + b.w);
+      }
+#pragma unroll
+      for (int c = 0; c < 16 / S::TPC; ++c)
+        store_chunk<TF32>(A2 + (size_t)((cb * (16 / S::TPC) + c) * S::TILE + tid) * 16, &z[c * S::TPC]);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (int j = 0; j < S::NM2; ++j)
+        tc::mma_ss<TF32>(tmem + H, dA2 + (uint64_t)((2 * j * S::TILE * 16) >> 4), dB2 + (uint64_t)((2 * j * D * 16) >> 4), idesc2, j > 0);
+      tc::mma_commit(mbar_m);
+    }
+    tc::mbar_wait(mbar_m, phase);
+    phase ^= 1;
+    tc::fence_after_sync();
+#pragma unroll
+    for (int cb = 0; cb < D / 16; ++cb) {
+      float z[16];
+      tc::tmem_ld16(my_tmem + H + cb * 16, z);
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(b2s + cb * 16 + i);
+        f[cb * 16 + i] = z[i] + b.x; f[cb * 16 + i + 1] = z[i + 1] + b.y;
+        f[cb * 16 + i + 2] = z[i + 2] + b.z; f[cb * 16 + i + 3] = z[i + 3] + b.w;
+      }
+    }
+  };
+
+  const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
+  const int ntiles = (p.B + S::TILE - 1) / S::TILE;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile * S::TILE + tid;
+    const bool valid = b < p.B;
+    float y[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) y[i] = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int i = 0; i < D; i += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(p.y0 + (size_t)b * D + i);
+        y[i] = q.x; y[i + 1] = q.y; y[i + 2] = q.z; y[i + 3] = q.w;
+      }
+      float* o = p.traj + tc_traj_off(p.layout, 0, b, p.B, p.T, D);
+#pragma unroll
+      for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+    }
+    for (int s = 0; s + 1 < p.T; ++s) {
+      const float dt = dtp[s];
+      // 3/8 rule with running combinations: after k2 only v = k1 - k2 and acc = k1 + 3 k2 are needed
+      float k[D], u[D], v[D], acc[D];
+      feval(y, k);  // k1
+#pragma unroll
+      for (int i = 0; i < D; ++i) { u[i] = y[i] + dt * k[i] * kThird; v[i] = k[i]; acc[i] = k[i]; }
+      feval(u, k);  // k2
+#pragma unroll
+      for (int i = 0; i < D; ++i) { u[i] = y[i] + dt * (k[i] - v[i] * kThird); v[i] = v[i] - k[i]; acc[i] += 3.f * k[i]; }
+      feval(u, k);  // k3
+#pragma unroll
+      for (int i = 0; i < D; ++i) { u[i] = y[i] + dt * (v[i] + k[i]); acc[i] += 3.f * k[i]; }
+      feval(u, k);  // k4
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[i] = y[i] + (acc[i] + k[i]) * dt * 0.125f;
+      if (valid) {
+        float* o = p.traj + tc_traj_off(p.layout, s + 1, b, p.B, p.T, D);
+#pragma unroll
+        for (int i = 0; i < D; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+      }
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, S::NCOLS);
+}
+
+template <int D, int H, bool TF32>
+static int launch_tc_rk4_fwd(TcRk4Args& a, cudaStream_t st) {
+  using S = TcShape<D, H, TF32>;
+  auto kern = tc_rk4_fwd_kernel<D, H, TF32>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
+  if (e != cudaSuccess) return -(1000 + (int)e);
+  static int per_sm_cache = 0;
+  if (per_sm_cache <= 0) {
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, S::BYTES);
+    if (e != cudaSuccess) return -(1000 + (int)e);
+    const int tmem_limit = 512 / (int)S::NCOLS;  // TMEM columns are a per-SM resource the occupancy API does not see
+    per_sm_cache = per_sm < tmem_limit ? per_sm : tmem_limit;
+    if (per_sm_cache < 1) per_sm_cache = 1;
+  }
+  const int ntiles = (a.B + S::TILE - 1) / S::TILE;
+  int grid = per_sm_cache * sm_count();
+  if (grid > ntiles) grid = ntiles;
+  kern<<<grid, 128, S::BYTES, st>>>(a);
+  return launch_status();
+}
+
+int tc_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+               int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,
+               cudaStream_t st) {
+  TcRk4Args a{};
+  a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.B = B; a.T = T; a.layout = out_layout;
+  if (dt_on_device) {
+    a.dt_dev = dt;
+  } else {
+    if (T - 1 > GODE_MAX_HOST_STEPS) return GODE_ERR_T_TOO_LONG;
+    for (int i = 0; i < T - 1; ++i) a.dt_val[i] = dt[i];
+  }
+  const bool tf32 = precision == GODE_PREC_TF32;
+  if (D == 16 && H == 16) return tf32 ? launch_tc_rk4_fwd<16, 16, true>(a, st) : launch_tc_rk4_fwd<16, 16, false>(a, st);
+  return GODE_ERR_SHAPE;
+}
+
+}  // namespace gode
