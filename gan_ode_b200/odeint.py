@@ -206,8 +206,10 @@ class _Rk4(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
+        # The backward always runs the FP32 kernels: after a tf32/bf16 forward they re-solve from the stored (tensor-
+        # core) trajectory, which keeps the gradient inside the 2e-3 budget of that mode.  (Tensor-core VJP: next.)
         rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
-                dt_dev, B, D, H, T, meta["precision"], meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
+                dt_dev, B, D, H, T, _lib.PREC["fp32"], meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
                 ws.data_ptr(), ws_bytes, _stream())
         if rc:
             _lib.check(rc, "gode_rk4_bwd")
@@ -407,7 +409,7 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
     if prec_name not in _lib.PREC:
         raise ValueError("options['precision'] must be one of {}".format(sorted(_lib.PREC)))
     prec = _lib.PREC[prec_name]
-    if not _lib.lib().gode_supported(D, H, prec):
+    if not _lib.lib().gode_supported(D, H, prec) or not _lib.lib().gode_supported(D, H, _lib.PREC["fp32"]):
         raise NotImplementedError("no sm_100a kernel compiled for ODEFunc(dim={}, dim_hidden={}) at precision {}; "
                                   "there is no fallback".format(D, H, prec_name))
     layout = _layout_code(options.get("layout", config.layout))

@@ -386,3 +386,54 @@ def test_rk4_random_grids_property():
             ref = tdq.odeint(f, y0, t, method="rk4")
             out = gode.odeint(clone_to(f, DEV), y0.to(DEV), t, method="rk4", options={"layout": "btd" if trial % 2 else "tbd"})
         assert rel_err(out, ref) <= TOL, (trial, B, T)
+
+
+# ---- tensor-core (tcgen05) mode: <= 2e-3 relative (BASELINE.json north_star) -------------------------------------------
+TC_TOL = 2e-3
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+@pytest.mark.parametrize("B", [1, 37, 128, 129, 4096])
+def test_rk4_tensor_core_forward_matches_oracle(precision, B):
+    _need_gpu()
+    f = make_field(seed=B + 7)
+    y0 = torch.randn(B, 16)
+    t = _t16()
+    with torch.no_grad():
+        ref = tdq.odeint(f, y0, t, method="rk4")
+        out = gode.odeint(clone_to(f, DEV), y0.to(DEV), t, method="rk4",
+                          options={"precision": precision, "layout": "btd" if B % 2 else "tbd"})
+    assert torch.equal(out[0].cpu(), y0)
+    e = rel_err(out, ref)
+    assert e <= TC_TOL, e
+    assert e > 1e-7  # it really is the reduced-precision path
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_rk4_tensor_core_stiffer_field_and_grids(precision):
+    _need_gpu()
+    f = make_field(seed=21, scale=3.0)
+    y0 = torch.randn(300, 16)
+    for t in (torch.linspace(0, 1, 16), torch.tensor([0.0, 0.2, 0.25, 1.0]), torch.linspace(1, 0, 7)):
+        with torch.no_grad():
+            ref = tdq.odeint(f, y0, t, method="rk4")
+            out = gode.odeint(clone_to(f, DEV), y0.to(DEV), t, method="rk4", options={"precision": precision})
+        assert rel_err(out, ref) <= TC_TOL
+
+
+@pytest.mark.parametrize("precision", ["tf32", "bf16"])
+def test_rk4_tensor_core_forward_with_adjoint_gradients(precision):
+    _need_gpu()
+    f = make_field(seed=33)
+    t = _t16()
+    y0 = torch.randn(512, 16)
+    g = torch.randn(16, 512, 16)
+
+    def run(fn, field, y, gg, **k):
+        y = y.clone().requires_grad_(True)
+        return torch.autograd.grad((fn(field, y, t, method="rk4", **k) * gg).sum(), [y] + list(field.parameters()))
+
+    ref = run(tdq.odeint_adjoint, f, y0, g)
+    out = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"precision": precision})
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) <= TC_TOL
