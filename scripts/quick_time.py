@@ -35,6 +35,11 @@ for B in (16, 1024, 4096, 65536, 1048576):
     t_a = timeit(lambda: torch.autograd.grad(sol, [y0r] + list(f.parameters()), g, retain_graph=True))
     sol2 = gode.odeint(f, y0r, t, method="rk4")
     t_b = timeit(lambda: torch.autograd.grad(sol2, [y0r] + list(f.parameters()), g, retain_graph=True))
+    with torch.no_grad():
+        t_tf = timeit(lambda: gode.odeint(f, y0, t, method="rk4", options={"precision": "tf32"}))
+        t_bf = timeit(lambda: gode.odeint(f, y0, t, method="rk4", options={"precision": "bf16"}))
+    print("B=%8d rk4 fwd fp32 %9.1f us | tf32 %9.1f us | bf16 %9.1f us  -> fwd traj-steps/s fp32 %.3e tf32 %.3e bf16 %.3e" % (
+        B, t_f, t_tf, t_bf, B * 15 / (t_f * 1e-6), B * 15 / (t_tf * 1e-6), B * 15 / (t_bf * 1e-6)), flush=True)
     line = "B=%8d rk4 fwd %9.1f us  adjoint bwd %9.1f us  backprop bwd %9.1f us | fwd+adj %.3e traj-steps/s" % (
         B, t_f, t_a, t_b, B * 15 / ((t_f + t_a) * 1e-6))
     if B <= 4096:
