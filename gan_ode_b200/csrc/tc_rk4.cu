@@ -73,7 +73,7 @@ __device__ __forceinline__ size_t tc_traj_off(int layout, int s, int b, int B, i
 }
 
 template <int D, int H, bool TF32>
-__global__ void __launch_bounds__(128) tc_rk4_fwd_kernel(const __grid_constant__ TcRk4Args p) {
+__global__ void __launch_bounds__(128, 5) tc_rk4_fwd_kernel(const __grid_constant__ TcRk4Args p) {
   using S = TcShape<D, H, TF32>;
   extern __shared__ __align__(128) unsigned char smem[];
   float* raw = reinterpret_cast<float*>(smem + S::OFF_RAW);
@@ -239,17 +239,12 @@ static int launch_tc_rk4_fwd(TcRk4Args& a, cudaStream_t st) {
   auto kern = tc_rk4_fwd_kernel<D, H, TF32>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES);
   if (e != cudaSuccess) return -(1000 + (int)e);
-  static int per_sm_cache = 0;
-  if (per_sm_cache <= 0) {
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, S::BYTES);
-    if (e != cudaSuccess) return -(1000 + (int)e);
-    const int tmem_limit = 512 / (int)S::NCOLS;  // TMEM columns are a per-SM resource the occupancy API does not see
-    per_sm_cache = per_sm < tmem_limit ? per_sm : tmem_limit;
-    if (per_sm_cache < 1) per_sm_cache = 1;
-  }
+  // Persistent grid: enough CTAs to fill every SM to its register/TMEM limit (<= 96 registers -> 5 CTAs of 128
+  // threads; 32 TMEM columns each).  Not a cooperative launch, so over-subscription would only queue CTAs.
+  constexpr int kCtasPerSm = 5;
+  static_assert(kCtasPerSm * (int)S::NCOLS <= 512, "TMEM columns are a per-SM resource");
   const int ntiles = (a.B + S::TILE - 1) / S::TILE;
-  int grid = per_sm_cache * sm_count();
+  int grid = kCtasPerSm * sm_count();
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, 128, S::BYTES, st>>>(a);
   return launch_status();
