@@ -425,8 +425,10 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
     if method == "dopri5":
         if prec != _lib.PREC["fp32"]:
             raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
-        if adjoint:
-            raise NotImplementedError("dopri5 continuous adjoint is not built yet; use odeint (backprop-through-solver)")
+        # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): the gradient is computed by
+        # reverse-mode through the recorded accepted steps (the DISCRETE adjoint of the forward solve) instead of
+        # torchdiffeq's continuous adjoint re-solve; the two agree to O(tolerance).  The continuous dopri5 adjoint
+        # kernel is listed in DESIGN.md §8.
         # torchdiffeq: t -> float64 for adaptive solvers; the grid rides in the launch parameters (syncs iff t is on GPU)
         t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
@@ -448,8 +450,9 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
 def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None,
                    adjoint_rtol=None, adjoint_atol=None, adjoint_method=None, adjoint_options=None,
                    adjoint_params=None):
-    """torchdiffeq.odeint_adjoint for the reference's ODEFunc: the backward pass is the continuous adjoint re-solved
-    per output interval with the same method (adjoint.py), fused into one kernel."""
+    """torchdiffeq.odeint_adjoint for the reference's ODEFunc.  method='rk4': the backward pass is torchdiffeq's
+    continuous adjoint re-solved per output interval with the same method (adjoint.py), fused into one kernel.
+    method='dopri5' (default): forward as odeint; backward = discrete adjoint through the recorded steps (see _solve)."""
     if event_fn is not None:
         raise NotImplementedError("event handling is not on the gan-ode hot path")
     if adjoint_params is None and not isinstance(func, nn.Module):

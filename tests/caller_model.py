@@ -33,3 +33,27 @@ class LatentMotionODE(nn.Module):
         x = self.linear(x)
         z_m_t = odeint(self.ode_fn, x, torch.linspace(0, 1, video_len).float(), method='rk4')
         return z_m_t.transpose(0, 1).reshape(-1, self.dim_z_motion)
+
+
+class LatentMotionODERNN(nn.Module):
+    """ODE-RNN sampler: models/mocogan_ode_rnn.py:21-54 (+ models/mocogan.py:198 GRUCell, :297-301 noise sources).
+    Per frame: h' = odeint(ode_fn, h, tensor([0,1]))[-1] with torchdiffeq DEFAULTS (dopri5, rtol 1e-7, atol 1e-9),
+    then h = GRUCell(e_t, h').  `h0` / `eps` may be injected so runs are repeatable."""
+
+    def __init__(self, dim_z_motion=16, video_length=16):
+        super().__init__()
+        self.dim_z_motion, self.video_length = dim_z_motion, video_length
+        self.recurrent = nn.GRUCell(dim_z_motion, dim_z_motion)
+        self.ode_fn = ODEFunc(dim=dim_z_motion, dim_hidden=dim_z_motion)
+
+    def sample_z_m(self, num_samples, video_len=None, h0=None, eps=None, **solver_kw):
+        from torchdiffeq import odeint_adjoint as odeint
+        video_len = video_len if video_len is not None else self.video_length
+        dev = next(self.parameters()).device
+        h_t = [torch.randn(num_samples, self.dim_z_motion, device=dev) if h0 is None else h0.to(dev)]
+        for frame_num in range(video_len):
+            e_t = torch.randn(num_samples, self.dim_z_motion, device=dev) if eps is None else eps[frame_num].to(dev)
+            h_t_prime = odeint(self.ode_fn, h_t[-1], torch.tensor([0, 1]).float(), **solver_kw)[-1]
+            h_t.append(self.recurrent(e_t, h_t_prime))
+        z_m_t = [h_k.view(-1, 1, self.dim_z_motion) for h_k in h_t]
+        return torch.cat(z_m_t[1:], dim=1).view(-1, self.dim_z_motion)

@@ -440,3 +440,55 @@ def test_rk4_tensor_core_forward_with_adjoint_gradients(precision):
     out = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"precision": precision})
     for a, b in zip(out, ref):
         assert rel_err(a, b) <= TC_TOL
+
+
+# ---- ODE-RNN call path (a6): reference loop unchanged, dopri5 default tolerances, GRU jump in PyTorch ------------------
+def test_odernn_caller_through_shim_matches_oracle(monkeypatch):
+    _need_gpu()
+    import sys
+    import types
+    from tests.caller_model import LatentMotionODERNN
+
+    torch.manual_seed(0)
+    cpu_model = LatentMotionODERNN(16, 6)
+    gpu_model = LatentMotionODERNN(16, 6)
+    gpu_model.load_state_dict(cpu_model.state_dict())
+    gpu_model.to(DEV)
+    h0, eps, w = torch.randn(24, 16), torch.randn(6, 24, 16), torch.randn(24 * 6, 16)
+
+    shim = types.ModuleType("torchdiffeq")
+    shim.odeint, shim.odeint_adjoint = tdq.odeint, tdq.odeint_adjoint
+    monkeypatch.setitem(sys.modules, "torchdiffeq", shim)
+    ref = cpu_model.sample_z_m(24, h0=h0, eps=eps)  # continuous adjoint, reference default tolerances
+    (ref * w).sum().backward()
+
+    monkeypatch.delitem(sys.modules, "torchdiffeq")
+    gode.install_shims()
+    try:
+        out = gpu_model.sample_z_m(24, h0=h0, eps=eps)
+        (out * w.to(DEV)).sum().backward()
+    finally:
+        sys.modules.pop("torchdiffeq", None)
+    assert out.shape == (144, 16)
+    assert rel_err(out, ref) <= 2e-5
+    # discrete adjoint (ours) vs continuous adjoint (oracle): equal to O(tolerance); fp32 noise at rtol=1e-7
+    for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        assert rel_err(p.grad, q.grad) <= 1e-3, (n, rel_err(p.grad, q.grad))
+
+
+def test_dopri5_adjoint_call_gradients_vs_continuous_adjoint():
+    _need_gpu()
+    f = make_field(seed=44, scale=2.0)
+    t = torch.tensor([0.0, 0.4, 1.0])
+    y0 = torch.randn(128, 16)
+    g = torch.randn(3, 128, 16)
+
+    def run(fn, field, y, gg):
+        y = y.clone().requires_grad_(True)
+        sol = fn(field, y, t, rtol=1e-6, atol=1e-8)
+        return torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref = run(tdq.odeint_adjoint, f, y0, g)
+    out = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV))
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) <= 1e-3

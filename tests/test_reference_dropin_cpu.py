@@ -58,3 +58,22 @@ def test_stand_in_caller_equals_reference_caller(ref_models):
     torch.manual_seed(2)
     my_codes = mine.sample_z_m(8)
     assert torch.equal(ref_codes, my_codes)
+
+
+def test_odernn_stand_in_equals_reference_caller(ref_models, monkeypatch):
+    """models/mocogan_ode_rnn.py imports a non-existent `on_dev` package: alias it to `models`."""
+    import models
+    from tests.caller_model import LatentMotionODERNN
+    monkeypatch.setitem(sys.modules, "on_dev", models)
+    monkeypatch.setitem(sys.modules, "on_dev.mocogan_ode", ref_models)
+    rnn_mod = importlib.import_module("models.mocogan_ode_rnn")
+    torch.manual_seed(3)
+    gen = rnn_mod.VideoGeneratorMNISTODERNN(1, 50, 0, 16, 4)
+    mine = LatentMotionODERNN(16, 4)
+    mine.load_state_dict({k: v for k, v in gen.state_dict().items() if k.startswith(("ode_fn.", "recurrent."))})
+    torch.manual_seed(4)
+    ref_codes = gen.sample_z_m(3)
+    torch.manual_seed(4)
+    my_codes = mine.sample_z_m(3)
+    assert ref_codes.shape == (12, 16)
+    assert torch.equal(ref_codes, my_codes)
