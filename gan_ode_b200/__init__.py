@@ -8,6 +8,7 @@ or, without touching the reference files, `gan_ode_b200.install_shims()` registe
 from .odeint import config, last_step_log, odeint, odeint_adjoint, recognise_field  # noqa: F401
 from ._lib import GodeError  # noqa: F401
 from .graphed import GraphedSolveStep  # noqa: F401
+from .sdeint import PhiloxBrownian, TableBrownian, sdeint, sdeint_adjoint  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -22,4 +23,8 @@ def install_shims():
     td.odeint_adjoint = odeint_adjoint
     td.__version__ = "0.2.2+gan_ode_b200"
     sys.modules["torchdiffeq"] = td
+    ts = types.ModuleType("torchsde")
+    ts.sdeint = sdeint
+    ts.sdeint_adjoint = sdeint_adjoint
+    sys.modules["torchsde"] = ts
     return td

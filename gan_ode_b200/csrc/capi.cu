@@ -113,4 +113,42 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+size_t gode_sde_workspace_bytes(int B, int D, int H) {
+  (void)B;
+  return sde_small_workspace_bytes(D, H);
+}
+
+static bool bad_nets(const float* const* a, const float* const* b) {
+  if (!a || !b) return true;
+  for (int i = 0; i < 4; ++i)
+    if (!a[i] || !b[i]) return true;
+  return false;
+}
+
+int gode_sde_em_fwd(const float* y0, const float* const* drift, const float* const* diffusion, const float* h_host,
+                    int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host, int B, int D,
+                    int H, int T, const float* dW, uint64_t seed, int64_t traj_offset, int out_layout, float* frames,
+                    float* states, gode_stream_t stream) {
+  if (!y0 || bad_nets(drift, diffusion) || !h_host || !out_step_host || !w0_host || !w1_host || !frames || B <= 0 ||
+      T < 2 || n_steps < 1 || (out_layout != GODE_LAYOUT_TBD && out_layout != GODE_LAYOUT_BTD))
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return sde_small_fwd(y0, drift, diffusion, h_host, n_steps, out_step_host, w0_host, w1_host, B, D, H, T, dW, seed,
+                       traj_offset, out_layout, frames, states, (cudaStream_t)stream);
+}
+
+int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* const* drift,
+                    const float* const* diffusion, const float* h_host, int n_steps, const int* out_step_host,
+                    const float* w0_host, const float* w1_host, int B, int D, int H, int T, const float* dW,
+                    uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
+                    void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (!states || !grad_frames || bad_nets(drift, diffusion) || !h_host || !out_step_host || !w0_host || !w1_host ||
+      !grad_y0 || !grad_params || !workspace || B <= 0 || T < 2 || n_steps < 1 ||
+      (layout != GODE_LAYOUT_TBD && layout != GODE_LAYOUT_BTD))
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return sde_small_bwd(states, grad_frames, drift, diffusion, h_host, n_steps, out_step_host, w0_host, w1_host, B, D, H,
+                       T, dW, seed, traj_offset, layout, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

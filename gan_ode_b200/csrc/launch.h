@@ -69,6 +69,16 @@ int tc_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W
                int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,
                cudaStream_t st);
 
+size_t sde_small_workspace_bytes(int D, int H);
+int sde_small_fwd(const float* y0, const float* const* fw, const float* const* gw, const float* h_host, int n_steps,
+                  const int* out_step_host, const float* w0_host, const float* w1_host, int B, int D, int H, int T,
+                  const float* dW, unsigned long long seed, long long traj_offset, int layout, float* out, float* states,
+                  cudaStream_t st);
+int sde_small_bwd(const float* states, const float* grad_out, const float* const* fw, const float* const* gw,
+                  const float* h_host, int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host,
+                  int B, int D, int H, int T, const float* dW, unsigned long long seed, long long traj_offset, int layout,
+                  float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 inline bool small_field_shape(int D, int H) { return D == 16 && H == 16; }
 inline bool tc_shape(int D, int H) { return D == 16 && H == 16; }
 

@@ -160,6 +160,27 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                              const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
                              void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- a7: neural SDE, fixed-step Euler–Maruyama (torchsde sdeint, method='euler', diagonal Ito noise) -------------- */
+/* drift / diffusion: HOST arrays of 4 DEVICE pointers {W1, b1, W2, b2} (SDEFunc.drift_fn / diffusion_fn,
+ * models/mocogan_sde.py:10-19).  The step grid is built on the host exactly as torchsde's fixed-step driver does
+ * (fp32 time accumulation) and passed by value: h_host[n_steps] step sizes; frame j (1 <= j < T) is emitted after
+ * step out_step_host[j] as w0_host[j]*y_k + w1_host[j]*y_{k+1} (linear interpolation); frame 0 = y0.
+ * dW: (n_steps,B,D) Brownian increments, or NULL to generate them in the kernel: Philox4x32-10, key = seed,
+ * counter = (traj_offset + b, step, d/4, 0) -> Box–Muller -> N(0,1) * sqrt(h)   (oracle/philox.py::normals).
+ * states: (n_steps,B,D) state at the start of every step, kept for the backward (NULL: not kept). */
+size_t gode_sde_workspace_bytes(int B, int D, int H);
+int gode_sde_em_fwd(const float* y0, const float* const* drift, const float* const* diffusion, const float* h_host,
+                    int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host, int B, int D,
+                    int H, int T, const float* dW, uint64_t seed, int64_t traj_offset, int out_layout, float* frames,
+                    float* states, gode_stream_t stream);
+/* exact reverse-mode through the Euler–Maruyama steps given the same increments (table or regenerated Philox).
+ * grad_params: flat [drift: W1|b1|W2|b2 | diffusion: W1|b1|W2|b2], overwritten. */
+int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* const* drift,
+                    const float* const* diffusion, const float* h_host, int n_steps, const int* out_step_host,
+                    const float* w0_host, const float* w1_host, int B, int D, int H, int T, const float* dW,
+                    uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
+                    void* workspace, size_t ws_bytes, gode_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,84 @@
+"""CPU tests of host-side logic of the boundary (no GPU, no kernel calls)."""
+import numpy as np
+import pytest
+import torch
+
+import gan_ode_b200 as gode
+from gan_ode_b200 import odeint as _unused  # noqa: F401
+from gan_ode_b200.sdeint import recognise_sde, step_grid
+from oracle import torchsde_restatement as tsde
+from oracle.latent_motion import ODEFunc, SDEFunc
+import importlib
+
+api = importlib.import_module("gan_ode_b200.odeint")
+
+
+def test_sde_step_grid_equals_torchsde_restatement():
+    for T, dt in ((16, 2.5e-2), (16, 0.1), (5, 0.3), (2, 1e-2)):
+        ts = torch.linspace(0, 1, T).float()
+        h, out_step, w0, w1 = step_grid(ts, dt)
+        pairs = tsde.step_grid(ts, dt)
+        assert len(h) == len(pairs)
+        assert np.array_equal(h, np.array([float(b - a) for a, b in pairs], dtype=np.float32))
+        assert out_step[0] == 0 and (np.diff(out_step[1:]) >= 0).all()
+        assert np.allclose(w0[1:] + w1[1:], 1.0, atol=1e-6)
+    h, *_ = step_grid(torch.linspace(0, 1, 16).float(), 2.5e-2)
+    assert len(h) == 41
+
+
+def test_host_steps_matches_torch_arithmetic():
+    t = torch.linspace(0, 1, 16).float()
+    t64, dt, fsign = api._host_steps(t)
+    assert fsign == 1.0 and np.array_equal(dt, (t[1:] - t[:-1]).numpy())
+    assert len(set(dt.tolist())) > 1  # fp32 linspace spacing is not uniform
+    t64, dt, fsign = api._host_steps(torch.linspace(1, 0, 9))
+    assert fsign == -1.0 and (dt < 0).all() and (np.diff(t64) > 0).all()
+    t64, dt, _ = api._host_steps(torch.linspace(0, 1, 16, dtype=torch.float64))
+    assert dt.dtype == np.float32
+    with pytest.raises(AssertionError):
+        api._host_steps(torch.tensor([0.0, 0.5, 0.5, 1.0]))
+
+
+def test_field_recognition():
+    W1, b1, W2, b2 = gode.recognise_field(ODEFunc(16, 24))
+    assert W1.shape == (24, 16) and W2.shape == (16, 24)
+
+    class Wrong(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fn = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.ReLU(), torch.nn.Linear(4, 4))
+
+    with pytest.raises(NotImplementedError):
+        gode.recognise_field(Wrong())
+    f, g = recognise_sde(SDEFunc(16, 16))
+    assert f[0].shape == (16, 16) and g[2].shape == (16, 16)
+    with pytest.raises(NotImplementedError):
+        recognise_sde(ODEFunc(16, 16))
+
+
+def test_boundary_rejects_cpu_and_bad_inputs_without_touching_the_gpu():
+    f = ODEFunc(16, 16)
+    t = torch.linspace(0, 1, 16)
+    with pytest.raises(gode.GodeError):
+        gode.odeint(f, torch.randn(4, 16), t, method="rk4")
+    with pytest.raises(TypeError):
+        gode.odeint(f, torch.zeros(4, 16, dtype=torch.long), t)
+    with pytest.raises(NotImplementedError):
+        gode.odeint(f, torch.randn(4, 16), t, method="rk4", event_fn=lambda t, y: y)
+    with pytest.raises(gode.GodeError):
+        gode.sdeint(SDEFunc(16, 16), torch.randn(4, 16), t, method="euler", dt=0.025)
+
+
+def test_shims_register_both_packages():
+    import sys
+    saved = {k: sys.modules.pop(k, None) for k in ("torchdiffeq", "torchsde")}
+    try:
+        gode.install_shims()
+        from torchdiffeq import odeint_adjoint
+        from torchsde import sdeint_adjoint
+        assert odeint_adjoint is gode.odeint_adjoint and sdeint_adjoint is gode.sdeint_adjoint
+    finally:
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v
