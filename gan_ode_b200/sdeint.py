@@ -103,8 +103,7 @@ class _SdeEM(torch.autograd.Function):
         ws = [_api._f32c(w) for w in weights]
         y0c = _api._f32c(y0)
         buf, view = _api._alloc_traj(T, B, D, meta["layout"], y0)
-        keep = torch.is_grad_enabled() and (y0.requires_grad or any(w.requires_grad for w in weights))
-        keep = keep or meta["force_keep"]
+        keep = meta["keep"]  # decided outside: grad mode is off inside Function.forward
         states = torch.empty((n_steps, B, D), dtype=torch.float32, device=y0.device) if keep else None
         dW = meta["dW"]
         rc = L.gode_sde_em_fwd(y0c.data_ptr(), _ptrs(ws[:4]), _ptrs(ws[4:]), h.ctypes.data, n_steps, out_step.ctypes.data,
@@ -168,8 +167,9 @@ def _solve(sde, y0, ts, bm, method, dt, adaptive, options, force_keep=False):
         raise NotImplementedError("no sm_100a kernel compiled for SDEFunc(dim={}, dim_hidden={})".format(D, H))
     options = {} if options is None else dict(options)
     grid = step_grid(ts, dt)
+    keep = force_keep or (torch.is_grad_enabled() and (y0.requires_grad or any(w.requires_grad for w in (*f, *g))))
     meta = dict(grid=grid, layout=_api._layout_code(options.get("layout", _api.config.layout)), dW=None, seed=0,
-                traj_offset=0, force_keep=force_keep)
+                traj_offset=0, keep=keep)
     if bm is None:
         bm = PhiloxBrownian(int(torch.randint(0, 2 ** 62, (1,)).item()))
     if isinstance(bm, PhiloxBrownian):
