@@ -332,11 +332,19 @@ def run_gpu(args):
                 "note": "B=4096 x D=16 is 256 KB of state: the solve is a chain of {} dependent stages with a grid "
                         "barrier per attempted step, i.e. latency-bound, not bandwidth-bound".format(2 + 6 * n_att)}
 
-    if world > 1:
-        dist.barrier()
-    if rank != 0:
+    def finish():
+        # Captured graphs hold NCCL kernels: release them before the communicator goes away, and do not call
+        # destroy_process_group() (it can wait forever on a communicator that graphs still reference).
+        sys.stdout.flush()
+        sys.stderr.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     units = B_PER_GPU * n_att * n_gpus
@@ -369,8 +377,7 @@ def run_gpu(args):
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
