@@ -23,7 +23,7 @@ const char* gode_strerror(int code) {
 int gode_param_count(int D, int H) { return H * D + H + D * H + D; }
 
 int gode_supported(int D, int H, int precision) {
-  if (precision == GODE_PREC_FP32) return small_field_shape(D, H) ? 1 : 0;
+  if (precision == GODE_PREC_FP32) return (small_field_shape(D, H) || wide_shape(D, H)) ? 1 : 0;
   if (precision == GODE_PREC_TF32 || precision == GODE_PREC_BF16) return tc_shape(D, H) ? 1 : 0;
   return 0;
 }
@@ -41,12 +41,19 @@ int gode_rk4_fwd(const float* y0, const float* W1, const float* b1, const float*
     return tc_rk4_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, precision, out_layout, traj, (cudaStream_t)stream);
   }
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
+  if (wide_shape(D, H))
+    return wide_rk4_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, out_layout, traj, (cudaStream_t)stream);
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return rk4_small_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, out_layout, traj, (cudaStream_t)stream);
 }
 
 size_t gode_bwd_workspace_bytes(int B, int D, int H) {
   (void)B;
+  return bwd_workspace_bytes(gode_param_count(D, H));
+}
+
+size_t gode_rk4_bwd_workspace_bytes(int B, int D, int H, int T) {
+  if (wide_shape(D, H)) return wide_bwd_workspace_bytes(B, D, H, T);
   return bwd_workspace_bytes(gode_param_count(D, H));
 }
 
@@ -57,6 +64,11 @@ static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_tra
   if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !dt || !grad_y0 || !grad_params || !workspace)
     return GODE_ERR_ARG;
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
+  if (wide_shape(D, H)) {
+    if (!adjoint) return GODE_ERR_SHAPE;  // wide backprop-through-solver: not built
+    return wide_rk4_adjoint_bwd(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
+                                grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+  }
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return rk4_small_bwd(adjoint, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
                        grad_params, workspace, ws_bytes, (cudaStream_t)stream);

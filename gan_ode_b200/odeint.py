@@ -202,7 +202,7 @@ class _Rk4(torch.autograd.Function):
         g = _grad_in_layout(grad_traj, meta["layout"])
         grad_y0 = torch.empty((B, D), dtype=torch.float32, device=buf.device)
         grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=buf.device)
-        ws_bytes = L.gode_bwd_workspace_bytes(B, D, H)
+        ws_bytes = L.gode_rk4_bwd_workspace_bytes(B, D, H, T)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
@@ -423,6 +423,8 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
 
     if method == "dopri5":
+        if not (D == 16 and H == 16):
+            raise NotImplementedError("the fused dopri5 kernels exist for the reference shape D=H=16 only")
         if prec != _lib.PREC["fp32"]:
             raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
         # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): the gradient is computed by

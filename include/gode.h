@@ -126,6 +126,9 @@ int gode_rk4_fwd(const float* y0, const float* W1, const float* b1, const float*
 /* grad_params: flat [W1|b1|W2|b2], OVERWRITTEN with this call's gradient (may be an NCCL buffer).
  * workspace: gode_bwd_workspace_bytes(B,D,H) bytes, contents undefined on entry. */
 size_t gode_bwd_workspace_bytes(int B, int D, int H);
+/* same, for any supported shape: wide fields (D,H multiples of 32, e.g. 64/256) additionally need scratch rows
+ * proportional to B*(T-1) for the two-pass parameter-gradient contraction */
+size_t gode_rk4_bwd_workspace_bytes(int B, int D, int H, int T);
 int gode_rk4_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1,
                          const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D,
                          int H, int T, int precision, int layout, float* grad_y0, float* grad_params,

@@ -589,3 +589,40 @@ def test_sde_reference_call_through_shim():
     assert z.shape == (16, 64, 16) and torch.equal(z, z2)
     z.transpose(0, 1).reshape(-1, 16).sum().backward()
     assert x.grad is not None and sde_g.diffusion_fn[0].weight.grad.abs().sum() > 0
+
+
+# ---- wide fields (BASELINE configs[3]: D=64, H=256 "larger motion latent"), FP32 ------------------------------------------
+@pytest.mark.parametrize("D,H", [(32, 32), (32, 64), (64, 256)])
+@pytest.mark.parametrize("B", [1, 19, 257])
+def test_wide_field_rk4_forward_and_adjoint(D, H, B):
+    _need_gpu()
+    f = make_field(D, H, seed=D + H + B)
+    t = _t16()
+    y0 = torch.randn(B, D)
+    g = torch.randn(16, B, D)
+
+    def run(fn, field, y, gg, **k):
+        y = y.clone().requires_grad_(True)
+        sol = fn(field, y, t, method="rk4", **k)
+        return sol.detach(), torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq.odeint_adjoint, f, y0, g)
+    _, ref64 = run(tdq.odeint_adjoint, clone_to(f, "cpu", torch.float64), y0.double(), g.double())
+    out_sol, out_g = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"layout": "btd" if B % 2 else "tbd"})
+    assert torch.equal(out_sol[0].cpu(), y0)
+    assert rel_err(out_sol, ref_sol) <= TOL
+    _assert_grads(out_g, ref_g, ref64)
+
+
+def test_wide_field_deterministic_and_unsupported_combinations():
+    _need_gpu()
+    f = clone_to(make_field(64, 256, seed=1), DEV)
+    y0 = torch.randn(64, 64, device=DEV, requires_grad=True)
+    g = torch.randn(16, 64, 64, device=DEV)
+    a = torch.autograd.grad(gode.odeint_adjoint(f, y0, _t16(), method="rk4"), [y0] + list(f.parameters()), g)
+    b = torch.autograd.grad(gode.odeint_adjoint(f, y0, _t16(), method="rk4"), [y0] + list(f.parameters()), g)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    with pytest.raises(NotImplementedError):  # no fused dopri5 for wide fields yet
+        gode.odeint(f, y0, _t16(), method="dopri5")
+    with pytest.raises(gode.GodeError):       # wide backprop-through-solver not built
+        torch.autograd.grad(gode.odeint(f, y0, _t16(), method="rk4"), [y0], g)
