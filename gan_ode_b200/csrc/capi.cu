@@ -24,7 +24,8 @@ int gode_param_count(int D, int H) { return H * D + H + D * H + D; }
 
 int gode_supported(int D, int H, int precision) {
   if (precision == GODE_PREC_FP32) return (small_field_shape(D, H) || wide_shape(D, H)) ? 1 : 0;
-  if (precision == GODE_PREC_TF32 || precision == GODE_PREC_BF16) return tc_shape(D, H) ? 1 : 0;
+  if (precision == GODE_PREC_TF32) return tc_shape(D, H) ? 1 : 0;
+  if (precision == GODE_PREC_BF16) return (tc_shape(D, H) || tc_wide_shape(D, H)) ? 1 : 0;
   return 0;
 }
 
@@ -36,6 +37,8 @@ int gode_rk4_fwd(const float* y0, const float* W1, const float* b1, const float*
                  int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,
                  gode_stream_t stream) {
   if (bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !dt || !traj) return GODE_ERR_ARG;
+  if (precision == GODE_PREC_BF16 && tc_wide_shape(D, H))
+    return tc_rk4_fwd_wide(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, out_layout, traj, (cudaStream_t)stream);
   if (precision == GODE_PREC_TF32 || precision == GODE_PREC_BF16) {
     if (!tc_shape(D, H)) return GODE_ERR_SHAPE;
     return tc_rk4_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, precision, out_layout, traj, (cudaStream_t)stream);

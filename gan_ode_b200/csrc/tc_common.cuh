@@ -131,3 +131,14 @@ __device__ __forceinline__ float tanh_approx(float x) {
 
 }  // namespace tc
 }  // namespace gode
+
+namespace gode {
+namespace tc {
+// two tanh per MUFU op on packed bf16 (sm_90+); the packed result is directly a BF16 MMA operand pair
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+  uint32_t y;
+  asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+}  // namespace tc
+}  // namespace gode

@@ -626,3 +626,29 @@ def test_wide_field_deterministic_and_unsupported_combinations():
         gode.odeint(f, y0, _t16(), method="dopri5")
     with pytest.raises(gode.GodeError):       # wide backprop-through-solver not built
         torch.autograd.grad(gode.odeint(f, y0, _t16(), method="rk4"), [y0], g)
+
+
+@pytest.mark.parametrize("B", [1, 129, 1000])
+def test_wide_field_tensor_core_forward_bf16(B):
+    """D=64, H=256 on tcgen05 (BF16 operands, tanh.approx.bf16x2): <= 2e-3 relative; gradients through the FP32 wide
+    adjoint kernels re-solving from the stored tensor-core trajectory."""
+    _need_gpu()
+    f = make_field(64, 256, seed=B)
+    t = _t16()
+    y0 = torch.randn(B, 64)
+    g = torch.randn(16, B, 64)
+
+    def run(fn, field, y, gg, **k):
+        y = y.clone().requires_grad_(True)
+        sol = fn(field, y, t, method="rk4", **k)
+        return sol.detach(), torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq.odeint_adjoint, f, y0, g)
+    out_sol, out_g = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"precision": "bf16"})
+    assert torch.equal(out_sol[0].cpu(), y0)
+    e = rel_err(out_sol, ref_sol)
+    assert 1e-7 < e <= TC_TOL, e
+    for a, b in zip(out_g, ref_g):
+        assert rel_err(a, b) <= TC_TOL, rel_err(a, b)
+    with pytest.raises(NotImplementedError):
+        gode.odeint(clone_to(f, DEV), y0.to(DEV), t, method="rk4", options={"precision": "tf32"})
