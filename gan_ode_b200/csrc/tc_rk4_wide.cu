@@ -131,20 +131,26 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_fwd_wide_kernel(const __grid_co
     tc::mbar_wait(mbar_m, phase);
     phase ^= 1;
     tc::fence_after_sync();
-#pragma unroll 2
-    for (int cb = 0; cb < S::HH / 16; ++cb) {
-      float z[16];
-      tc::tmem_ld16(my_tmem + hf * S::HH + cb * 16, z);
-      uint32_t q[8];
+    // 64 columns per iteration: four TMEM loads in flight before one wait
+#pragma unroll 1
+    for (int cq = 0; cq < S::HH / 64; ++cq) {
+      uint32_t zr[4][16];
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(b1s + cb * 16 + i);
-        q[i / 2] = tc::tanh_bf16x2(tc::pack_bf16x2(z[i] + b.x, z[i + 1] + b.y));
-        q[i / 2 + 1] = tc::tanh_bf16x2(tc::pack_bf16x2(z[i + 2] + b.z, z[i + 3] + b.w));
+      for (int q4 = 0; q4 < 4; ++q4) tc::tmem_ld16_nowait(my_tmem + hf * S::HH + cq * 64 + q4 * 16, zr[q4]);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t q[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(b1s + cq * 64 + q4 * 16 + i);
+          q[i / 2] = tc::tanh_bf16x2(tc::pack_bf16x2(__uint_as_float(zr[q4][i]) + b.x, __uint_as_float(zr[q4][i + 1]) + b.y));
+          q[i / 2 + 1] = tc::tanh_bf16x2(tc::pack_bf16x2(__uint_as_float(zr[q4][i + 2]) + b.z, __uint_as_float(zr[q4][i + 3]) + b.w));
+        }
+        const int kc = (hf * S::HH + cq * 64 + q4 * 16) / 8;
+        *reinterpret_cast<uint4*>(A2 + (size_t)(kc * S::TILE + row) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
+        *reinterpret_cast<uint4*>(A2 + (size_t)((kc + 1) * S::TILE + row) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
       }
-      const int kc = (hf * S::HH + cb * 16) / 8;
-      *reinterpret_cast<uint4*>(A2 + (size_t)(kc * S::TILE + row) * 16) = make_uint4(q[0], q[1], q[2], q[3]);
-      *reinterpret_cast<uint4*>(A2 + (size_t)((kc + 1) * S::TILE + row) * 16) = make_uint4(q[4], q[5], q[6], q[7]);
     }
     tc::fence_async_smem();
     tc::fence_before_sync();
