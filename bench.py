@@ -152,6 +152,60 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measure_extras(gode, dev):
+    """Side measurements (not the headline): where the kernels sit against their rooflines once the batch is large
+    enough to leave the latency regime.  CUDA events, GPU kept busy while the host enqueues, median of 5."""
+    from tests.helpers import make_field, clone_to
+
+    def timeit(fn, n=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        for a, b in evs:
+            torch.cuda._sleep(1000000)
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in evs)[n // 2] * 1e-3  # s
+
+    out = {}
+    hbm, _ = peaks()
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = float(json.load(open(pk)).get("bf16_tflops_sustained", 1348.6)) if os.path.exists(pk) else 1400.0
+    t = torch.linspace(0, 1, 16).float()
+    f16 = clone_to(make_field(16, 16, seed=0), dev)
+    B = 1 << 20
+    y0 = torch.randn(B, 16, device=dev)
+    with torch.no_grad():
+        for prec in ("fp32", "tf32", "bf16"):
+            sec = timeit(lambda: gode.odeint(f16, y0, t, method="rk4", options={"precision": prec}))
+            out["rk4_fwd_D16_H16_B1M_" + prec] = {
+                "trajectory_steps_per_s": B * 15 / sec, "ms": sec * 1e3,
+                "hbm_frac": (B * 15 * 64 / sec / 1e9) / hbm,      # 4*D bytes per trajectory-step (trajectory write)
+                "fp32_ffma_tflops": (B * 15 * 4096 / sec / 1e12) if prec == "fp32" else None}
+    B2 = 1 << 18
+    y0r = torch.randn(B2, 16, device=dev, requires_grad=True)
+    g = torch.randn(16, B2, 16, device=dev)
+    sol = gode.odeint_adjoint(f16, y0r, t, method="rk4")
+    sec_b = timeit(lambda: torch.autograd.grad(sol, [y0r] + list(f16.parameters()), g, retain_graph=True))
+    with torch.no_grad():
+        sec_f = timeit(lambda: gode.odeint(f16, y0r, t, method="rk4"))
+    out["rk4_fwd_adjoint_D16_H16_B262144_fp32"] = {
+        "trajectory_steps_per_s": B2 * 15 / (sec_f + sec_b), "fwd_ms": sec_f * 1e3, "bwd_ms": sec_b * 1e3,
+        "fp32_tflops": B2 * 15 * 16384 / (sec_f + sec_b) / 1e12,
+        "hbm_frac": (B2 * 15 * 192 / (sec_f + sec_b) / 1e9) / hbm}
+    del y0, y0r, g, sol
+    fw = clone_to(make_field(64, 256, seed=0), dev)
+    B3 = 148 * 128
+    yw = torch.randn(B3, 64, device=dev)
+    with torch.no_grad():
+        sec = timeit(lambda: gode.odeint(fw, yw, t, method="rk4", options={"precision": "bf16"}))
+    tfl = B3 * 15 * 262144 / sec / 1e12
+    out["tc_rk4_fwd_D64_H256_B18944_bf16"] = {"trajectory_steps_per_s": B3 * 15 / sec, "ms": sec * 1e3, "tflops": tfl,
+                                              "frac_of_measured_bf16_gemm": tfl / bf16}
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import gan_ode_b200 as gode
@@ -364,6 +418,13 @@ def run_gpu(args):
                "sample": "full workload (B=4096, {} attempted steps) x 7 timed steps, median {:.3f} s/step; "
                          "torchdiffeq-restatement oracle (PyTorch CPU)".format(na, sec)}
 
+    extras = None
+    if n_gpus == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(gode, dev)
+        except Exception as e:  # noqa: BLE001
+            extras = {"error": str(e)[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -375,7 +436,7 @@ def run_gpu(args):
                 "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
         "gpu_launches": 2 * args.steps,
         "eager_ms_per_step": eager_ms / args.steps,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
     }
     print(json.dumps(line), flush=True)
     finish()
@@ -389,6 +450,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--no-extras", action="store_true", help="skip the large-batch / wide-field side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
