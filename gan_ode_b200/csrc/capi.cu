@@ -128,6 +128,37 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_dopri5_traj_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts,
+                         int out_layout, float* traj, GodeStepLog* log, int32_t* n_acc, int32_t* n_att,
+                         double* att_dt, float* att_er, uint8_t* att_acc, float* ckpt, double* acc_t0,
+                         double* acc_dt, gode_stream_t stream) {
+  if (bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !t_host || !opts || !traj || !log || !n_acc || !n_att)
+    return GODE_ERR_ARG;
+  if (opts->log_capacity > 0 && (!att_dt || !att_er || !att_acc)) return GODE_ERR_ARG;
+  if (opts->ckpt_capacity > 0 && (!ckpt || !acc_t0 || !acc_dt)) return GODE_ERR_ARG;
+  for (int i = 1; i < T; ++i)
+    if (!(t_host[i] > t_host[i - 1])) return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_traj_small_fwd(y0, W1, b1, W2, b2, t_host, B, D, H, T, opts, out_layout, traj, log, n_acc, n_att,
+                               opts->log_capacity > 0 ? att_dt : nullptr, att_er, att_acc, ckpt, acc_t0, acc_dt,
+                               (cudaStream_t)stream);
+}
+
+int gode_dopri5_traj_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                                  const GodeStepLog* log, const int32_t* n_acc, const float* ckpt,
+                                  const double* acc_t0, const double* acc_dt, int ckpt_capacity, float fsign,
+                                  float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                                  gode_stream_t stream) {
+  if (bad_common(grad_traj, W1, b1, W2, b2, B, T, layout) || !t_host || !log || !n_acc || !ckpt || !acc_t0 || !acc_dt ||
+      ckpt_capacity <= 0 || !grad_y0 || !grad_params || !workspace)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_traj_small_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, n_acc, ckpt, acc_t0, acc_dt,
+                               ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 size_t gode_sde_workspace_bytes(int B, int D, int H) {
   (void)B;
   return sde_small_workspace_bytes(D, H);

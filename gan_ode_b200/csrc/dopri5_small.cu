@@ -6,35 +6,9 @@
 //                               per-attempt device->host sync (`if error_ratio <= 1`) by an in-kernel barrier.
 //   dopri5_backprop_bwd_kernel  reverse-mode through the accepted steps + dense-output interpolation,
 //                               dt sequence read from the device-side step log (no host round trip).
-#include "small_field.cuh"
-#include "launch.h"
+#include "dopri5_common.cuh"
 
 namespace gode {
-
-// dopri5.py tableau, built in fp64 and cast to fp32 exactly as torchdiffeq casts it to y0.dtype
-#define F32(x) ((float)(x))
-__device__ constexpr float kBeta[6][6] = {
-    {F32(1.0 / 5), 0, 0, 0, 0, 0},
-    {F32(3.0 / 40), F32(9.0 / 40), 0, 0, 0, 0},
-    {F32(44.0 / 45), F32(-56.0 / 15), F32(32.0 / 9), 0, 0, 0},
-    {F32(19372.0 / 6561), F32(-25360.0 / 2187), F32(64448.0 / 6561), F32(-212.0 / 729), 0, 0},
-    {F32(9017.0 / 3168), F32(-355.0 / 33), F32(46732.0 / 5247), F32(49.0 / 176), F32(-5103.0 / 18656), 0},
-    {F32(35.0 / 384), 0, F32(500.0 / 1113), F32(125.0 / 192), F32(-2187.0 / 6784), F32(11.0 / 84)}};
-__device__ constexpr float kCErr[7] = {F32(35.0 / 384 - 1951.0 / 21600),
-                                        0,
-                                        F32(500.0 / 1113 - 22642.0 / 50085),
-                                        F32(125.0 / 192 - 451.0 / 720),
-                                        F32(-2187.0 / 6784 - -12231.0 / 42400),
-                                        F32(11.0 / 84 - 649.0 / 6300),
-                                        F32(-1.0 / 60)};
-__device__ constexpr float kCMid[7] = {F32(6025192743.0 / 30085553152.0 / 2),
-                                        0,
-                                        F32(51252292925.0 / 65400821598.0 / 2),
-                                        F32(-2691868925.0 / 45128329728.0 / 2),
-                                        F32(187940372067.0 / 1594534317056.0 / 2),
-                                        F32(-1776094331.0 / 19743644256.0 / 2),
-                                        F32(11237099.0 / 235043384.0 / 2)};
-#undef F32
 
 constexpr int kMaxT = 256;  // output times passed by value
 
@@ -56,28 +30,6 @@ struct Dp5Args {
 
 __device__ __forceinline__ size_t toff(int layout, int s, int b, int B, int T, int D) {
   return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
-}
-
-// misc.py::_optimal_step_size in fp64
-__device__ __forceinline__ double optimal_step(double dt, float er32, const GodeAdaptiveOpts& o) {
-  if (er32 == 0.f) return dt * o.ifactor;
-  const double dfactor = er32 < 1.f ? 1.0 : o.dfactor;
-  const double er = (double)er32;
-  // er^(1/5) as exp(log(er)/5): er is a positive finite fp32 value here (0 and NaN are handled around this line),
-  // so none of pow()'s special-case machinery is needed; relative error ~1e-15, far inside the 1e-5*dt budget.
-  const double factor = fmin(o.ifactor, fmax(o.safety / exp(0.2 * log(er)), dfactor));
-  // torch.min/max propagate NaN; fmin/fmax do not
-  return (er != er) ? er : dt * factor;
-}
-
-// the (possibly time-reversed) field: out = fsign * f(u)
-template <int D, int H, int L, class Lines>
-__device__ __forceinline__ void field(const RowWeights<D, H, L>& w, const Lines& ln, int l, float fsign,
-                                      const float (&u)[Shape<D, H, L>::DL], float (&out)[Shape<D, H, L>::DL],
-                                      float (&hk)[Shape<D, H, L>::HL]) {
-  mlp_forward<D, H, L>(w, ln, l, u, out, hk);
-#pragma unroll
-  for (int c = 0; c < Shape<D, H, L>::DL; ++c) out[c] *= fsign;
 }
 
 template <int D, int H, int L, int WARPS>

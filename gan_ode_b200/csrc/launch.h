@@ -79,6 +79,16 @@ int sde_small_bwd(const float* states, const float* grad_out, const float* const
                   int B, int D, int H, int T, const float* dW, unsigned long long seed, long long traj_offset, int layout,
                   float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+int dopri5_traj_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                          float* traj, GodeStepLog* log, int32_t* n_acc, int32_t* n_att, double* att_dt, float* att_er,
+                          uint8_t* att_acc, float* ckpt, double* acc_t0, double* acc_dt, cudaStream_t st);
+int dopri5_traj_small_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const double* t_host, int B, int D, int H, int T, int layout, const GodeStepLog* log,
+                          const int32_t* n_acc, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                          int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                          size_t ws_bytes, cudaStream_t st);
+
 bool wide_shape(int D, int H);
 size_t wide_bwd_workspace_bytes(int B, int D, int H, int T);
 int wide_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,

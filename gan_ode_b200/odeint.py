@@ -13,6 +13,8 @@ eager/CPU fallback.
 
 Extra keys accepted in `options` (ignored by torchdiffeq, so reference code never passes them):
   precision : 'fp32' (default) | 'tf32' | 'bf16'      arithmetic of the MLP contractions
+  norm      : 'batch' (default) | 'trajectory'        dopri5 step control: torchdiffeq's one-(t,dt)-per-batch, or
+                                                      per-trajectory (= torchdiffeq called with B=1 per trajectory)
   layout    : 'tbd' (default) | 'btd'                 memory order of the returned (T,B,D) tensor; 'btd' makes the
                                                       caller's .transpose(0,1).reshape(-1,D) a free view
   check     : bool (default False)                    synchronise and raise solver asserts eagerly
@@ -372,6 +374,104 @@ class _Dopri5(torch.autograd.Function):
         return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
 
 
+class TrajStepLog:
+    """Host view of a per-trajectory dopri5 solve: `n_accepted`, `n_attempts` are (B,) arrays; `dt`, `error_ratio`,
+    `accepted` are (n_max, B) arrays of per-attempt records (rows beyond a trajectory's own n_attempts are undefined).
+    Reading any attribute synchronises."""
+
+    def __init__(self, hdr, n_acc, n_att, att, cap, B):
+        self._t = (hdr, n_acc, n_att, att, cap, B)
+        self._host = None
+
+    def _load(self):
+        if self._host is None:
+            hdr, n_acc, n_att, att, cap, B = self._t
+            h = GodeStepLog.from_buffer_copy(hdr.cpu().numpy().tobytes()[:C.sizeof(GodeStepLog)])
+            na, nt = n_acc.cpu().numpy(), n_att.cpu().numpy()
+            d = dict(status=h.status, max_attempts=h.n_attempts, max_accepted=h.n_accepted, nfe=h.nfe,
+                     n_accepted=na, n_attempts=nt)
+            if att is not None:
+                raw = att.cpu().numpy().tobytes()
+                n = min(int(nt.max()) if len(nt) else 0, cap)
+                d["dt"] = np.frombuffer(raw, dtype=np.float64, count=cap * B).reshape(cap, B)[:n]
+                d["error_ratio"] = np.frombuffer(raw, dtype=np.float32, count=cap * B, offset=8 * cap * B).reshape(cap, B)[:n]
+                d["accepted"] = np.frombuffer(raw, dtype=np.uint8, count=cap * B, offset=12 * cap * B).reshape(cap, B)[:n].astype(bool)
+            self._host = d
+        return self._host
+
+    def __getattr__(self, k):
+        if k.startswith("_"):
+            raise AttributeError(k)
+        return self._load()[k]
+
+
+class _Dopri5Traj(torch.autograd.Function):
+    """dopri5 with per-trajectory step control (options={'norm': 'trajectory'}): gode_dopri5_traj_fwd /
+    gode_dopri5_traj_backprop_bwd.  Same semantics as running torchdiffeq once per trajectory."""
+
+    @staticmethod
+    def forward(ctx, y0, meta, W1, b1, W2, b2):
+        L = _lib.lib()
+        B, D = y0.shape
+        H = W1.shape[0]
+        T = meta["T"]
+        dev = y0.device
+        y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
+        buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
+        o = meta["opts"]
+        keep = meta["keep_ckpt"]
+        kc = o.ckpt_capacity if keep else 0
+        cap = int(meta["traj_log_capacity"])
+        opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
+        opts.ckpt_capacity, opts.log_capacity = kc, cap
+        hdr = torch.empty(64, dtype=torch.uint8, device=dev)
+        counts = torch.empty((2, B), dtype=torch.int32, device=dev)
+        att = torch.empty(13 * cap * B, dtype=torch.uint8, device=dev) if cap > 0 else None
+        ckpt = torch.empty((max(kc, 1), B, D), dtype=torch.float32, device=dev) if keep else None
+        acc = torch.empty((2, max(kc, 1), B), dtype=torch.float64, device=dev) if keep else None
+        ab = att.data_ptr() if att is not None else 0
+        tarr = meta["t64"]
+        _lib.check(L.gode_dopri5_traj_fwd(
+            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
+            meta["layout"], _ptr(buf), hdr.data_ptr(), counts[0].data_ptr(), counts[1].data_ptr(),
+            ab if cap else None, (ab + 8 * cap * B) if cap else None, (ab + 12 * cap * B) if cap else None,
+            _ptr(ckpt), acc[0].data_ptr() if keep else None, acc[1].data_ptr() if keep else None, _stream()),
+            "gode_dopri5_traj_fwd")
+        log = TrajStepLog(hdr, counts[0], counts[1], att, cap, B)
+        _LAST_LOG[0] = log
+        if meta["check"]:
+            raise_for_status(log.status)
+        ctx.meta, ctx.log, ctx.kc, ctx.tarr = meta, log, kc, tarr
+        ctx.save_for_backward(hdr, counts, ckpt, acc, W1c, b1c, W2c, b2c)
+        return view
+
+    @staticmethod
+    def backward(ctx, grad_traj):
+        L = _lib.lib()
+        hdr, counts, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors
+        meta, kc = ctx.meta, ctx.kc
+        if ckpt is None:
+            raise GodeError("dopri5 forward ran without checkpoints (inputs did not require grad)")
+        if meta["check"]:
+            raise_for_status(ctx.log.status)
+        T = meta["T"]
+        _, B, D = ckpt.shape
+        H = W1c.shape[0]
+        g = _grad_in_layout(grad_traj, meta["layout"])
+        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=ckpt.device)
+        grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
+        ws_bytes = L.gode_bwd_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
+        _lib.check(L.gode_dopri5_traj_backprop_bwd(
+            _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T, meta["layout"],
+            hdr.data_ptr(), counts[0].data_ptr(), _ptr(ckpt), acc[0].data_ptr(), acc[1].data_ptr(), kc,
+            C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes, _stream()),
+            "gode_dopri5_traj_backprop_bwd")
+        needs = ctx.needs_input_grad
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6])
+        return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
+
+
 def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
     if isinstance(rtol, torch.Tensor) or isinstance(atol, torch.Tensor):
         rtol, atol = float(rtol), float(atol)
@@ -386,9 +486,10 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
     o.max_step = float(options.get("max_step", float("inf")))
     o.max_num_steps = int(min(options.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
     norm = options.get("norm", None)
-    if norm is not None and norm not in ("batch", "rms"):
-        raise NotImplementedError("custom error norms are not supported by the fused dopri5 kernel (batch-global RMS only)")
-    o.norm_scope = _lib.NORM_BATCH
+    if norm is not None and norm not in ("batch", "rms", "trajectory", "per_trajectory"):
+        raise NotImplementedError("custom error norms are not supported by the fused dopri5 kernels: 'batch' (torchdiffeq's "
+                                  "batch-global RMS, default) or 'trajectory' (per-trajectory step control)")
+    o.norm_scope = _lib.NORM_TRAJ if norm in ("trajectory", "per_trajectory") else _lib.NORM_BATCH
     o.log_capacity = int(options.get("log_capacity", config.log_capacity))
     o.ckpt_capacity = int(options.get("ckpt_capacity", config.ckpt_capacity))
     o.fsign = fsign
@@ -435,7 +536,10 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
         meta["t64"] = t64
+        meta["traj_log_capacity"] = int(options.get("traj_log_capacity", 0))  # per-attempt logs per trajectory (tests)
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
+        if meta["opts"].norm_scope == _lib.NORM_TRAJ:
+            return _Dopri5Traj.apply(y0, meta, W1, b1, W2, b2)
         return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
 
     raise NotImplementedError('method "{}" is not on the gan-ode hot path (rk4 and dopri5 are; SURVEY §8f-4)'.format(method))

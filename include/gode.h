@@ -163,6 +163,24 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                              const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
                              void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- a5 (opt-in): dopri5 with PER-TRAJECTORY step control (GODE_NORM_TRAJ) ----------------------------------- */
+/* Every trajectory has its own (t, dt), RMS error norm over its own D components and accept/reject sequence — what
+ * torchdiffeq computes when called with B = 1 per trajectory.  No grid-wide reduction, ordinary launch, any B.
+ * n_acc / n_att: (B) int32 accepted / attempted steps per trajectory.  att_dt (f64), att_er (f32), att_acc (u8):
+ * (log_capacity, B) per-attempt logs or NULL.  ckpt: (ckpt_capacity, B, D); acc_t0 / acc_dt: (ckpt_capacity, B) f64.
+ * log: status = OR over trajectories, n_attempts / n_accepted / nfe = max over trajectories. */
+int gode_dopri5_traj_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                         const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts,
+                         int out_layout, float* traj, GodeStepLog* log, int32_t* n_acc, int32_t* n_att,
+                         double* att_dt, float* att_er, uint8_t* att_acc, float* ckpt, double* acc_t0,
+                         double* acc_dt, gode_stream_t stream);
+int gode_dopri5_traj_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                                  const GodeStepLog* log, const int32_t* n_acc, const float* ckpt,
+                                  const double* acc_t0, const double* acc_dt, int ckpt_capacity, float fsign,
+                                  float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                                  gode_stream_t stream);
+
 /* ---- a7: neural SDE, fixed-step Euler–Maruyama (torchsde sdeint, method='euler', diagonal Ito noise) -------------- */
 /* drift / diffusion: HOST arrays of 4 DEVICE pointers {W1, b1, W2, b2} (SDEFunc.drift_fn / diffusion_fn,
  * models/mocogan_sde.py:10-19).  The step grid is built on the host exactly as torchsde's fixed-step driver does
