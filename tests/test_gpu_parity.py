@@ -713,7 +713,7 @@ def test_dopri5_per_trajectory_free_running_controller_vs_oracle():
             s = tdq.odeint(f, y0[b:b + 1], t, method="dopri5", rtol=1e-5, atol=1e-5)
             rl = tdq.last_step_log()
             n = int(log.n_attempts[b])
-            assert rel_err(sol[:, b], s[:, 0]) <= 1e-4
+            assert rel_err(sol[:, b], s[:, 0]) <= 3e-4  # two rtol=1e-5 solves on different step sequences, 6x stiffer field
             # The dt after the noise-level first attempt differs by a few per cent between two correct implementations
             # (see _replay_dt), which moves later error ratios by ~5x that; flags are only comparable when no oracle
             # error ratio sits within that band of the accept threshold.
