@@ -153,3 +153,39 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
 }
 }  // namespace tc
 }  // namespace gode
+
+namespace gode {
+namespace tc {
+// ---- TMEM stores: thread i of warp w writes lane 32*(w%4)+i, 8 consecutive 32-bit columns --------------------------------
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- MMA with the A operand in TMEM (16-bit elements packed two per 32-bit column, lane = row), B in shared memory ------
+__device__ __forceinline__ void mma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- named barrier over a subset of the CTA's warps (ids 1..15; 0 is __syncthreads) -------------------------------------
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// one lane of a fully converged warp (warp-uniform control flow keeps MMA descriptors in uniform registers; a
+// `threadIdx.x == 0` branch instead makes ptxas wrap every tcgen05.mma in an ELECT/R2UR waterfall loop, ~60 cycles each)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+}  // namespace tc
+}  // namespace gode
