@@ -196,13 +196,17 @@ def measure_extras(gode, dev):
         "hbm_frac": (B2 * 15 * 192 / (sec_f + sec_b) / 1e9) / hbm}
     del y0, y0r, g, sol
     fw = clone_to(make_field(64, 256, seed=0), dev)
-    B3 = 148 * 128
-    yw = torch.randn(B3, 64, device=dev)
-    with torch.no_grad():
-        sec = timeit(lambda: gode.odeint(fw, yw, t, method="rk4", options={"precision": "bf16"}))
-    tfl = B3 * 15 * 262144 / sec / 1e12
-    out["tc_rk4_fwd_D64_H256_B18944_bf16"] = {"trajectory_steps_per_s": B3 * 15 / sec, "ms": sec * 1e3, "tflops": tfl,
-                                              "frac_of_measured_bf16_gemm": tfl / bf16}
+    for B3 in (148 * 128, 4 * 296 * 128):  # one tile per SM (latency regime) / four rounds of two tiles per SM
+        yw = torch.randn(B3, 64, device=dev)
+        with torch.no_grad():
+            sec = timeit(lambda: gode.odeint(fw, yw, t, method="rk4", options={"precision": "bf16"}))
+        tfl = B3 * 15 * 262144 / sec / 1e12
+        # binding roofline of this shape is the MUFU pipe: 256 tanh per trajectory-stage at 16 tanh/clk/SM (measured,
+        # scripts/tmem_bench.cu) = half the tcgen05 rate, so 0.5 of the GEMM peak is the ceiling of the fused stage
+        out["tc_rk4_fwd_D64_H256_B%d_bf16" % B3] = {"trajectory_steps_per_s": B3 * 15 / sec, "ms": sec * 1e3, "tflops": tfl,
+                                                    "frac_of_measured_bf16_gemm": tfl / bf16,
+                                                    "frac_of_mufu_bound": tfl / (0.5 * bf16)}
+        del yw
     return out
 
 

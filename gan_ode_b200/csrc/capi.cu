@@ -56,7 +56,10 @@ size_t gode_bwd_workspace_bytes(int B, int D, int H) {
 }
 
 size_t gode_rk4_bwd_workspace_bytes(int B, int D, int H, int T) {
-  if (wide_shape(D, H)) return wide_bwd_workspace_bytes(B, D, H, T);
+  if (wide_shape(D, H)) {
+    const size_t a = wide_bwd_workspace_bytes(B, D, H, T), b = tc_wide_shape(D, H) ? tc_rk4_adj_wide_workspace_bytes(B) : 0;
+    return a > b ? a : b;
+  }
   return bwd_workspace_bytes(gode_param_count(D, H));
 }
 
@@ -66,6 +69,9 @@ static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_tra
                           size_t ws_bytes, gode_stream_t stream) {
   if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !dt || !grad_y0 || !grad_params || !workspace)
     return GODE_ERR_ARG;
+  if (precision == GODE_PREC_BF16 && tc_wide_shape(D, H) && adjoint)  // tensor-core continuous adjoint (wide field)
+    return tc_rk4_adj_wide(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                           workspace, ws_bytes, (cudaStream_t)stream);
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
   if (wide_shape(D, H)) {
     if (!adjoint) return GODE_ERR_SHAPE;  // wide backprop-through-solver: not built

@@ -18,6 +18,7 @@ Extra keys accepted in `options` (ignored by torchdiffeq, so reference code neve
   layout    : 'tbd' (default) | 'btd'                 memory order of the returned (T,B,D) tensor; 'btd' makes the
                                                       caller's .transpose(0,1).reshape(-1,D) a free view
   check     : bool (default False)                    synchronise and raise solver asserts eagerly
+  bwd_precision : 'bf16' (default) | 'fp32'           wide field in bf16 mode only: tensor-core adjoint or the FP32 one
 """
 from __future__ import annotations
 
@@ -208,10 +209,15 @@ class _Rk4(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
-        # The backward always runs the FP32 kernels: after a tf32/bf16 forward they re-solve from the stored (tensor-
-        # core) trajectory, which keeps the gradient inside the 2e-3 budget of that mode.  (Tensor-core VJP: next.)
+        # Wide field (D=64, H=256) in bf16 mode: the continuous adjoint runs on tcgen05 too (csrc/tc_rk4_adj_wide.cu).
+        # Everything else backpropagates with the FP32 kernels, re-solving from the stored (tensor-core) trajectory,
+        # which keeps the gradient inside the 2e-3 budget of the tf32/bf16 modes.
+        bwd_prec = _lib.PREC["fp32"]
+        if meta["adjoint"] and meta["precision"] == _lib.PREC["bf16"] and (D, H) == (64, 256) \
+                and meta.get("bwd_precision", "bf16") == "bf16":
+            bwd_prec = _lib.PREC["bf16"]
         rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
-                dt_dev, B, D, H, T, _lib.PREC["fp32"], meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
+                dt_dev, B, D, H, T, bwd_prec, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
                 ws.data_ptr(), ws_bytes, _stream())
         if rc:
             _lib.check(rc, "gode_rk4_bwd")
@@ -517,7 +523,8 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
     if t.is_cuda and t.device != y0.device:
         warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
         t = t.to(y0.device)
-    meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)))
+    meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)),
+                bwd_precision=options.get("bwd_precision", "bf16"))
 
     if method == "rk4":
         dt = _rk4_dt(t, options, y0.device)
