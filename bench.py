@@ -201,12 +201,28 @@ def measure_extras(gode, dev):
         with torch.no_grad():
             sec = timeit(lambda: gode.odeint(fw, yw, t, method="rk4", options={"precision": "bf16"}))
         tfl = B3 * 15 * 262144 / sec / 1e12
-        # binding roofline of this shape is the MUFU pipe: 256 tanh per trajectory-stage at 16 tanh/clk/SM (measured,
-        # scripts/tmem_bench.cu) = half the tcgen05 rate, so 0.5 of the GEMM peak is the ceiling of the fused stage
+        # binding roofline of this shape is the MUFU pipe: one tanh per 4*D = 256 FLOP at 16 tanh/clk/SM (measured,
+        # scripts/tmem_bench.cu) = half the tcgen05 rate at the same clock.  The bound is quoted at the MAXIMUM SM clock
+        # (the kernel's actual clock under load is lower), so the fraction is a lower bound.
+        mufu_tfl = 16 * 148 * 1965e6 * 256 / 1e12
         out["tc_rk4_fwd_D64_H256_B%d_bf16" % B3] = {"trajectory_steps_per_s": B3 * 15 / sec, "ms": sec * 1e3, "tflops": tfl,
                                                     "frac_of_measured_bf16_gemm": tfl / bf16,
-                                                    "frac_of_mufu_bound": tfl / (0.5 * bf16)}
+                                                    "mufu_bound_tflops_at_1965mhz": mufu_tfl,
+                                                    "frac_of_mufu_bound": tfl / mufu_tfl}
         del yw
+    # forward + tensor-core continuous adjoint of the wide field (configs[3]'s shape), 64*D*H FLOP per trajectory-step
+    B4 = 296 * 128
+    yw = torch.randn(B4, 64, device=dev, requires_grad=True)
+    gw = torch.randn(16, B4, 64, device=dev)
+    solw = gode.odeint_adjoint(fw, yw, t, method="rk4", options={"precision": "bf16"})
+    sec_b = timeit(lambda: torch.autograd.grad(solw, [yw] + list(fw.parameters()), gw, retain_graph=True))
+    with torch.no_grad():
+        sec_f = timeit(lambda: gode.odeint(fw, yw, t, method="rk4", options={"precision": "bf16"}))
+    tfl = B4 * 15 * 1048576 / (sec_f + sec_b) / 1e12
+    out["tc_rk4_fwd_adjoint_D64_H256_B%d_bf16" % B4] = {
+        "trajectory_steps_per_s": B4 * 15 / (sec_f + sec_b), "fwd_ms": sec_f * 1e3, "bwd_ms": sec_b * 1e3, "tflops": tfl,
+        "frac_of_measured_bf16_gemm": tfl / bf16}
+    del yw, gw, solw
     return out
 
 
