@@ -9,6 +9,7 @@ from .odeint import config, last_step_log, odeint, odeint_adjoint, recognise_fie
 from ._lib import GodeError  # noqa: F401
 from .graphed import GraphedSolveStep  # noqa: F401
 from .sdeint import PhiloxBrownian, TableBrownian, sdeint, sdeint_adjoint  # noqa: F401
+from .odernn import gru_jump, odernn_codes  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -53,6 +53,13 @@ _SIGS = {
     "gode_dopri5_traj_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 11),
     "gode_dopri5_traj_backprop_bwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P,
                                            C.c_size_t, _P]),
+    "gode_gru_param_count": (_I, [_I]),
+    "gode_gru_jump_fwd": (_I, [_P] * 6 + [_I, _I, _P, _P]),
+    "gode_gru_jump_bwd": (_I, [_P] * 7 + [_I, _I, _P, _P, _P, _P, C.c_size_t, _P]),
+    "gode_odernn_log_stride": (C.c_size_t, [_I]),
+    "gode_odernn_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "gode_odernn_fwd": (_I, [_P] * 10 + [_I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts)] + [_P] * 6 + [C.c_size_t, _P]),
+    "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 10 + [C.c_size_t, _P]),
     "gode_sde_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_sde_em_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P]),
     "gode_sde_em_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P,

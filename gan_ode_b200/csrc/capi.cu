@@ -203,4 +203,50 @@ int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* 
                        T, dW, seed, traj_offset, layout, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_gru_param_count(int D) { return 2 * 3 * D * D + 2 * 3 * D; }
+
+int gode_gru_jump_fwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, int B, int D, float* h_out, gode_stream_t stream) {
+  if (!x || !h || !w_ih || !w_hh || !b_ih || !b_hh || !h_out || B <= 0) return GODE_ERR_ARG;
+  return gru_jump_fwd(x, h, w_ih, w_hh, b_ih, b_hh, B, D, h_out, (cudaStream_t)stream);
+}
+
+int gode_gru_jump_bwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, const float* grad_out, int B, int D, float* grad_x, float* grad_h,
+                      float* grad_params, void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (!x || !h || !w_ih || !w_hh || !b_ih || !b_hh || !grad_out || !grad_h || !grad_params || !workspace || B <= 0)
+    return GODE_ERR_ARG;
+  return gru_jump_bwd(x, h, w_ih, w_hh, b_ih, b_hh, grad_out, nullptr, B, D, grad_x, grad_h, grad_params, 0, workspace,
+                      ws_bytes, (cudaStream_t)stream);
+}
+
+size_t gode_odernn_log_stride(int log_capacity) { return odernn_log_stride(log_capacity); }
+size_t gode_odernn_workspace_bytes(int B, int D, int H) { return odernn_workspace_bytes(B, D, H); }
+
+int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H,
+                    int F, const GodeAdaptiveOpts* opts, float* codes, float* seg, void* logs, float* ckpt, double* acc,
+                    void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (!h0 || !eps || !W1 || !b1 || !W2 || !b2 || !w_ih || !w_hh || !b_ih || !b_hh || !opts || !codes || !seg || !logs ||
+      !workspace || B <= 0 || F < 1)
+    return GODE_ERR_ARG;
+  if (opts->ckpt_capacity > 0 && (!ckpt || !acc)) return GODE_ERR_ARG;
+  if (opts->norm_scope != GODE_NORM_BATCH || opts->log_capacity < 0) return GODE_ERR_ARG;
+  return odernn_fwd(h0, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh, B, D, H, F, opts, codes, seg,
+                    reinterpret_cast<unsigned char*>(logs), ckpt, acc, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
+int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
+                    const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
+                    int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
+                    const float* ckpt, const double* acc, float* grad_h0, float* grad_eps, float* grad_ode,
+                    float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (!grad_codes || !eps || !W1 || !b1 || !W2 || !b2 || !w_ih || !w_hh || !b_ih || !b_hh || !seg || !logs || !ckpt ||
+      !acc || !grad_h0 || !grad_ode || !grad_gru || !scratch || !workspace || B <= 0 || F < 1 || ckpt_capacity <= 0)
+    return GODE_ERR_ARG;
+  return odernn_bwd(grad_codes, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh, B, D, H, F, ckpt_capacity, seg,
+                    reinterpret_cast<const unsigned char*>(logs), odernn_log_stride(log_capacity), ckpt, acc, grad_h0,
+                    grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes, (cudaStream_t)stream);
+}
+
 }  // extern "C"

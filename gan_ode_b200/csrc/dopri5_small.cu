@@ -373,11 +373,11 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H) {
 template <int D, int H, int L>
 static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   const int grid = dp5_fwd_grid<D, H, L>(a.B);
-  if (ws_bytes < grid_sync_bytes(grid)) return GODE_ERR_WORKSPACE;
   auto kern = dopri5_fwd_kernel<D, H, L, kDp5Warps>;
   static int limit_cache = 0;
   const int cap = coop_limit(kern, kDp5Warps * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
+  if (ws_bytes < grid_sync_bytes(grid)) return GODE_ERR_WORKSPACE;
   grid_sync_bind(a.gs, workspace);
   cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);
@@ -428,7 +428,14 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
   a.ckpt = ckpt; a.acc_t0 = acc_t0; a.acc_dt = acc_dt;
   a.o = *opts; a.B = B; a.T = T; a.layout = out_layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
-  if (D == 16 && H == 16) return launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
+  if (D == 16 && H == 16) {
+    // Every trajectory of the batch has to be resident at once (batch-global error norm).  8 lanes per trajectory is
+    // the fastest mapping (shortest dependent chain) and holds 7104 trajectories on 148 SMs; beyond that 4 lanes per
+    // trajectory (twice the state per thread) hold 9472.  Larger batches: shard them (multi-GPU) or use norm='trajectory'.
+    const int rc = launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
+    if (rc != GODE_ERR_COOP) return rc;
+    return launch_dp5_fwd<16, 16, 4>(a, workspace, ws_bytes, st);
+  }
   return GODE_ERR_SHAPE;
 }
 

@@ -104,6 +104,22 @@ size_t tc_rk4_adj_wide_workspace_bytes(int B);
 int tc_rk4_adj_wide(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
                     float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+size_t odernn_log_stride(int log_capacity);
+size_t odernn_workspace_bytes(int B, int D, int H);
+int gru_jump_fwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, int B, int D, float* h_out, cudaStream_t st);
+int gru_jump_bwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, const float* grad_out, const float* grad_carry, int B, int D, float* grad_x,
+                 float* grad_h, float* grad_params, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t st);
+int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
+               const GodeAdaptiveOpts* opts, float* codes, float* seg, unsigned char* logs, float* ckpt, double* acc,
+               void* workspace, size_t ws_bytes, cudaStream_t st);
+int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
+               int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
+               const double* acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch,
+               void* workspace, size_t ws_bytes, cudaStream_t st);
 inline bool tc_shape(int D, int H) { return D == 16 && H == 16; }
 inline bool tc_wide_shape(int D, int H) { return D == 64 && H == 256; }  // BF16 only
 

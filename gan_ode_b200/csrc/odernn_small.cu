@@ -1,0 +1,254 @@
+// odernn_small.cu — the ODE-RNN sampler of models/mocogan_ode_rnn.py:40-54 behind ONE C-ABI call per direction.
+//   per frame f:  h'_f = odeint(ode_fn, h_{f-1}, [0, 1])[-1]        (dopri5, the reference passes no solver kwargs)
+//                 h_f  = GRUCell(e_f, h'_f)                          (input = noise, hidden = the ODE-evolved state)
+// The solves are the fused dopri5 kernels of dopri5_small.cu (one launch per frame, batch-global step control exactly as
+// each of the reference's 16 odeint calls); this file adds the fused GRU jump (forward and backward, PyTorch nn.GRUCell
+// semantics: gate order r, z, n; n = tanh(W_in x + b_in + r (W_hn h + b_hn)); h_out = (1 - z) n + z h) and the frame
+// loop on the host side of the C ABI, so a whole 16-frame forward (or backward) is enqueued without the Python
+// interpreter, with every intermediate staying on the device:
+//   * h_f is written straight into the output codes (F, B, D) and is the next frame's y0 (no copies);
+//   * the backward walks the frames in reverse: GRU VJP -> discrete adjoint of that frame's solve
+//     (dopri5_backprop_bwd_kernel over the frame's own device-side step log and checkpoints);
+//   * parameter gradients: one slot per frame, summed in frame order at the end (deterministic).
+#include "launch.h"
+
+namespace gode {
+
+namespace {
+
+constexpr int GD = 16;             // dim_z_motion of the reference (models/mocogan.py:198: GRUCell(16, 16))
+constexpr int GT = 16;             // trajectories per tile
+constexpr int GP = 2 * 3 * GD * GD + 2 * 3 * GD;  // flat [w_ih (3D,D) | w_hh (3D,D) | b_ih (3D) | b_hh (3D)] = 1632
+
+constexpr int GS = GD + 1;         // padded row stride of the weights in shared memory (rows by lane: conflict-free)
+struct GruW {
+  float wih[3 * GD * GS], whh[3 * GD * GS], bih[3 * GD], bhh[3 * GD];
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ void load_w(GruW& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                                       int tid, int n) {
+  for (int e = tid; e < 3 * GD * GD; e += n) { w.wih[(e / GD) * GS + e % GD] = w_ih[e]; w.whh[(e / GD) * GS + e % GD] = w_hh[e]; }
+  for (int e = tid; e < 3 * GD; e += n) { w.bih[e] = b_ih[e]; w.bhh[e] = b_hh[e]; }
+}
+
+// gates of unit j of trajectory t (x, h rows in shared memory)
+struct Gates { float r, z, n, hn; };
+__device__ __forceinline__ Gates gates(const GruW& w, const float* x, const float* h, int j) {
+  float ir = w.bih[j], iz = w.bih[GD + j], in = w.bih[2 * GD + j];
+  float hr = w.bhh[j], hz = w.bhh[GD + j], hn = w.bhh[2 * GD + j];
+#pragma unroll
+  for (int k = 0; k < GD; ++k) {
+    const float xv = x[k], hv = h[k];
+    ir = fmaf(w.wih[j * GS + k], xv, ir);
+    iz = fmaf(w.wih[(GD + j) * GS + k], xv, iz);
+    in = fmaf(w.wih[(2 * GD + j) * GS + k], xv, in);
+    hr = fmaf(w.whh[j * GS + k], hv, hr);
+    hz = fmaf(w.whh[(GD + j) * GS + k], hv, hz);
+    hn = fmaf(w.whh[(2 * GD + j) * GS + k], hv, hn);
+  }
+  Gates g;
+  g.r = sigmoidf_(ir + hr);
+  g.z = sigmoidf_(iz + hz);
+  g.hn = hn;
+  g.n = tanhf(in + g.r * hn);
+  return g;
+}
+
+// h_out = GRUCell(x, h); one thread per (trajectory, unit), 16 trajectories per 256-thread tile
+__global__ void __launch_bounds__(256) gru_jump_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                           const float* w_ih, const float* w_hh, const float* b_ih,
+                                                           const float* b_hh, int B, float* __restrict__ h_out) {
+  __shared__ GruW w;
+  __shared__ float sx[GT][GD + 1], sh[GT][GD + 1];
+  const int tid = threadIdx.x, t = tid / GD, j = tid % GD;
+  load_w(w, w_ih, w_hh, b_ih, b_hh, tid, 256);
+  for (int base = blockIdx.x * GT; base < B; base += gridDim.x * GT) {
+    const int b = base + t;
+    __syncthreads();
+    sx[t][j] = b < B ? x[(size_t)b * GD + j] : 0.f;
+    sh[t][j] = b < B ? h[(size_t)b * GD + j] : 0.f;
+    __syncthreads();
+    const Gates g = gates(w, sx[t], sh[t], j);
+    if (b < B) h_out[(size_t)b * GD + j] = (1.f - g.z) * g.n + g.z * sh[t][j];
+  }
+}
+
+// VJP of the jump.  go = grad_out (+ carry), per tile: (t,j) threads form the gate cotangents, (j,k) threads accumulate
+// the weight gradients over the tile's trajectories in registers (persistent over tiles), (t,k) threads form dx and dh.
+// Each CTA writes ONE partial row of GP floats; gru_reduce_kernel adds the rows in CTA order.
+__global__ void __launch_bounds__(256) gru_jump_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
+                                                           const float* w_ih, const float* w_hh, const float* b_ih,
+                                                           const float* b_hh, const float* __restrict__ grad_out,
+                                                           const float* __restrict__ grad_carry, int B,
+                                                           float* __restrict__ grad_x, float* __restrict__ grad_h,
+                                                           float* __restrict__ partial) {
+  __shared__ GruW w;
+  __shared__ float sx[GT][GD + 1], sh[GT][GD + 1];
+  __shared__ float sa[GT][4][GD + 1];  // cotangents of (a_r, a_z, a_n, hn) per trajectory and unit
+  __shared__ float sz[GT][GD + 1];     // go * z (direct path to h)
+  const int tid = threadIdx.x, t = tid / GD, j = tid % GD;  // also used as (j, k) = (tid / GD, tid % GD)
+  load_w(w, w_ih, w_hh, b_ih, b_hh, tid, 256);
+  float aih[3] = {0.f, 0.f, 0.f}, ahh[3] = {0.f, 0.f, 0.f}, abi[3] = {0.f, 0.f, 0.f}, abh[3] = {0.f, 0.f, 0.f};
+  for (int base = blockIdx.x * GT; base < B; base += gridDim.x * GT) {
+    const int b = base + t;
+    __syncthreads();
+    sx[t][j] = b < B ? x[(size_t)b * GD + j] : 0.f;
+    sh[t][j] = b < B ? h[(size_t)b * GD + j] : 0.f;
+    __syncthreads();
+    {
+      const Gates g = gates(w, sx[t], sh[t], j);
+      float go = 0.f;
+      if (b < B) go = grad_out[(size_t)b * GD + j] + (grad_carry ? grad_carry[(size_t)b * GD + j] : 0.f);
+      const float dn = go * (1.f - g.z), dz = go * (sh[t][j] - g.n);
+      const float dan = dn * (1.f - g.n * g.n);
+      const float dr = dan * g.hn;
+      sa[t][0][j] = dr * g.r * (1.f - g.r);
+      sa[t][1][j] = dz * g.z * (1.f - g.z);
+      sa[t][2][j] = dan;
+      sa[t][3][j] = dan * g.r;
+      sz[t][j] = go * g.z;
+    }
+    __syncthreads();
+    {  // weight gradients: this thread owns (unit jj = t, input k = j) of all three gates of both matrices
+      const int jj = t, k = j;
+#pragma unroll
+      for (int tt = 0; tt < GT; ++tt) {
+        const float xv = sx[tt][k], hv = sh[tt][k];
+        const float ar = sa[tt][0][jj], az = sa[tt][1][jj], an = sa[tt][2][jj], ah = sa[tt][3][jj];
+        aih[0] = fmaf(ar, xv, aih[0]); aih[1] = fmaf(az, xv, aih[1]); aih[2] = fmaf(an, xv, aih[2]);
+        ahh[0] = fmaf(ar, hv, ahh[0]); ahh[1] = fmaf(az, hv, ahh[1]); ahh[2] = fmaf(ah, hv, ahh[2]);
+        if (k == 0) { abi[0] += ar; abi[1] += az; abi[2] += an; abh[0] += ar; abh[1] += az; abh[2] += ah; }
+      }
+    }
+    {  // dx[t][k], dh[t][k]
+      const int k = j;
+      float dx = 0.f, dh = sz[t][k];
+#pragma unroll
+      for (int jj = 0; jj < GD; ++jj) {
+        const float ar = sa[t][0][jj], az = sa[t][1][jj], an = sa[t][2][jj], ah = sa[t][3][jj];
+        dx = fmaf(w.wih[jj * GS + k], ar, dx); dx = fmaf(w.wih[(GD + jj) * GS + k], az, dx); dx = fmaf(w.wih[(2 * GD + jj) * GS + k], an, dx);
+        dh = fmaf(w.whh[jj * GS + k], ar, dh); dh = fmaf(w.whh[(GD + jj) * GS + k], az, dh); dh = fmaf(w.whh[(2 * GD + jj) * GS + k], ah, dh);
+      }
+      if (b < B) {
+        if (grad_x) grad_x[(size_t)b * GD + k] = dx;
+        grad_h[(size_t)b * GD + k] = dh;
+      }
+    }
+  }
+  float* out = partial + (size_t)blockIdx.x * GP;
+  const int jj = t, k = j;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    out[(g * GD + jj) * GD + k] = aih[g];
+    out[3 * GD * GD + (g * GD + jj) * GD + k] = ahh[g];
+    if (k == 0) { out[6 * GD * GD + g * GD + jj] = abi[g]; out[6 * GD * GD + 3 * GD + g * GD + jj] = abh[g]; }
+  }
+}
+
+// out[e] (+)= sum over rows k of partial[k][e], rows added in order
+__global__ void rows_sum_kernel(const float* __restrict__ partial, int rows, int len, float* __restrict__ out, int accumulate) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  float s = accumulate ? out[e] : 0.f;
+  for (int k = 0; k < rows; ++k) s += partial[(size_t)k * len + e];
+  out[e] = s;
+}
+
+int gru_grid(int B) {
+  const int tiles = (B + GT - 1) / GT, cap = sm_count() * 4;
+  return tiles < cap ? tiles : cap;
+}
+
+}  // namespace
+
+size_t odernn_log_stride(int log_capacity) { return align256(64 + (size_t)21 * (size_t)(log_capacity > 0 ? log_capacity : 0)); }
+
+size_t odernn_workspace_bytes(int B, int D, int H) {
+  const size_t dp = dopri5_small_workspace_bytes(B, D, H), bw = bwd_workspace_bytes(H * D + H + D * H + D);
+  return align256(dp > bw ? dp : bw) + sizeof(float) * (size_t)GP * (size_t)(sm_count() * 4) + 256;
+}
+
+int gru_jump_fwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, int B, int D, float* h_out, cudaStream_t st) {
+  if (D != GD) return GODE_ERR_SHAPE;
+  gru_jump_fwd_kernel<<<gru_grid(B), 256, 0, st>>>(x, h, w_ih, w_hh, b_ih, b_hh, B, h_out);
+  return launch_status();
+}
+
+// grad_params: flat [w_ih|w_hh|b_ih|b_hh]; accumulate != 0 adds to it.  workspace: gru partial rows.
+int gru_jump_bwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                 const float* b_hh, const float* grad_out, const float* grad_carry, int B, int D, float* grad_x,
+                 float* grad_h, float* grad_params, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (D != GD) return GODE_ERR_SHAPE;
+  const int grid = gru_grid(B);
+  if (ws_bytes < sizeof(float) * (size_t)GP * (size_t)grid) return GODE_ERR_WORKSPACE;
+  float* partial = reinterpret_cast<float*>(workspace);
+  gru_jump_bwd_kernel<<<grid, 256, 0, st>>>(x, h, w_ih, w_hh, b_ih, b_hh, grad_out, grad_carry, B, grad_x, grad_h, partial);
+  rows_sum_kernel<<<(GP + 255) / 256, 256, 0, st>>>(partial, grid, GP, grad_params, accumulate);
+  return launch_status();
+}
+
+int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
+               const GodeAdaptiveOpts* opts, float* codes, float* seg, unsigned char* logs, float* ckpt, double* acc,
+               void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  const double t01[2] = {0.0, 1.0};
+  const int cap = opts->log_capacity, kc = opts->ckpt_capacity;
+  const size_t ls = odernn_log_stride(cap), bd = (size_t)B * D;
+  for (int f = 0; f < F; ++f) {
+    const float* y0 = f == 0 ? h0 : codes + (size_t)(f - 1) * bd;
+    unsigned char* lg = logs + (size_t)f * ls;
+    float* tr = seg + (size_t)f * 2 * bd;
+    int rc = dopri5_small_fwd(y0, W1, b1, W2, b2, t01, B, D, H, 2, opts, GODE_LAYOUT_TBD, tr,
+                              reinterpret_cast<GodeStepLog*>(lg), reinterpret_cast<double*>(lg + 64),
+                              reinterpret_cast<double*>(lg + 64 + 8 * (size_t)cap), reinterpret_cast<float*>(lg + 64 + 16 * (size_t)cap),
+                              lg + 64 + 20 * (size_t)cap, kc > 0 ? ckpt + (size_t)f * kc * bd : nullptr,
+                              kc > 0 ? acc + (size_t)f * 2 * kc : nullptr, kc > 0 ? acc + (size_t)f * 2 * kc + kc : nullptr,
+                              workspace, ws_bytes, st);
+    if (rc) return rc;
+    rc = gru_jump_fwd(eps + (size_t)f * bd, tr + bd, w_ih, w_hh, b_ih, b_hh, B, D, codes + (size_t)f * bd, st);
+    if (rc) return rc;
+  }
+  return GODE_OK;
+}
+
+// grad_codes (F,B,D) -> grad_h0 (B,D), grad_eps (F,B,D) or null, grad_ode (P1) and grad_gru (GP) OVERWRITTEN.
+// scratch: floats [carry (B,D) | gtraj (2,B,D) | ode slots (F, P1)]
+int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+               const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
+               int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
+               const double* acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch,
+               void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  const double t01[2] = {0.0, 1.0};
+  const int P1 = H * D + H + D * H + D, kc = ckpt_capacity;
+  const size_t bd = (size_t)B * D;
+  float* carry = scratch;
+  float* gtraj = scratch + bd;
+  float* slots = scratch + 3 * bd;
+  const size_t dp_ws = align256(ws_bytes > 0 ? (dopri5_small_workspace_bytes(B, D, H) > bwd_workspace_bytes(P1)
+                                                   ? dopri5_small_workspace_bytes(B, D, H) : bwd_workspace_bytes(P1)) : 0);
+  if (ws_bytes < dp_ws + sizeof(float) * (size_t)GP * (size_t)gru_grid(B)) return GODE_ERR_WORKSPACE;
+  void* gru_ws = reinterpret_cast<unsigned char*>(workspace) + dp_ws;
+  cudaMemsetAsync(gtraj, 0, sizeof(float) * bd, st);  // no gradient reaches the solve's copy of its own input
+  for (int f = F - 1; f >= 0; --f) {
+    const float* tr = seg + (size_t)f * 2 * bd;
+    int rc = gru_jump_bwd(eps + (size_t)f * bd, tr + bd, w_ih, w_hh, b_ih, b_hh, grad_codes + (size_t)f * bd,
+                          f == F - 1 ? nullptr : carry, B, D, grad_eps ? grad_eps + (size_t)f * bd : nullptr, gtraj + bd,
+                          grad_gru, f != F - 1, gru_ws, ws_bytes - dp_ws, st);
+    if (rc) return rc;
+    const unsigned char* lg = logs + (size_t)f * log_stride;
+    rc = dopri5_small_backprop_bwd(gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD,
+                                   reinterpret_cast<const GodeStepLog*>(lg), ckpt + (size_t)f * kc * bd,
+                                   acc + (size_t)f * 2 * kc, acc + (size_t)f * 2 * kc + kc, kc, 1.0f,
+                                   f == 0 ? grad_h0 : carry, slots + (size_t)f * P1, workspace, dp_ws, st);
+    if (rc) return rc;
+  }
+  rows_sum_kernel<<<(P1 + 255) / 256, 256, 0, st>>>(slots, F, P1, grad_ode, 0);
+  return launch_status();
+}
+
+}  // namespace gode

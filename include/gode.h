@@ -202,6 +202,39 @@ int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* 
                     uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
                     void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- a6: ODE-RNN sampler (models/mocogan_ode_rnn.py:40-54) ---------------------------------------------------- */
+/* The GRU jump h_out = GRUCell(x, h) of models/mocogan_ode_rnn.py:49 (nn.GRUCell semantics, models/mocogan.py:198:
+ * gate order r, z, n; n = tanh(W_in x + b_in + r (W_hn h + b_hn)); h_out = (1 - z) n + z h).  D = 16.
+ * Parameters as PyTorch stores them: w_ih (3D,D), w_hh (3D,D), b_ih (3D), b_hh (3D); flat gradient in that order. */
+int gode_gru_param_count(int D);
+int gode_gru_jump_fwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, int B, int D, float* h_out, gode_stream_t stream);
+/* grad_x may be NULL.  grad_params is OVERWRITTEN.  workspace: gode_odernn_workspace_bytes(B, D, D). */
+int gode_gru_jump_bwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
+                      const float* b_hh, const float* grad_out, int B, int D, float* grad_x, float* grad_h,
+                      float* grad_params, void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* The whole sampler in one call: for f in 0..F-1: h' = dopri5 solve of the ODEFunc over [0,1] from h_{f-1} (h_{-1} = h0)
+ * with `opts` (the reference passes none: rtol 1e-7, atol 1e-9), h_f = GRUCell(eps[f], h').  codes: (F,B,D), codes[f] = h_f
+ * (the reference's torch.cat(...).view(-1, D), models/mocogan_ode_rnn.py:51-52, is its (B,F,D) transpose).
+ * Saved for the backward (all caller-allocated, device): seg (F,2,B,D) = each solve's [input copy, h']; logs = F slots of
+ * gode_odernn_log_stride(opts->log_capacity) bytes ([GodeStepLog | attempt arrays], as gode_dopri5_fwd lays them out);
+ * ckpt (F, ckpt_capacity, B, D) and acc (F, 2, ckpt_capacity) doubles, or NULL with opts->ckpt_capacity = 0 (no backward). */
+size_t gode_odernn_log_stride(int log_capacity);
+size_t gode_odernn_workspace_bytes(int B, int D, int H);
+int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H,
+                    int F, const GodeAdaptiveOpts* opts, float* codes, float* seg, void* logs, float* ckpt, double* acc,
+                    void* workspace, size_t ws_bytes, gode_stream_t stream);
+/* Reverse-mode through the F (solve, jump) pairs: GRU VJP, then the discrete adjoint of that frame's recorded solve.
+ * grad_eps may be NULL.  grad_ode ([W1|b1|W2|b2]) and grad_gru are OVERWRITTEN (per-frame slots summed in frame order).
+ * scratch: (3*B*D + F*gode_param_count(D,H)) floats. */
+int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
+                    const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
+                    int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
+                    const float* ckpt, const double* acc, float* grad_h0, float* grad_eps, float* grad_ode,
+                    float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, gode_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -235,3 +235,15 @@ def test_cuda_caller_reproduces_reference_run_odernn(cuda_as_torchdiffeq):
     z = load("reference_sample_z_m_odernn")
     m = _caller_rnn(z, DEV)
     _check_caller(z, m, m.sample_z_m(z["h0"].shape[0], h0=T(z["h0"]), eps=T(z["eps"])), 2e-5, 1e-3, DEV)
+
+
+@pytest.mark.gpu
+def test_cuda_fused_odernn_reproduces_reference_run():
+    """The one-call sampler (gode.odernn_codes: C-level frame loop + fused GRU jump) on the fixture made by the
+    unmodified models/mocogan_ode_rnn.py."""
+    _need_gpu()
+    import gan_ode_b200 as gode
+    z = load("reference_sample_z_m_odernn")
+    m = _caller_rnn(z, DEV)
+    codes = gode.odernn_codes(m.ode_fn, m.recurrent, T(z["h0"], DEV), T(z["eps"], DEV))
+    _check_caller(z, m, codes.transpose(0, 1).reshape(-1, 16), 2e-5, 1e-3, DEV)

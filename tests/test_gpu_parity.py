@@ -743,3 +743,78 @@ def test_dopri5_per_trajectory_large_batch_and_ragged():
         with torch.no_grad():
             ref = gode.odeint(f, y0, _t16(), method="rk4")   # both integrate the same ODE: agree to solver tolerance
         assert rel_err(sol, ref) <= 5e-4
+
+
+# ---- ODE-RNN fused path (a6): GRU jump kernel and the one-call sampler ---------------------------------------------------------
+@pytest.mark.parametrize("B", [1, 37, 4096])
+def test_gru_jump_matches_nn_grucell(B):
+    _need_gpu()
+    torch.manual_seed(B)
+    cell = torch.nn.GRUCell(16, 16)
+    x, h, go = torch.randn(B, 16), torch.randn(B, 16), torch.randn(B, 16)
+
+    def run(fn, c, xx, hh, gg):
+        xx, hh = xx.clone().requires_grad_(True), hh.clone().requires_grad_(True)
+        out = fn(xx, hh, c)
+        return out.detach(), torch.autograd.grad((out * gg).sum(), [xx, hh] + list(c.parameters()))
+
+    ref, ref_g = run(lambda a, b, c: c(a, b), cell.double(), x.double(), h.double(), go.double())
+    import copy
+    out, out_g = run(gode.gru_jump, copy.deepcopy(cell).float().to(DEV), x.to(DEV), h.to(DEV), go.to(DEV))
+    assert rel_err(out, ref) <= TOL
+    for a, b in zip(out_g, ref_g):
+        assert rel_err(a, b) <= TOL, rel_err(a, b)
+
+
+def test_odernn_fused_sampler_matches_oracle_and_unfused_path(monkeypatch):
+    """gode.odernn_codes (one C call per direction) against the reference loop on the CPU oracle (continuous adjoint,
+    default tolerances) and against the unfused shim path on the GPU (same kernels for the solves)."""
+    _need_gpu()
+    import sys
+    import types
+    from tests.caller_model import LatentMotionODERNN
+
+    torch.manual_seed(5)
+    F, B = 6, 40
+    cpu_model = LatentMotionODERNN(16, F)
+    gpu_model = LatentMotionODERNN(16, F)
+    gpu_model.load_state_dict(cpu_model.state_dict())
+    gpu_model.to(DEV)
+    h0, eps, w = torch.randn(B, 16), torch.randn(F, B, 16), torch.randn(B * F, 16)
+
+    shim = types.ModuleType("torchdiffeq")
+    shim.odeint, shim.odeint_adjoint = tdq.odeint, tdq.odeint_adjoint
+    monkeypatch.setitem(sys.modules, "torchdiffeq", shim)
+    ref = cpu_model.sample_z_m(B, h0=h0, eps=eps)
+    (ref * w).sum().backward()
+    monkeypatch.delitem(sys.modules, "torchdiffeq")
+
+    h0g, epsg = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+    codes = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg)
+    out = codes.transpose(0, 1).reshape(-1, 16)     # models/mocogan_ode_rnn.py:51-52
+    (out * w.to(DEV)).sum().backward()
+    assert out.shape == (B * F, 16)
+    assert rel_err(out, ref) <= 2e-5
+    for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        assert rel_err(p.grad, q.grad) <= 1e-3, (n, rel_err(p.grad, q.grad))
+    fused = {n: p.grad.clone() for n, p in gpu_model.named_parameters()}
+    logs = gode.odernn.last_log().frames()
+    assert len(logs) == F and all(l["status"] == 0 and l["n_accepted"] >= 1 for l in logs)
+
+    # unfused path: the reference loop through the shim, nn.GRUCell in PyTorch
+    gpu_model.zero_grad()
+    gode.install_shims()
+    try:
+        h0u, epsu = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+        out_u = gpu_model.sample_z_m(B, h0=h0u, eps=epsu)
+        (out_u * w.to(DEV)).sum().backward()
+    finally:
+        sys.modules.pop("torchdiffeq", None)
+        sys.modules.pop("torchsde", None)
+    assert rel_err(out, out_u) <= 1e-5
+    assert rel_err(h0g.grad, h0u.grad) <= 2e-5 and rel_err(epsg.grad, epsu.grad) <= 2e-5
+    for n, p in gpu_model.named_parameters():
+        assert rel_err(fused[n], p.grad) <= 5e-5, (n, rel_err(fused[n], p.grad))
+    # deterministic
+    codes2 = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg)
+    assert torch.equal(codes, codes2)
