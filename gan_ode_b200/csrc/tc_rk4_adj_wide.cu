@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
   float* red = reinterpret_cast<float*>(smem + OFF_RED);
   uint64_t* mbar_w = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* mbar_m = mbar_w + 1;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_w + 2);
+  uint64_t* mbar_b = mbar_w + 2;  // completion of the dW2^T MMAs (they read HD, which the d' epilogue overwrites)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_w + 3);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform (keeps MMA descriptors in uniform registers)
   const int q = warp & 3, hf = warp >> 2, row = q * 32 + lane;
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
   if (tid == 0) {
     tc::mbar_init(mbar_w, 1);
     tc::mbar_init(mbar_m, 1);
+    tc::mbar_init(mbar_b, 1);
     tc::mbar_fence_init();
   }
   tc::fence_before_sync();
@@ -140,17 +142,19 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
   constexpr uint32_t id_v = tc::make_idesc(tc::kFmtBF16, 128, 64) | B_MN;
   constexpr uint32_t id_w2 = tc::make_idesc(tc::kFmtBF16, 128, 64) | A_MN | B_MN;
   constexpr uint32_t id_w1 = tc::make_idesc(tc::kFmtBF16, 128, NE) | A_MN | B_MN;
-  uint32_t phase = 0;
+  uint32_t phase = 0, phase_b = 0;
   uint32_t acc_live = 0;  // 0 until the weight-gradient accumulators have been written once
 
-  auto sync_issue = [&](auto&& issue) {  // operands written by all threads -> one elected lane issues -> everybody waits
+  // operands written by all threads -> one elected lane issues (the lambda ends with the commit(s) it wants) -> everybody
+  // waits for mbar_m.  MMAs issued AFTER the commit to mbar_m keep running under the epilogue that follows; the tensor
+  // pipe completes MMAs in issue order, so any later completed commit also covers them.
+  auto sync_issue = [&](auto&& issue) {
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0 && tc::elect_one()) {
       tc::fence_after_sync();
       issue();
-      tc::mma_commit(mbar_m);
     }
     tc::mbar_wait(mbar_m, phase);
     phase ^= 1;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
         // ---- z1 -> h (two halves of 128 hidden units) ----
 #pragma unroll 1
         for (int h2 = 0; h2 < 2; ++h2) {
-          sync_issue([&] { issue_z(cur, h2); });
+          sync_issue([&] { issue_z(cur, h2); tc::mma_commit(mbar_m); });
 #pragma unroll
           for (int cc = 0; cc < 4; cc += 2) {
             uint32_t za[16], zb[16];
@@ -233,7 +237,7 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
             *reinterpret_cast<uint4*>(HD + (size_t)((kc + 3) * TILE + row) * 16) = make_uint4(qb[4], qb[5], qb[6], qb[7]);
           }
         }
-        // ---- f = h W2^T (not needed after the last stage), dW2^T += h^T (c a), g' half 0 ----
+        // ---- f = h W2^T (not needed after the last stage), g' half 0; then dW2^T += h^T (c a) under the y epilogue ----
         sync_issue([&] {
           if (s < 3) {
             const uint64_t dA = tc::make_smem_desc(sHD, TILE * 16, 128);
@@ -241,6 +245,8 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < H / 16; ++k) tc::mma_ss<false>(tmem + T_F, adv(dA, k * 2 * TILE * 16), adv(dB, k * 2 * D * 16), id_f, k > 0);
           }
+          issue_g(0);
+          tc::mma_commit(mbar_m);
           const uint64_t dBa = tc::make_smem_desc(sAA, 128, TILE * 16);
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh) {
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
             for (int k = 0; k < TILE / 16; ++k)
               tc::mma_ss<false>(tmem + T_W2T + mh * D, adv(dAh, k * 256), adv(dBa, k * 256), id_w2, acc_live | (uint32_t)(k > 0));
           }
-          issue_g(0);
+          tc::mma_commit(mbar_b);
         });
         // y part of the 3/8 step in reversed time: ky = -f.  Packs the next stage's u into the other A1 buffer.
         if (s < 3) {
@@ -267,10 +273,12 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
           }
           pack32(A1n, un, 1.f);
         }
-        // ---- d' = g' (1 - h^2), written over h; second g' half in between ----
+        // ---- d' = g' (1 - h^2), written over h (once dW2^T has read it); second g' half in between ----
+        tc::mbar_wait(mbar_b, phase_b);
+        phase_b ^= 1;
 #pragma unroll 1
         for (int h2 = 0; h2 < 2; ++h2) {
-          if (h2 == 1) sync_issue([&] { issue_g(1); });
+          if (h2 == 1) sync_issue([&] { issue_g(1); tc::mma_commit(mbar_m); });
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             uint32_t g16[16];
@@ -291,12 +299,14 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
             *p1 = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
-        // ---- v' = d' W1 and [dW1|db1] += d'^T [u|1] ----
+        // ---- v' = d' W1; then [dW1|db1] += d'^T [u|1], which nothing waits for: it runs under the a epilogue and the next
+        // stage's packing, and the next commit (z1 of the next stage, or the final one) covers it ----
         sync_issue([&] {
           const uint64_t dA = tc::make_smem_desc(sHD, TILE * 16, 128);
           const uint64_t dB = tc::make_smem_desc(sB1, 128, H * 16);
 #pragma unroll
           for (int k = 0; k < H / 16; ++k) tc::mma_ss<false>(tmem + T_ZG, adv(dA, k * 2 * TILE * 16), adv(dB, k * 256), id_v, k > 0);
+          tc::mma_commit(mbar_m);
           const uint64_t dBu = tc::make_smem_desc(sA1 + cur * A1_BYTES, 128, TILE * 16);
 #pragma unroll
           for (int mh = 0; mh < 2; ++mh) {
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(256, 1) tc_rk4_adj_wide_kernel(const __grid_co
 
   // ---- this CTA's partial: accumulators out of TMEM + db2 ----
   float* part = p.partial + (size_t)blockIdx.x * PART;
-  tc::fence_after_sync();
+  sync_issue([&] { tc::mma_commit(mbar_m); });  // drains the last [dW1|db1] MMAs
 #pragma unroll 1
   for (int mh = 0; mh < 2; ++mh) {
     const int j = mh * 128 + row;
