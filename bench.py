@@ -236,8 +236,15 @@ def run_gpu(args):
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    out_fd = 1
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
+        # stdout must carry exactly ONE JSON line (rank 0).  NCCL prints its version banner (and anything NCCL_DEBUG asks
+        # for) on fd 1 from native code, so fd 1 is pointed at stderr for the whole run and the JSON line is written to
+        # the saved descriptor at the end.
+        sys.stdout.flush()
+        out_fd = os.dup(1)
+        os.dup2(2, 1)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         gode.config.grad_allreduce = True
     n_gpus = world
@@ -458,7 +465,8 @@ def run_gpu(args):
         "eager_ms_per_step": eager_ms / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(out_fd, (json.dumps(line) + "\n").encode())
     finish()
 
 
