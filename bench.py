@@ -246,7 +246,10 @@ def run_gpu(args):
         os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-        gode.config.grad_allreduce = True
+        from gan_ode_b200.dist import enable_p2p_allreduce
+        p2p = False if args.nccl_allreduce else enable_p2p_allreduce()
+        if not p2p:
+            gode.config.grad_allreduce = True
     n_gpus = world
 
     f, y0, grad, t = make_inputs(seed=rank, device=dev)
@@ -457,11 +460,14 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": dict(CONFIG, global_batch=B_PER_GPU * n_gpus, cuda_graph=graphed,
                                             attempted_steps=n_att, accepted_steps=n_acc,
-                                            parallelism="dp{}".format(n_gpus)),
+                                            parallelism="dp{}".format(n_gpus),
+                                            grad_allreduce=("none (1 GPU)" if n_gpus == 1 else
+                                                            "fused one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
+                                                            if callable(gode.config.grad_allreduce) else "ncclAllReduce")),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
                 "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": (2 + (1 if n_gpus > 1 and callable(gode.config.grad_allreduce) else 0)) * args.steps,
         "eager_ms_per_step": eager_ms / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
     }
@@ -478,6 +484,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "
+                    "of the fused peer-memory kernel")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch / wide-field side measurements")
     args = ap.parse_args()
     if args.impl == "reference":

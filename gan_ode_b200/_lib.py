@@ -60,6 +60,7 @@ _SIGS = {
     "gode_odernn_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_odernn_fwd": (_I, [_P] * 10 + [_I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts)] + [_P] * 6 + [C.c_size_t, _P]),
     "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 10 + [C.c_size_t, _P]),
+    "gode_allreduce_p2p": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "gode_sde_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_sde_em_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P]),
     "gode_sde_em_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P,

@@ -249,4 +249,11 @@ int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, 
                     grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* pads_dev, int rank, int world, int cap,
+                       uint32_t* epoch_ctr, gode_stream_t stream) {
+  if (!data || n <= 0 || !bufs_dev || !pads_dev || !epoch_ctr) return GODE_ERR_ARG;
+  return p2p_allreduce(data, n, reinterpret_cast<float* const*>(bufs_dev), reinterpret_cast<unsigned int* const*>(pads_dev),
+                       rank, world, cap, epoch_ctr, (cudaStream_t)stream);
+}
+
 }  // extern "C"

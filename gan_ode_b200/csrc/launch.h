@@ -120,6 +120,8 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
                int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
                const double* acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch,
                void* workspace, size_t ws_bytes, cudaStream_t st);
+int p2p_allreduce(float* data, int n, float* const* bufs_dev, unsigned int* const* pads_dev, int rank, int world, int cap,
+                  unsigned int* epoch_ctr, cudaStream_t st);
 inline bool tc_shape(int D, int H) { return D == 16 && H == 16; }
 inline bool tc_wide_shape(int D, int H) { return D == 64 && H == 256; }  // BF16 only
 

@@ -13,7 +13,8 @@ import torch.distributed as dist
 
 _api = importlib.import_module(__package__ + ".odeint")
 
-__all__ = ["shard_bounds", "shard_batch", "enable_grad_allreduce", "disable_grad_allreduce", "philox_for_shard"]
+__all__ = ["shard_bounds", "shard_batch", "enable_grad_allreduce", "disable_grad_allreduce", "philox_for_shard",
+           "enable_p2p_allreduce", "P2PAllReduce"]
 
 
 def shard_bounds(B: int, rank: int, world: int) -> Tuple[int, int]:
@@ -47,3 +48,46 @@ def philox_for_shard(seed: int, y0: torch.Tensor, rank: int = None, world: int =
     from .sdeint import PhiloxBrownian
     local, lo = shard_batch(y0, rank, world)
     return local, PhiloxBrownian(seed, traj_offset=lo)
+
+
+class P2PAllReduce:
+    """One-shot all-reduce of small fp32 vectors over NVLink peer memory (csrc/p2p_allreduce.cu), built on torch's
+    symmetric-memory rendezvous for the address exchange only.  `cap` floats per vector at most."""
+
+    small = 8192  # floats up to which the single-CTA kernel beats ncclAllReduce (measured: 544 floats 11 vs 17 us at N=2)
+
+    def __init__(self, group=None, cap: int = 65536):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank, self.cap = dist.get_world_size(group), dist.get_rank(group), int(cap)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.buf = symm_mem.empty(2 * self.world * self.cap, dtype=torch.float32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        if self.hdl.signal_pad_size < 8 * self.world:
+            raise RuntimeError("symmetric-memory signal pad too small")
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._lib = _lib
+        self.hdl.barrier()  # signal pads are zero-initialised by torch; make sure every rank has mapped everything
+
+    def __call__(self, flat: torch.Tensor):
+        assert flat.dtype is torch.float32 and flat.is_contiguous() and flat.numel() <= self.cap
+        L = self._lib.lib()
+        self._lib.check(L.gode_allreduce_p2p(flat.data_ptr(), flat.numel(), self.hdl.buffer_ptrs_dev,
+                                             self.hdl.signal_pad_ptrs_dev, self.rank, self.world, self.cap,
+                                             self.epoch.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                        "gode_allreduce_p2p")
+        return flat
+
+
+def enable_p2p_allreduce(group=None, cap: int = 65536) -> bool:
+    """Route the parameter-gradient exchange through the fused peer-memory kernel instead of NCCL.  Returns False (and
+    leaves the NCCL path in place) if symmetric memory cannot be set up on this system."""
+    try:
+        _api.config.grad_allreduce = P2PAllReduce(group, cap)
+        return True
+    except Exception as e:  # noqa: BLE001
+        import sys
+        sys.stderr.write("[gan_ode_b200] peer-memory all-reduce unavailable ({}); using NCCL\n".format(str(e)[:200]))
+        _api.config.grad_allreduce = True if group is None else group
+        return False

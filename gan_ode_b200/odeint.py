@@ -156,6 +156,11 @@ def _maybe_allreduce(flat):
     g = config.grad_allreduce
     if g is None or g is False:
         return
+    if callable(g):          # gan_ode_b200.dist.P2PAllReduce: fused one-shot kernel over NVLink peer memory
+        if flat.numel() <= g.small and not (flat.data_ptr() & 15):  # larger vectors: NCCL's multi-channel ring wins
+            g(flat)
+            return
+        g = True
     import torch.distributed as dist
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=None if g is True else g)
 

@@ -235,6 +235,17 @@ int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, 
                     const float* ckpt, const double* acc, float* grad_h0, float* grad_eps, float* grad_ode,
                     float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- e: data-parallel exchange ------------------------------------------------------------------------------------ */
+/* One-shot all-reduce (sum, in place) of `n` floats over peer memory (NVLink / NVSwitch), the fused alternative to
+ * ncclAllReduce for the flat parameter-gradient buffer a backward kernel has just written on the same stream.
+ * bufs_dev / pads_dev: DEVICE arrays of `world` pointers to every rank's symmetric buffer (2 * world * cap floats) and
+ * signal pad (>= 2 * world uint32, zero-initialised) as mapped into THIS process (e.g. torch symmetric memory's
+ * buffer_ptrs_dev / signal_pad_ptrs_dev).  epoch_ctr: one zero-initialised device uint32 owned by this rank.
+ * Every rank must issue the same sequence of calls.  Slots are added in rank order: results are bit-identical on all
+ * ranks and from run to run.  data must be 16-byte aligned, n <= cap, cap % 4 == 0. */
+int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* pads_dev, int rank, int world, int cap,
+                       uint32_t* epoch_ctr, gode_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

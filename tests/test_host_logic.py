@@ -82,3 +82,31 @@ def test_shims_register_both_packages():
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_grad_exchange_hook_prefers_the_fused_kernel_for_small_vectors_only():
+    """odeint._maybe_allreduce: a callable in config.grad_allreduce (gan_ode_b200.dist.P2PAllReduce on a GPU box) gets the
+    small flat gradient buffers; anything larger than its `small` threshold goes to torch.distributed."""
+    import torch
+    from gan_ode_b200 import odeint as api
+
+    calls = []
+
+    class Fake:
+        small, cap = 1024, 65536
+
+        def __call__(self, flat):
+            calls.append(flat.numel())
+            return flat
+
+    prev = api.config.grad_allreduce
+    api.config.grad_allreduce = Fake()
+    try:
+        api._maybe_allreduce(torch.zeros(544))
+        assert calls == [544]
+        import pytest
+        with pytest.raises(Exception):  # no process group here: the large vector must have been routed to dist.all_reduce
+            api._maybe_allreduce(torch.zeros(4096))
+        assert calls == [544]
+    finally:
+        api.config.grad_allreduce = prev
