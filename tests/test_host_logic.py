@@ -87,8 +87,9 @@ def test_shims_register_both_packages():
 def test_grad_exchange_hook_prefers_the_fused_kernel_for_small_vectors_only():
     """odeint._maybe_allreduce: a callable in config.grad_allreduce (gan_ode_b200.dist.P2PAllReduce on a GPU box) gets the
     small flat gradient buffers; anything larger than its `small` threshold goes to torch.distributed."""
+    import importlib
     import torch
-    from gan_ode_b200 import odeint as api
+    api = importlib.import_module("gan_ode_b200.odeint")
 
     calls = []
 
