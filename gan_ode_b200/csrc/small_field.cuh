@@ -143,38 +143,37 @@ struct BwdLines {   // mlp_forward + VJP
   }
 };
 
-// dot of a register row with a padded shared line, two partial sums for ILP
+// Dot products run on packed FP32 FMAs (FFMA2, sm_100): two FMAs per issue slot at the same 128 FMA/clk/SM
+// (scripts/ffma2_bench.cu).  ONE packed accumulator = the same two partial sums (even / odd elements) and the same single
+// final add as a two-accumulator scalar loop: the FMA pipe, which bounds these kernels at large batch, does no extra work.
+
+// dot of a register row with a padded shared line
 template <int N>
 __device__ __forceinline__ float dot_line(const float (&w)[N], const float* __restrict__ line, float init) {
-  float s0 = init, s1 = 0.f;
+  static_assert(N % 4 == 0, "rows are multiples of 4 floats");
+  float2 s = make_float2(init, 0.f);
 #pragma unroll
-  for (int i = 0; i < N; i += 8) {
+  for (int i = 0; i < N; i += 4) {
     const float4 v = *reinterpret_cast<const float4*>(line + i);
-    s0 = fmaf(w[i], v.x, s0); s0 = fmaf(w[i + 1], v.y, s0); s0 = fmaf(w[i + 2], v.z, s0); s0 = fmaf(w[i + 3], v.w, s0);
-    if (i + 4 < N) {
-      const float4 u = *reinterpret_cast<const float4*>(line + i + 4);
-      s1 = fmaf(w[i + 4], u.x, s1); s1 = fmaf(w[i + 5], u.y, s1); s1 = fmaf(w[i + 6], u.z, s1); s1 = fmaf(w[i + 7], u.w, s1);
-    }
+    s = __ffma2_rn(make_float2(w[i], w[i + 1]), make_float2(v.x, v.y), s);
+    s = __ffma2_rn(make_float2(w[i + 2], w[i + 3]), make_float2(v.z, v.w), s);
   }
-  return s0 + s1;
+  return s.x + s.y;
 }
 
 // dot of a shared weight row with a shared line (both padded, float4)
 template <int N>
 __device__ __forceinline__ float dot_smem(const float* __restrict__ wrow, const float* __restrict__ line) {
-  float s0 = 0.f, s1 = 0.f;
+  static_assert(N % 4 == 0, "rows are multiples of 4 floats");
+  float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < N; i += 8) {
+  for (int i = 0; i < N; i += 4) {
     const float4 w = *reinterpret_cast<const float4*>(wrow + i);
     const float4 v = *reinterpret_cast<const float4*>(line + i);
-    s0 = fmaf(w.x, v.x, s0); s0 = fmaf(w.y, v.y, s0); s0 = fmaf(w.z, v.z, s0); s0 = fmaf(w.w, v.w, s0);
-    if (i + 4 < N) {
-      const float4 w2 = *reinterpret_cast<const float4*>(wrow + i + 4);
-      const float4 v2 = *reinterpret_cast<const float4*>(line + i + 4);
-      s1 = fmaf(w2.x, v2.x, s1); s1 = fmaf(w2.y, v2.y, s1); s1 = fmaf(w2.z, v2.z, s1); s1 = fmaf(w2.w, v2.w, s1);
-    }
+    s = __ffma2_rn(make_float2(w.x, w.y), make_float2(v.x, v.y), s);
+    s = __ffma2_rn(make_float2(w.z, w.w), make_float2(v.z, v.w), s);
   }
-  return s0 + s1;
+  return s.x + s.y;
 }
 
 // ---- the vector field --------------------------------------------------------------------------------------
@@ -223,10 +222,12 @@ struct GradAcc {
 template <int N>
 __device__ __forceinline__ void axpy_line(float (&acc)[N], float s, const float* __restrict__ line) {
 #pragma unroll
-  for (int i = 0; i < N; i += 4) {
+  const float2 ss = make_float2(s, s);
+  for (int i = 0; i < N; i += 4) {  // packed FMAs: same arithmetic per element as the scalar form, half the issue slots
     const float4 v = *reinterpret_cast<const float4*>(line + i);
-    acc[i] = fmaf(s, v.x, acc[i]); acc[i + 1] = fmaf(s, v.y, acc[i + 1]);
-    acc[i + 2] = fmaf(s, v.z, acc[i + 2]); acc[i + 3] = fmaf(s, v.w, acc[i + 3]);
+    const float2 lo = __ffma2_rn(ss, make_float2(v.x, v.y), make_float2(acc[i], acc[i + 1]));
+    const float2 hi = __ffma2_rn(ss, make_float2(v.z, v.w), make_float2(acc[i + 2], acc[i + 3]));
+    acc[i] = lo.x; acc[i + 1] = lo.y; acc[i + 2] = hi.x; acc[i + 3] = hi.y;
   }
 }
 
