@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(128, 5) tc_rk4_fwd_kernel(const __grid_constan
   uint64_t* mbar_w = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
   uint64_t* mbar_m = mbar_w + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(mbar_w + 2);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform: MMA descriptors stay in uniform registers
 
   if (warp == 0) tc::tmem_alloc(s_tmem, S::NCOLS);
   if (tid == 0) {
@@ -97,7 +98,7 @@ __global__ void __launch_bounds__(128, 5) tc_rk4_fwd_kernel(const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = *s_tmem;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *s_tmem, 0);
   const uint32_t my_tmem = tmem + ((uint32_t)(warp * 32) << 16);
 
   // weights: TMA bulk copies, once per CTA
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(128, 5) tc_rk4_fwd_kernel(const __grid_constan
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::fence_after_sync();
 #pragma unroll
       for (int j = 0; j < S::NM1; ++j)
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(128, 5) tc_rk4_fwd_kernel(const __grid_constan
     tc::fence_async_smem();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && tc::elect_one()) {
       tc::fence_after_sync();
 #pragma unroll
       for (int j = 0; j < S::NM2; ++j)
