@@ -194,6 +194,15 @@ def measure_extras(gode, dev):
         "trajectory_steps_per_s": B2 * 15 / (sec_f + sec_b), "fwd_ms": sec_f * 1e3, "bwd_ms": sec_b * 1e3,
         "fp32_tflops": B2 * 15 * 16384 / (sec_f + sec_b) / 1e12,
         "hbm_frac": (B2 * 15 * 192 / (sec_f + sec_b) / 1e9) / hbm}
+    # the same shape with both directions on tcgen05 (bf16 operands): forward tc_rk4_fwd_kernel + adjoint tc_rk4_adj_small_kernel
+    o16 = {"precision": "bf16", "bwd_precision": "bf16"}
+    sol = gode.odeint_adjoint(f16, y0r, t, method="rk4", options=o16)
+    sec_b = timeit(lambda: torch.autograd.grad(sol, [y0r] + list(f16.parameters()), g, retain_graph=True))
+    with torch.no_grad():
+        sec_f = timeit(lambda: gode.odeint(f16, y0r, t, method="rk4", options=o16))
+    out["tc_rk4_fwd_adjoint_D16_H16_B262144_bf16"] = {
+        "trajectory_steps_per_s": B2 * 15 / (sec_f + sec_b), "fwd_ms": sec_f * 1e3, "bwd_ms": sec_b * 1e3,
+        "hbm_frac": (B2 * 15 * 192 / (sec_f + sec_b) / 1e9) / hbm}
     del y0, y0r, g, sol
     fw = clone_to(make_field(64, 256, seed=0), dev)
     for B3 in (148 * 128, 4 * 296 * 128):  # one tile per SM (latency regime) / four rounds of two tiles per SM

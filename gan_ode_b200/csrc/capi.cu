@@ -60,7 +60,10 @@ size_t gode_rk4_bwd_workspace_bytes(int B, int D, int H, int T) {
     const size_t a = wide_bwd_workspace_bytes(B, D, H, T), b = tc_wide_shape(D, H) ? tc_rk4_adj_wide_workspace_bytes(B) : 0;
     return a > b ? a : b;
   }
-  return bwd_workspace_bytes(gode_param_count(D, H));
+  {
+    const size_t a = bwd_workspace_bytes(gode_param_count(D, H)), b = tc_shape(D, H) ? tc_rk4_adj_small_workspace_bytes(B) : 0;
+    return a > b ? a : b;
+  }
 }
 
 static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
@@ -72,6 +75,9 @@ static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_tra
   if (precision == GODE_PREC_BF16 && tc_wide_shape(D, H) && adjoint)  // tensor-core continuous adjoint (wide field)
     return tc_rk4_adj_wide(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
                            workspace, ws_bytes, (cudaStream_t)stream);
+  if (precision == GODE_PREC_BF16 && tc_shape(D, H) && adjoint)       // tensor-core continuous adjoint (reference shape)
+    return tc_rk4_adj_small(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                            workspace, ws_bytes, (cudaStream_t)stream);
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
   if (wide_shape(D, H)) {
     if (!adjoint) return GODE_ERR_SHAPE;  // wide backprop-through-solver: not built

@@ -122,6 +122,10 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
                void* workspace, size_t ws_bytes, cudaStream_t st);
 int p2p_allreduce(float* data, int n, float* const* bufs_dev, unsigned int* const* pads_dev, int rank, int world, int cap,
                   unsigned int* epoch_ctr, cudaStream_t st);
+size_t tc_rk4_adj_small_workspace_bytes(int B);
+int tc_rk4_adj_small(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                     const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
+                     float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
 inline bool tc_shape(int D, int H) { return D == 16 && H == 16; }
 inline bool tc_wide_shape(int D, int H) { return D == 64 && H == 256; }  // BF16 only
 

@@ -18,7 +18,8 @@ Extra keys accepted in `options` (ignored by torchdiffeq, so reference code neve
   layout    : 'tbd' (default) | 'btd'                 memory order of the returned (T,B,D) tensor; 'btd' makes the
                                                       caller's .transpose(0,1).reshape(-1,D) a free view
   check     : bool (default False)                    synchronise and raise solver asserts eagerly
-  bwd_precision : 'bf16' (default) | 'fp32'           wide field in bf16 mode only: tensor-core adjoint or the FP32 one
+  bwd_precision : 'bf16' | 'fp32'                     bf16 mode + odeint_adjoint: adjoint on tcgen05 or on the FP32 kernels
+                                                      (default: 'bf16' for D=64/H=256, 'fp32' for D=H=16)
 """
 from __future__ import annotations
 
@@ -218,9 +219,12 @@ class _Rk4(torch.autograd.Function):
         # Everything else backpropagates with the FP32 kernels, re-solving from the stored (tensor-core) trajectory,
         # which keeps the gradient inside the 2e-3 budget of the tf32/bf16 modes.
         bwd_prec = _lib.PREC["fp32"]
-        if meta["adjoint"] and meta["precision"] == _lib.PREC["bf16"] and (D, H) == (64, 256) \
-                and meta.get("bwd_precision", "bf16") == "bf16":
-            bwd_prec = _lib.PREC["bf16"]
+        want = meta.get("bwd_precision")
+        if meta["adjoint"] and meta["precision"] == _lib.PREC["bf16"]:
+            if (D, H) == (64, 256) and want in (None, "bf16"):     # default for the wide field
+                bwd_prec = _lib.PREC["bf16"]
+            elif (D, H) == (16, 16) and want == "bf16":            # opt-in for the reference shape (tc_rk4_adj_small.cu)
+                bwd_prec = _lib.PREC["bf16"]
         rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
                 dt_dev, B, D, H, T, bwd_prec, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
                 ws.data_ptr(), ws_bytes, _stream())
@@ -529,7 +533,7 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
         t = t.to(y0.device)
     meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)),
-                bwd_precision=options.get("bwd_precision", "bf16"))
+                bwd_precision=options.get("bwd_precision"))
 
     if method == "rk4":
         dt = _rk4_dt(t, options, y0.device)

@@ -444,6 +444,30 @@ def test_rk4_tensor_core_forward_with_adjoint_gradients(precision):
         assert rel_err(a, b) <= TC_TOL
 
 
+@pytest.mark.parametrize("B", [1, 300, 50000])
+@pytest.mark.parametrize("layout", ["tbd", "btd"])
+def test_rk4_tensor_core_adjoint_reference_shape(B, layout):
+    """D=H=16 continuous adjoint on tcgen05 (csrc/tc_rk4_adj_small.cu, opt-in bwd_precision='bf16'): grad_y0 within the
+    tensor-core tolerance, parameter gradients within 2x (all operands of all contractions are bf16); deterministic."""
+    _need_gpu()
+    f = make_field(seed=B + 3)
+    t = _t16()
+    y0 = torch.randn(B, 16)
+    g = torch.randn(16, B, 16)
+
+    def run(fn, field, y, gg, **k):
+        y = y.clone().requires_grad_(True)
+        return torch.autograd.grad((fn(field, y, t, method="rk4", **k) * gg).sum(), [y] + list(field.parameters()))
+
+    ref = run(tdq.odeint_adjoint, f, y0, g)
+    opts = {"precision": "bf16", "bwd_precision": "bf16", "layout": layout}
+    out = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options=opts)
+    errs = [rel_err(a, b) for a, b in zip(out, ref)]
+    assert errs[0] <= TC_TOL and max(errs) <= 2 * TC_TOL, errs
+    again = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options=opts)
+    assert all(torch.equal(a, b) for a, b in zip(out, again))
+
+
 # ---- ODE-RNN call path (a6): reference loop unchanged, dopri5 default tolerances, GRU jump in PyTorch ------------------
 def test_odernn_caller_through_shim_matches_oracle(monkeypatch):
     _need_gpu()
