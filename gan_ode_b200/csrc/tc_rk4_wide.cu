@@ -266,6 +266,12 @@ struct TcWide2Shape {
 };
 
 __device__ __forceinline__ uint32_t tcw2_hcol(int c) { return 8u * c; }
+#ifndef GODE_TANH_FMA_EVERY
+#define GODE_TANH_FMA_EVERY 1000
+#endif
+constexpr int kTanhFmaEvery = GODE_TANH_FMA_EVERY;  // one pair in every kTanhFmaEvery goes to the FMA pipe (1000: none).
+// Measured (B = 151 552): none 844 us, every 4th pair 858 us, every 2nd pair 930 us -- the extra ~11 issue slots per pair
+// cost more than the MUFU cycles they free with only two epilogue warps per scheduler, so the default is OFF.
 
 template <int D, int H>
 __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_constant__ TcWideArgs p) {
@@ -351,8 +357,14 @@ __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_c
   auto tanh_chunk = [&](const uint32_t(&z)[16], int c) {
     uint32_t q[8];
 #pragma unroll
-    for (int i = 0; i < 16; i += 2)
-      q[i / 2] = tc::pack_bf16x2(tc::tanh_approx(__uint_as_float(z[i])), tc::tanh_approx(__uint_as_float(z[i + 1])));
+    for (int i = 0; i < 16; i += 2) {
+      if ((i / 2) % kTanhFmaEvery == kTanhFmaEvery - 1) {  // this pair on the FMA pipe + one MUFU.RCP (tc_common.cuh)
+        const float2 th = tc::tanh_pair_fma(__uint_as_float(z[i]), __uint_as_float(z[i + 1]));
+        q[i / 2] = tc::pack_bf16x2(th.x, th.y);
+      } else {
+        q[i / 2] = tc::pack_bf16x2(tc::tanh_approx(__uint_as_float(z[i])), tc::tanh_approx(__uint_as_float(z[i + 1])));
+      }
+    }
     tc::tmem_st8(my_tmem + tcw2_hcol(c), q);
   };
   // layer-2 MMAs: 16 K steps, A = packed h in TMEM (half j/8, 8 columns per step), D = this group's columns [64,128)
@@ -411,9 +423,9 @@ __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_c
       tc::tmem_ld_wait();
     }
     TCW_T(3);
-    tc::tmem_st_wait();
+    if (!last_token) tc::named_bar_arrive(tok_other, 512);  // hand the MUFU pipe to the other group (our last tanh ops are
+    tc::tmem_st_wait();                                     // issued; the stores drain while the other group starts)
     tc::fence_before_sync();
-    if (!last_token) tc::named_bar_arrive(tok_other, 512);  // hand the MUFU pipe to the other group
     tc::named_bar_sync(bar_id, 256);
     if (issuer_warp && tc::elect_one()) {
       tc::fence_after_sync();
