@@ -430,11 +430,16 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
   if (D == 16 && H == 16) {
     // Every trajectory of the batch has to be resident at once (batch-global error norm).  8 lanes per trajectory is
-    // the fastest mapping (shortest dependent chain) and holds 7104 trajectories on 148 SMs; beyond that 4 lanes per
-    // trajectory (twice the state per thread) hold 9472.  Larger batches: shard them (multi-GPU) or use norm='trajectory'.
-    const int rc = launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
+    // the fastest mapping (shortest dependent chain) and holds 7104 trajectories on 148 SMs; beyond that 4, 2 and finally 1
+    // lane per trajectory (more state per thread, the compiler spills part of it) hold 9472 / 18 944 / 37 888.  Larger
+    // batches: shard them (multi-GPU) or use norm='trajectory'.
+    int rc = launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
     if (rc != GODE_ERR_COOP) return rc;
-    return launch_dp5_fwd<16, 16, 4>(a, workspace, ws_bytes, st);
+    rc = launch_dp5_fwd<16, 16, 4>(a, workspace, ws_bytes, st);
+    if (rc != GODE_ERR_COOP) return rc;
+    rc = launch_dp5_fwd<16, 16, 2>(a, workspace, ws_bytes, st);   // state partly in local memory (L1/L2): slower, but resident
+    if (rc != GODE_ERR_COOP) return rc;
+    return launch_dp5_fwd<16, 16, 1>(a, workspace, ws_bytes, st);
   }
   return GODE_ERR_SHAPE;
 }
