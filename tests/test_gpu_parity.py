@@ -844,3 +844,35 @@ def test_odernn_fused_sampler_matches_oracle_and_unfused_path(monkeypatch):
     # deterministic
     codes2 = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg)
     assert torch.equal(codes, codes2)
+
+
+@pytest.mark.parametrize("D,H", [(64, 256), (16, 16)])
+@pytest.mark.parametrize("case", ["btd_decreasing", "two_points", "long_grid_device_dt"])
+def test_tensor_core_forward_and_adjoint_layouts_and_grids(D, H, case):
+    """The bf16 tcgen05 forward + adjoint pairs on the (B,T,D) layout, a decreasing non-uniform grid, a two-point grid and
+    a 300-point grid (step table on the device instead of the launch parameters)."""
+    _need_gpu()
+    f = make_field(D, H, seed=17)
+    B = 130
+    if case == "btd_decreasing":
+        t, layout = torch.tensor([1.0, 0.9, 0.55, 0.5, 0.2, 0.0]), "btd"
+    elif case == "two_points":
+        t, layout = torch.tensor([0.0, 0.25]), "tbd"
+    else:
+        t, layout = torch.linspace(0, 1, 300).float(), "tbd"
+    y0 = torch.randn(B, D)
+    g = torch.randn(len(t), B, D)
+
+    def run(fn, field, y, gg, **k):
+        y = y.clone().requires_grad_(True)
+        sol = fn(field, y, t, method="rk4", **k)
+        return sol.detach(), torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq.odeint_adjoint, f, y0, g)
+    out_sol, out_g = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV),
+                         options={"precision": "bf16", "bwd_precision": "bf16", "layout": layout})
+    assert out_sol.shape == ref_sol.shape
+    assert rel_err(out_sol, ref_sol) <= TC_TOL
+    errs = [rel_err(a, b) for a, b in zip(out_g, ref_g)]
+    # parameter gradients: bf16 operand rounding (2^-9) with little averaging on short grids / 130 trajectories
+    assert errs[0] <= TC_TOL and max(errs) <= 3 * TC_TOL, errs
