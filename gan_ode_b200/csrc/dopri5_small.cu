@@ -6,6 +6,7 @@
 //                               per-attempt device->host sync (`if error_ratio <= 1`) by an in-kernel barrier.
 //   dopri5_backprop_bwd_kernel  reverse-mode through the accepted steps + dense-output interpolation,
 //                               dt sequence read from the device-side step log (no host round trip).
+#include <stdlib.h>
 #include "dopri5_common.cuh"
 
 namespace gode {
@@ -358,9 +359,9 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kDp5Warps = 4;
 
-template <int D, int H, int L>
+template <int D, int H, int L, int WARPS = kDp5Warps>
 static int dp5_fwd_grid(int B) {
-  const int per_cta = kDp5Warps * Shape<D, H, L>::G;
+  const int per_cta = WARPS * Shape<D, H, L>::G;
   return (B + per_cta - 1) / per_cta;
 }
 
@@ -370,19 +371,19 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   return align256(grid_sync_bytes(dp5_fwd_grid<16, 16, 8>(B)));
 }
 
-template <int D, int H, int L>
+template <int D, int H, int L, int WARPS = kDp5Warps>
 static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
-  const int grid = dp5_fwd_grid<D, H, L>(a.B);
-  auto kern = dopri5_fwd_kernel<D, H, L, kDp5Warps>;
+  const int grid = dp5_fwd_grid<D, H, L, WARPS>(a.B);
+  auto kern = dopri5_fwd_kernel<D, H, L, WARPS>;
   static int limit_cache = 0;
-  const int cap = coop_limit(kern, kDp5Warps * 32, 0, limit_cache);
+  const int cap = coop_limit(kern, WARPS * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
   if (ws_bytes < grid_sync_bytes(grid)) return GODE_ERR_WORKSPACE;
   grid_sync_bind(a.gs, workspace);
   cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kDp5Warps * 32), args, 0, st);
+  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, 0, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }
@@ -429,15 +430,19 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
   a.o = *opts; a.B = B; a.T = T; a.layout = out_layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
   if (D == 16 && H == 16) {
-    // Every trajectory of the batch has to be resident at once (batch-global error norm).  8 lanes per trajectory is
-    // the fastest mapping (shortest dependent chain) and holds 7104 trajectories on 148 SMs; beyond that 4, 2 and finally 1
-    // lane per trajectory (more state per thread, the compiler spills part of it) hold 9472 / 18 944 / 37 888.  Larger
-    // batches: shard them (multi-GPU) or use norm='trajectory'.
-    int rc = launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st);
+    // Every trajectory of the batch has to be resident at once (batch-global error norm), and every attempted step ends in
+    // a grid-wide reduction whose cost grows with the number of CTAs.  Measured (scripts/dp5_lane_sweep.py, graph replay):
+    // 8 lanes per trajectory (shortest dependent chain, 16 trajectories per CTA) wins below ~2048 trajectories; from there
+    // 4 lanes (32 per CTA, half the CTAs) is faster — 24.6 vs 28.8 us at B = 4096, 29.7 vs 37.8 us at B = 7000 — and holds
+    // 9472 trajectories.  Beyond that 2 and finally 1 lane per trajectory (the compiler spills part of the stage vectors)
+    // hold 18 944 / 56 832.  Larger batches: shard them (multi-GPU) or use norm='trajectory'.
+    const char* force = getenv("GODE_DP5_LANES");  // developer switch: '8' / '4' force that mapping first
+    const bool first8 = force ? force[0] == '8' : B < 2048;
+    int rc = first8 ? launch_dp5_fwd<16, 16, 8>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
     if (rc != GODE_ERR_COOP) return rc;
     rc = launch_dp5_fwd<16, 16, 4>(a, workspace, ws_bytes, st);
     if (rc != GODE_ERR_COOP) return rc;
-    rc = launch_dp5_fwd<16, 16, 2>(a, workspace, ws_bytes, st);   // state partly in local memory (L1/L2): slower, but resident
+    rc = launch_dp5_fwd<16, 16, 2>(a, workspace, ws_bytes, st);
     if (rc != GODE_ERR_COOP) return rc;
     return launch_dp5_fwd<16, 16, 1>(a, workspace, ws_bytes, st);
   }

@@ -6,8 +6,9 @@
 //
 //     CTAs                              16     32     64    128    256
 //     cooperative_groups grid.sync    4116   4031   4713   4206   4337    (+ re-read of per-CTA partials)
-//     counter (red.release + poll 1)  3542   3516   3528   4179   4407    <- used for > 48 CTAs
-//     tagged-word all-gather          1745   1817   3635   7641  11634    <- used for <= 48 CTAs
+//     counter (red.release + poll 1)  3542   3516   3528   4179   4407    <- used for > 16 CTAs
+//     tagged-word all-gather          1745   1817   3635   7641  11634    <- used for <= 16 CTAs (in the real kernel 32
+//                                                                          polling CTAs were slower than the counter)
 //     16-CTA clusters + DSMEM         2637   3326   3333   3585   4275    (not worth the launch constraints)
 //
 //   * tagged-word all-gather: every CTA publishes ONE 64-bit word per value, {fp32 partial | epoch << 32}, with a
@@ -32,7 +33,7 @@
 namespace gode {
 
 constexpr int kGsMaxVals = 4;
-constexpr int kGsFlagMaxCtas = 48;
+constexpr int kGsFlagMaxCtas = 16;  // measured inside dopri5_fwd_kernel (scripts/dp5_lane_sweep.py): beyond 16 CTAs the counter wins
 
 struct GridSyncWs {
   unsigned int* counter;      // 256-byte slot
