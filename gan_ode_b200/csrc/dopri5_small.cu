@@ -388,10 +388,9 @@ static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
   return launch_status();
 }
 
-template <int D, int H, int L>
+template <int D, int H, int L, int WARPS = 4>
 static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   using S = Shape<D, H, L>;
-  constexpr int WARPS = 4;
   auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS>;
   const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P);
   cudaError_t e;
@@ -461,7 +460,7 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
   a.o.ckpt_capacity = ckpt_capacity; a.o.fsign = fsign; a.grad_y0 = grad_y0; a.grad_params = grad_params;
   a.B = B; a.T = T; a.layout = layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
-  if (D == 16 && H == 16) return launch_dp5_bwd<16, 16, 8>(a, workspace, ws_bytes, st);
+  if (D == 16 && H == 16) return launch_dp5_bwd<16, 16, 8>(a, workspace, ws_bytes, st);  // (8-warp CTAs measured: slower)
   return GODE_ERR_SHAPE;
 }
 
