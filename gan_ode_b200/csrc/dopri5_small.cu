@@ -12,6 +12,7 @@
 namespace gode {
 
 constexpr int kMaxT = 256;  // output times passed by value
+constexpr int kDp5StageT = 32;  // output grids up to this length have their upstream gradients staged in shared memory
 
 struct Dp5Args {
   const float *y0, *W1, *b1, *W2, *b2;
@@ -215,7 +216,14 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   float* s_lines = smem;
   float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;
   float* s_red = s_cw + ColWeights<D, H, L>::kFloats;
+  // upstream gradients of this warp's trajectories for ALL output times, staged once per trajectory group with every load
+  // in flight (T <= kDp5StageT): inside the replay loop they used to be T dependent global loads, each a full L2/HBM latency
+  float* s_gr = s_red + WARPS * S::P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  const bool staged = p.T <= kDp5StageT;
+  float* my_gr = s_gr + (size_t)warp * p.T * (S::G * D);
+  // the step log is read first so that its latency overlaps the weight loads below (all are cold global reads)
+  const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
@@ -224,12 +232,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
-  acc.zero();
   __syncthreads();
-  const int n_acc = min(p.log->n_accepted, p.o.ckpt_capacity);
+  const int n_acc = min(log_n_accepted, p.o.ckpt_capacity);
   // A forward that failed (dt underflow, non-finite state, step budget, checkpoint overflow) has no valid replay:
   // return NaN gradients instead of silently truncated ones (the host does not sync to look at the status).
-  const float poison = p.log->status != 0 ? __int_as_float(0x7fc00000) : 0.f;
+  const float poison = log_status != 0 ? __int_as_float(0x7fc00000) : 0.f;
   acc.fill(poison);
   const int stride = gridDim.x * WARPS * S::G;
   for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
@@ -240,13 +247,47 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
 #pragma unroll
     for (int c = 0; c < S::DL; ++c) { ybar[c] = poison; fbar[c] = 0.f; }
     int iout = p.T - 1;
+    if (staged) {
+      __syncwarp();
+      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store
+      for (int e0 = lane; e0 < p.T * (S::G * D / 4); e0 += 8 * 32) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = e0 + 32 * q;
+          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < p.T * (S::G * D / 4) && base + gg < p.B)
+            v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = e0 + 32 * q;
+          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+          if (e < p.T * (S::G * D / 4)) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
+        }
+      }
+      __syncwarp();
+    }
+    // checkpoint and step table of the step about to be replayed are fetched one step ahead
+    float y0n[S::DL];
+    double t0n = 0.0, dtn = 0.0;
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) y0n[c] = 0.f;
+    if (n_acc > 0) {
+      t0n = p.acc_t0[n_acc - 1]; dtn = p.acc_dt[n_acc - 1];
+      if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(n_acc - 1) * p.B + b) * D + l * S::DL, y0n);
+    }
     for (int s = n_acc - 1; s >= 0; --s) {
-      const double t0 = p.acc_t0[s], dtd = p.acc_dt[s], t1 = t0 + dtd;
+      const double t0 = t0n, dtd = dtn, t1 = t0 + dtd;
       const float dt32 = (float)dtd;
       float y0[S::DL], k[7][S::DL], h[7][S::HL], u[S::DL];
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) y0[c] = 0.f;
-      if (valid) load_frag<S::DL>(p.ckpt + ((size_t)s * p.B + b) * D + l * S::DL, y0);
+      for (int c = 0; c < S::DL; ++c) y0[c] = y0n[c];
+      if (s > 0) {
+        t0n = p.acc_t0[s - 1]; dtn = p.acc_dt[s - 1];
+        if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(s - 1) * p.B + b) * D + l * S::DL, y0n);
+      }
       // recompute the step exactly as the forward did
       field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], h[0]);
 #pragma unroll
@@ -269,7 +310,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
         float gout[S::DL];
 #pragma unroll
         for (int c = 0; c < S::DL; ++c) gout[c] = 0.f;
-        if (valid) load_frag<S::DL>(p.grad_traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, gout);
+        if (staged) load_frag<S::DL>(my_gr + (size_t)iout * (S::G * D) + g * D + l * S::DL, gout);
+        else if (valid) load_frag<S::DL>(p.grad_traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, gout);
         const float x = (float)((p.t[iout] - t0) * inv_span);
         const float p2 = x * x, p3 = p2 * x, p4 = p3 * x;
         const float cy0 = 1.f - 11.f * p2 + 18.f * p3 - 8.f * p4;
@@ -347,7 +389,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
 #pragma unroll
     for (int c = 0; c < S::DL; ++c) g0[c] = 0.f;
     if (valid) {
-      load_frag<S::DL>(p.grad_traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, g0);
+      if (staged) load_frag<S::DL>(my_gr + g * D + l * S::DL, g0);
+      else load_frag<S::DL>(p.grad_traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, g0);
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) g0[c] += ybar[c];
       store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
@@ -392,7 +435,8 @@ template <int D, int H, int L, int WARPS = 4>
 static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   using S = Shape<D, H, L>;
   auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS>;
-  const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P);
+  const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P +
+                                       (a.T <= kDp5StageT ? (size_t)WARPS * a.T * S::G * D : 0));
   cudaError_t e;
   if (smem > 48 * 1024) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
