@@ -102,15 +102,24 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
     float a[S::DL];
 #pragma unroll
     for (int i = 0; i < S::DL; ++i) a[i] = 0.f;
-    if (valid) load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, a);
+    // stored state and upstream gradient of an interval are fetched one interval ahead (they are cold global reads, and
+    // at small batch the kernel is a chain of dependent latencies)
+    float yn[S::DL], gn[S::DL];
+#pragma unroll
+    for (int i = 0; i < S::DL; ++i) { yn[i] = 0.f; gn[i] = 0.f; }
+    if (valid) {
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, a);
+      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, gn);
+    }
     for (int i = p.T - 1; i >= 1; --i) {
       const float dt = dtp[i - 1];
       float y[S::DL], gprev[S::DL];
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) { y[c] = 0.f; gprev[c] = 0.f; }
-      if (valid) {
-        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i, b, p.B, p.T, D) + l * S::DL, y);
-        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 1, b, p.B, p.T, D) + l * S::DL, gprev);
+      for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gprev[c] = gn[c]; }
+      if (valid && i > 1) {
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i - 1, b, p.B, p.T, D) + l * S::DL, yn);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 2, b, p.B, p.T, D) + l * S::DL, gn);
       }
       const float c18 = dt * 0.125f, c38 = 3.f * c18;
       const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
@@ -173,15 +182,22 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
     float yb[S::DL];  // cotangent of y_{s+1}
 #pragma unroll
     for (int c = 0; c < S::DL; ++c) yb[c] = 0.f;
-    if (valid) load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yb);
+    float yn[S::DL], gn[S::DL];  // next step's stored state / upstream gradient, fetched one step ahead
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) { yn[c] = 0.f; gn[c] = 0.f; }
+    if (valid) {
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yb);
+      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, yn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, gn);
+    }
     for (int s = p.T - 2; s >= 0; --s) {
       const float dt = dtp[s];
       float y[S::DL], gs[S::DL];
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) { y[c] = 0.f; gs[c] = 0.f; }
-      if (valid) {
-        load_frag<S::DL>(p.traj_in + traj_off(p.layout, s, b, p.B, p.T, D) + l * S::DL, y);
-        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, s, b, p.B, p.T, D) + l * S::DL, gs);
+      for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gs[c] = gn[c]; }
+      if (valid && s > 0) {
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, s - 1, b, p.B, p.T, D) + l * S::DL, yn);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, s - 1, b, p.B, p.T, D) + l * S::DL, gn);
       }
       // recompute (same expressions as the forward kernel)
       float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u2[S::DL], u3[S::DL], u4[S::DL];
