@@ -154,10 +154,19 @@ __global__ void __launch_bounds__(128, 3) tc_rk4_adj_small_kernel(const __grid_c
       }
     };
     load16(p.grad_traj + (valid ? off3(p.layout, p.T - 1, b, p.B, p.T) : 0), A);
+    float Yn[16], Gn[16];  // stored state of the next interval / upstream gradient of this one, fetched an interval ahead
+    load16(p.traj + (valid ? off3(p.layout, p.T - 1, b, p.B, p.T) : 0), Yn);
+    load16(p.grad_traj + (valid ? off3(p.layout, p.T - 2, b, p.B, p.T) : 0), Gn);
     for (int i = p.T - 1; i >= 1; --i) {
       const float dt = dtp[i - 1];
       const float cs[4] = {dt * 0.125f, dt * 0.375f, dt * 0.375f, dt * 0.125f};
-      load16(p.traj + (valid ? off3(p.layout, i, b, p.B, p.T) : 0), Y);
+      float gp[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { Y[e] = Yn[e]; gp[e] = Gn[e]; }
+      if (i > 1) {
+        load16(p.traj + (valid ? off3(p.layout, i - 1, b, p.B, p.T) : 0), Yn);
+        load16(p.grad_traj + (valid ? off3(p.layout, i - 2, b, p.B, p.T) : 0), Gn);
+      }
       {
         unsigned char* r = smem + OFF_R + cur * R_BYTES;
         pack16(r, A, cs[0]);
@@ -233,8 +242,6 @@ __global__ void __launch_bounds__(128, 3) tc_rk4_adj_small_kernel(const __grid_c
         {  // a part: ka = v'/c; next stage's (c a) -> the other input tile
           uint32_t zv[16];
           tc::tmem_ld16_nowait(my_t + T_V, zv);
-          float gp[16];
-          if (s == 3) load16(p.grad_traj + (valid ? off3(p.layout, i - 1, b, p.B, p.T) : 0), gp);
           tc::tmem_ld_wait();
           float an[16];
 #pragma unroll
