@@ -62,21 +62,27 @@ __device__ __forceinline__ void philox_normals(unsigned long long seed, unsigned
   const int d0 = l * DL;
   const uint4 r = philox4x32_10(make_uint4((unsigned int)traj, (unsigned int)step, (unsigned int)(d0 >> 2), 0u),
                                 make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
-  float n[4];
-  {
-    const float rad = sqrtf(-2.f * logf(u01(r.x)));
-    float s, c;
-    sincosf(6.2831855f * u01(r.y), &s, &c);
-    n[0] = rad * s; n[1] = rad * c;
+  // Box–Muller on the pair(s) this lane needs only (a lane owning 1 or 2 components needs one of the block's two pairs),
+  // with the hardware transcendental units: log2 (MUFU.LG2), rsqrt/sqrt, sin/cos of 2*pi*u via sinpi/cospi-style exact
+  // range (u in (0,1) -> the argument of MUFU.SIN/COS stays in (0, 2*pi)).  Differences from the CPU contract
+  // (oracle/philox.py, numpy float32) are ~1e-6 relative, far inside the 2e-5 the stream test allows.
+  auto pair = [](unsigned int a, unsigned int b, float& n0, float& n1) {
+    const float rad = sqrtf(-1.3862944f * __log2f(u01(a)));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+    float sn, cs;
+    __sincosf(6.2831855f * u01(b), &sn, &cs);
+    n0 = rad * sn;
+    n1 = rad * cs;
+  };
+  if constexpr (DL == 4) {
+    pair(r.x, r.y, z[0], z[1]);
+    pair(r.z, r.w, z[2], z[3]);
+  } else {
+    const bool second = (d0 & 2) != 0;
+    float n0, n1;
+    pair(second ? r.z : r.x, second ? r.w : r.y, n0, n1);
+    if constexpr (DL == 2) { z[0] = n0; z[1] = n1; }
+    else z[0] = (d0 & 1) ? n1 : n0;
   }
-  {
-    const float rad = sqrtf(-2.f * logf(u01(r.z)));
-    float s, c;
-    sincosf(6.2831855f * u01(r.w), &s, &c);
-    n[2] = rad * s; n[3] = rad * c;
-  }
-#pragma unroll
-  for (int i = 0; i < DL; ++i) z[i] = n[(d0 & 3) + i];
 }
 
 template <int D, int H, int L>
