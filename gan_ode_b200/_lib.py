@@ -11,6 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
 
+METHODS = {"rk4": 0, "euler": 1, "midpoint": 2}
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
@@ -60,6 +61,9 @@ _SIGS = {
     "gode_odernn_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_odernn_fwd": (_I, [_P] * 10 + [_I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts)] + [_P] * 6 + [C.c_size_t, _P]),
     "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 10 + [C.c_size_t, _P]),
+    "gode_fixed_fwd": (_I, [_I] + [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "gode_fixed_adjoint_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
+    "gode_fixed_backprop_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_allreduce_p2p": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "gode_sde_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_sde_em_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P]),

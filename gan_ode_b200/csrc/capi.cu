@@ -262,4 +262,41 @@ int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* p
                        rank, world, cap, epoch_ctr, (cudaStream_t)stream);
 }
 
+static bool bad_method(int m) { return m != GODE_METHOD_RK4 && m != GODE_METHOD_EULER && m != GODE_METHOD_MIDPOINT; }
+
+int gode_fixed_fwd(int method, const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                   const float* dt, int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj,
+                   gode_stream_t stream) {
+  if (bad_method(method) || bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !dt || !traj) return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_fwd(y0, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, out_layout, traj, (cudaStream_t)stream, method);
+}
+
+static int fixed_bwd(bool adjoint, int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                     const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                     int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (bad_method(method) || bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !dt || !grad_y0 || !grad_params ||
+      !workspace)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_bwd(adjoint, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                       workspace, ws_bytes, (cudaStream_t)stream, method);
+}
+
+int gode_fixed_adjoint_bwd(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                           const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                           int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                           gode_stream_t stream) {
+  return fixed_bwd(true, method, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                   workspace, ws_bytes, stream);
+}
+
+int gode_fixed_backprop_bwd(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                            int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                            gode_stream_t stream) {
+  return fixed_bwd(false, method, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                   workspace, ws_bytes, stream);
+}
+
 }  // extern "C"

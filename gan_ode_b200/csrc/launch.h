@@ -49,10 +49,12 @@ inline int coop_limit(K kern, int threads, size_t smem, int& cache) {
 
 // entry points of the per-family translation units
 int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
-                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st);
+                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st,
+                  int method = GODE_METHOD_RK4);
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
-                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
+                  int method = GODE_METHOD_RK4);
 
 size_t dopri5_small_workspace_bytes(int B, int D, int H);
 int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,

@@ -1,4 +1,4 @@
-// rk4_small.cu — fixed-grid RK4 (3/8 rule) for the small-field shapes, FP32.
+// rk4_small.cu — fixed-grid solvers for the small-field shapes, FP32: RK4 (3/8 rule, METHOD 0), Euler (1), midpoint (2).
 //   rk4_fwd_kernel          torchdiffeq FixedGridODESolver.integrate + rk4_alt_step_func        
 //   rk4_adjoint_bwd_kernel  torchdiffeq OdeintAdjointMethod.backward with method='rk4'          
 //   rk4_backprop_bwd_kernel autograd through the same forward (discretise-then-optimise)        
@@ -8,6 +8,7 @@
 
 namespace gode {
 
+constexpr int kRk4 = GODE_METHOD_RK4, kEuler = GODE_METHOD_EULER, kMidpoint = GODE_METHOD_MIDPOINT;
 constexpr float kOneThird = 0.33333334f;  // float(1/3): torchdiffeq multiplies fp32 tensors by the Python double 1/3
 
 struct Rk4Args {
@@ -28,7 +29,7 @@ __device__ __forceinline__ size_t traj_off(int layout, int s, int b, int B, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int D, int H, int L, int WARPS>
+template <int D, int H, int L, int WARPS, int METHOD>
 __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_constant__ Rk4Args p) {
   using S = Shape<D, H, L>;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
@@ -53,6 +54,22 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
       const float dt = dtp[s];
       float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u[S::DL], hk[S::HL];
       mlp_forward<D, H, L>(w, ln, l, y, k1, hk);
+      if constexpr (METHOD == kEuler) {          // fixed_grid.py::Euler: dy = dt * f(t0, y0)
+#pragma unroll
+        for (int i = 0; i < S::DL; ++i) y[i] = y[i] + dt * k1[i];
+        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+        continue;
+      }
+      if constexpr (METHOD == kMidpoint) {       // fixed_grid.py::Midpoint: y_mid = y0 + f(y0) * (dt/2); dy = dt * f(y_mid)
+        const float half_dt = 0.5f * dt;
+#pragma unroll
+        for (int i = 0; i < S::DL; ++i) u[i] = y[i] + k1[i] * half_dt;
+        mlp_forward<D, H, L>(w, ln, l, u, k2, hk);
+#pragma unroll
+        for (int i = 0; i < S::DL; ++i) y[i] = y[i] + dt * k2[i];
+        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < S::DL; ++i) u[i] = y[i] + dt * k1[i] * kOneThird;
       mlp_forward<D, H, L>(w, ln, l, u, k2, hk);
@@ -75,7 +92,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
 // value at the start of every interval and grad_traj[i-1] is added to a at its end, exactly as adjoint.py does.
 // theta_bar is linear in the stage contributions, so each lane keeps its rows of theta_bar in registers across ALL
 // intervals and ALL its trajectories and the grid reduces once at the end.
-template <int D, int H, int L, int WARPS>
+template <int D, int H, int L, int WARPS, int METHOD>
 __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __grid_constant__ Rk4Args p) {
   using S = Shape<D, H, L>;
   using BL = BwdLines<D, H, L>;
@@ -125,6 +142,25 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
       const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
       float f[S::DL], v[S::DL], hk[S::HL], uy[S::DL], ua[S::DL];
       float k1y[S::DL], k1a[S::DL], k2y[S::DL], k2a[S::DL], k3y[S::DL], k3a[S::DL];
+      if constexpr (METHOD == kEuler) {          // one Euler step of the augmented system from (y_i, a_i)
+        mlp_forward<D, H, L>(w, ln, l, y, f, hk);
+        mlp_vjp<D, H, L>(cw, ln, l, hk, a, sc * dt, v, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) a[c] = a[c] + dt * v[c] + gprev[c];
+        continue;
+      }
+      if constexpr (METHOD == kMidpoint) {       // X1 = X0 + dt F(X0 + dt/2 F(X0)): only the second stage feeds theta_bar
+        const float half_dt = 0.5f * dt;
+        mlp_forward<D, H, L>(w, ln, l, y, f, hk);
+        mlp_vjp<D, H, L>(cw, ln, l, hk, a, 0.f, v, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) { uy[c] = y[c] - f[c] * half_dt; ua[c] = a[c] + v[c] * half_dt; }
+        mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
+        mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * dt, v, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) a[c] = a[c] + dt * v[c] + gprev[c];
+        continue;
+      }
       // stage 1
       mlp_forward<D, H, L>(w, ln, l, y, f, hk);
       mlp_vjp<D, H, L>(cw, ln, l, hk, a, sc * c18, v, acc);
@@ -154,7 +190,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
 // ------------------------------------------------------------------------------------------------------------
 // Exact reverse-mode through the forward's arithmetic.  Per step the four stage inputs u_s and tanh vectors are
 // recomputed from the stored y_s (bit-identical to the forward), then the stages are walked 4..1.
-template <int D, int H, int L, int WARPS>
+template <int D, int H, int L, int WARPS, int METHOD>
 __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __grid_constant__ Rk4Args p) {
   using S = Shape<D, H, L>;
   using BL = BwdLines<D, H, L>;
@@ -203,6 +239,32 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
       float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u2[S::DL], u3[S::DL], u4[S::DL];
       float h1[S::HL], h2[S::HL], h3[S::HL], h4[S::HL];
       mlp_forward<D, H, L>(w, ln, l, y, k1, h1);
+      if constexpr (METHOD == kEuler) {          // y1 = y0 + dt f(y0)
+        float cot[S::DL], ub[S::DL];
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) cot[c] = dt * yb[c];
+        mlp_vjp<D, H, L>(cw, ln, l, h1, cot, sc, ub, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) yb[c] += ub[c] + gs[c];
+        continue;
+      }
+      if constexpr (METHOD == kMidpoint) {       // u = y0 + (dt/2) f(y0); y1 = y0 + dt f(u)
+        const float half_dt = 0.5f * dt;
+        float cot[S::DL], ub[S::DL];
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) u2[c] = y[c] + k1[c] * half_dt;
+        mlp_forward<D, H, L>(w, ln, l, u2, k2, h2);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) cot[c] = dt * yb[c];
+        mlp_vjp<D, H, L>(cw, ln, l, h2, cot, sc, ub, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) { yb[c] += ub[c]; cot[c] = half_dt * ub[c]; }
+        regather<D, H, L>(ln, l, y, h1);
+        mlp_vjp<D, H, L>(cw, ln, l, h1, cot, sc, ub, acc);
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) yb[c] += ub[c] + gs[c];
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) u2[c] = y[c] + dt * k1[c] * kOneThird;
       mlp_forward<D, H, L>(w, ln, l, u2, k2, h2);
@@ -254,7 +316,7 @@ static int fill_dt(Rk4Args& a, const float* dt, int dt_on_device, int T) {
   return GODE_OK;
 }
 
-template <int D, int H, int L>
+template <int D, int H, int L, int METHOD>
 static int launch_rk4_fwd(Rk4Args& a, cudaStream_t st) {
   constexpr int WARPS = 4;
   using S = Shape<D, H, L>;
@@ -262,15 +324,15 @@ static int launch_rk4_fwd(Rk4Args& a, cudaStream_t st) {
   int grid = (a.B + per_cta - 1) / per_cta;
   const int cap = sm_count() * 16;  // 16 CTAs of 128 threads fill an SM; beyond that, loop
   if (grid > cap) grid = cap;
-  rk4_fwd_kernel<D, H, L, WARPS><<<grid, WARPS * 32, 0, st>>>(a);
+  rk4_fwd_kernel<D, H, L, WARPS, METHOD><<<grid, WARPS * 32, 0, st>>>(a);
   return launch_status();
 }
 
-template <int D, int H, int L, bool ADJOINT>
+template <int D, int H, int L, bool ADJOINT, int METHOD>
 static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   constexpr int WARPS = 4;
   using S = Shape<D, H, L>;
-  auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS> : rk4_backprop_bwd_kernel<D, H, L, WARPS>;
+  auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS, METHOD> : rk4_backprop_bwd_kernel<D, H, L, WARPS, METHOD>;
   const size_t smem = bwd_smem_bytes<D, H, L, WARPS>();
   cudaError_t e;
   if (smem > 48 * 1024) {
@@ -297,24 +359,36 @@ static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStre
 }
 
 int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
-                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st) {
+                  int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st, int method) {
   Rk4Args a{};
   a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.B = B; a.T = T; a.layout = out_layout;
   if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
-  if (D == 16 && H == 16) return launch_rk4_fwd<16, 16, 8>(a, st);
+  if (D == 16 && H == 16) {
+    if (method == kEuler) return launch_rk4_fwd<16, 16, 8, kEuler>(a, st);
+    if (method == kMidpoint) return launch_rk4_fwd<16, 16, 8, kMidpoint>(a, st);
+    return launch_rk4_fwd<16, 16, 8, kRk4>(a, st);
+  }
   return GODE_ERR_SHAPE;
 }
 
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
-                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                  int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
+                  int method) {
   Rk4Args a{};
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj_in = traj; a.grad_traj = grad_traj; a.grad_y0 = grad_y0;
   a.grad_params = grad_params; a.B = B; a.T = T; a.layout = layout;
   if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
-  if (D == 16 && H == 16)
-    return adjoint ? launch_rk4_bwd<16, 16, 8, true>(a, workspace, ws_bytes, st)
-                   : launch_rk4_bwd<16, 16, 8, false>(a, workspace, ws_bytes, st);
+  if (D == 16 && H == 16) {
+    if (method == kEuler)
+      return adjoint ? launch_rk4_bwd<16, 16, 8, true, kEuler>(a, workspace, ws_bytes, st)
+                     : launch_rk4_bwd<16, 16, 8, false, kEuler>(a, workspace, ws_bytes, st);
+    if (method == kMidpoint)
+      return adjoint ? launch_rk4_bwd<16, 16, 8, true, kMidpoint>(a, workspace, ws_bytes, st)
+                     : launch_rk4_bwd<16, 16, 8, false, kMidpoint>(a, workspace, ws_bytes, st);
+    return adjoint ? launch_rk4_bwd<16, 16, 8, true, kRk4>(a, workspace, ws_bytes, st)
+                   : launch_rk4_bwd<16, 16, 8, false, kRk4>(a, workspace, ws_bytes, st);
+  }
   return GODE_ERR_SHAPE;
 }
 

@@ -188,8 +188,12 @@ class _Rk4(torch.autograd.Function):
         y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
         buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
         dt_ptr, dt_dev = _dt_arg(dt)
-        rc = L.gode_rk4_fwd(y0c.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
-                            dt_dev, B, D, H, T, meta["precision"], meta["layout"], buf.data_ptr(), _stream())
+        if meta.get("method", 0):   # euler / midpoint (FP32, D = H = 16): same kernels, other tableau
+            rc = L.gode_fixed_fwd(meta["method"], y0c.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(),
+                                  b2c.data_ptr(), dt_ptr, dt_dev, B, D, H, T, meta["layout"], buf.data_ptr(), _stream())
+        else:
+            rc = L.gode_rk4_fwd(y0c.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
+                                dt_dev, B, D, H, T, meta["precision"], meta["layout"], buf.data_ptr(), _stream())
         if rc:
             _lib.check(rc, "gode_rk4_fwd")
         ctx.meta = meta
@@ -225,9 +229,15 @@ class _Rk4(torch.autograd.Function):
                 bwd_prec = _lib.PREC["bf16"]
             elif (D, H) == (16, 16) and want == "bf16":            # opt-in for the reference shape (tc_rk4_adj_small.cu)
                 bwd_prec = _lib.PREC["bf16"]
-        rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
-                dt_dev, B, D, H, T, bwd_prec, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
-                ws.data_ptr(), ws_bytes, _stream())
+        if meta.get("method", 0):
+            fn = L.gode_fixed_adjoint_bwd if meta["adjoint"] else L.gode_fixed_backprop_bwd
+            rc = fn(meta["method"], buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(),
+                    b2c.data_ptr(), dt_ptr, dt_dev, B, D, H, T, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
+                    ws.data_ptr(), ws_bytes, _stream())
+        else:
+            rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
+                    dt_dev, B, D, H, T, bwd_prec, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
+                    ws.data_ptr(), ws_bytes, _stream())
         if rc:
             _lib.check(rc, "gode_rk4_bwd")
         needs = ctx.needs_input_grad
@@ -539,6 +549,13 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         dt = _rk4_dt(t, options, y0.device)
         return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
 
+    if method in ("euler", "midpoint"):   # torchdiffeq's other fixed-grid methods on the same field
+        if (D, H) != (16, 16) or prec != _lib.PREC["fp32"]:
+            raise NotImplementedError('method "{}" exists for the reference shape D=H=16 in fp32 only'.format(method))
+        dt = _rk4_dt(t, options, y0.device)
+        meta["method"] = _lib.METHODS[method]
+        return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
+
     if method == "dopri5":
         if not (D == 16 and H == 16):
             raise NotImplementedError("the fused dopri5 kernels exist for the reference shape D=H=16 only")
@@ -558,7 +575,7 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
             return _Dopri5Traj.apply(y0, meta, W1, b1, W2, b2)
         return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
 
-    raise NotImplementedError('method "{}" is not on the gan-ode hot path (rk4 and dopri5 are; SURVEY §8f-4)'.format(method))
+    raise NotImplementedError('method "{}" is not built (rk4, euler, midpoint and dopri5 are; SURVEY §8f-4)'.format(method))
 
 
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):

@@ -246,6 +246,26 @@ int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, 
 int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* pads_dev, int rank, int world, int cap,
                        uint32_t* epoch_ctr, gode_stream_t stream);
 
+/* ---- f4: the other fixed-grid methods of torchdiffeq for the same field (FP32, D = H = 16) ------------------------------- */
+/* method: GODE_METHOD_RK4 (torchdiffeq 'rk4' = 3/8 rule; identical to the gode_rk4_* entry points), GODE_METHOD_EULER
+ * (fixed_grid.py::Euler), GODE_METHOD_MIDPOINT (fixed_grid.py::Midpoint).  Same arguments, layouts and workspace as
+ * gode_rk4_fwd / gode_rk4_adjoint_bwd (continuous adjoint re-solved per interval with the SAME method, adjoint.py) /
+ * gode_rk4_backprop_bwd (reverse mode through the forward's arithmetic). */
+#define GODE_METHOD_RK4 0
+#define GODE_METHOD_EULER 1
+#define GODE_METHOD_MIDPOINT 2
+int gode_fixed_fwd(int method, const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                   const float* dt, int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj,
+                   gode_stream_t stream);
+int gode_fixed_adjoint_bwd(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                           const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                           int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                           gode_stream_t stream);
+int gode_fixed_backprop_bwd(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                            const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                            int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                            gode_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -173,7 +173,7 @@ def _check_inputs(func, y0, t, rtol, atol, method, options):
         options = options.copy()
     if method is None:
         method = "dopri5"
-    if method not in ("rk4", "dopri5", "euler"):
+    if method not in ("rk4", "dopri5", "euler", "midpoint"):
         raise ValueError('Invalid method "{}" (oracle restates rk4, dopri5, euler only)'.format(method))
 
     if is_tuple:
@@ -229,6 +229,13 @@ def _euler_step_func(func, t0, dt, t1, y0):
     return dt * func(t0, y0)
 
 
+def _midpoint_step_func(func, t0, dt, t1, y0):
+    """fixed_grid.py::Midpoint._step_func."""
+    half_dt = 0.5 * dt
+    y_mid = y0 + func(t0, y0) * half_dt
+    return dt * func(t0 + half_dt, y_mid)
+
+
 def _linear_interp(t0, t1, y0, y1, t):
     """solvers.py::FixedGridODESolver._linear_interp."""
     if t == t0:
@@ -270,6 +277,8 @@ def _fixed_grid_integrate(func, y0, t, method, options):
         dt = t1 - t0
         if method == "rk4":
             dy = rk4_alt_step_func(func, t0, dt, t1, y0)
+        elif method == "midpoint":
+            dy = _midpoint_step_func(func, t0, dt, t1, y0)
         else:
             dy = _euler_step_func(func, t0, dt, t1, y0)
         y1 = y0 + dy

@@ -876,3 +876,28 @@ def test_tensor_core_forward_and_adjoint_layouts_and_grids(D, H, case):
     errs = [rel_err(a, b) for a, b in zip(out_g, ref_g)]
     # parameter gradients: bf16 operand rounding (2^-9) with little averaging on short grids / 130 trajectories
     assert errs[0] <= TC_TOL and max(errs) <= 3 * TC_TOL, errs
+
+
+# ---- torchdiffeq's other fixed-grid methods on the same field -------------------------------------------------
+@pytest.mark.parametrize("method", ["euler", "midpoint"])
+@pytest.mark.parametrize("adjoint", [True, False])
+@pytest.mark.parametrize("B,tname", [(1, "lin16"), (37, "nonuniform_decreasing"), (4096, "lin16")])
+def test_euler_and_midpoint_match_oracle(method, adjoint, B, tname):
+    _need_gpu()
+    f = make_field(seed=B + len(method))
+    t = _t16() if tname == "lin16" else torch.tensor([1.0, 0.8, 0.75, 0.4, 0.1, 0.0])
+    y0 = torch.randn(B, 16)
+    g = torch.randn(len(t), B, 16)
+
+    def run(mod, field, y, gg, dtype=torch.float32):
+        y = y.clone().to(dtype).requires_grad_(True)
+        sol = (mod.odeint_adjoint if adjoint else mod.odeint)(field, y, t.to(dtype), method=method)
+        return sol.detach(), torch.autograd.grad((sol * gg.to(dtype)).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq, f, y0, g)
+    out_sol, out_g = run(gode, clone_to(f, DEV), y0.to(DEV), g.to(DEV))
+    assert torch.equal(out_sol[0].cpu(), y0)
+    assert rel_err(out_sol, ref_sol) <= TOL
+    r64 = run(tdq, clone_to(f, "cpu", torch.float64), y0, g, torch.float64)[1]
+    for a, b, c in zip(out_g, ref_g, r64):   # the fp32 oracle's own rounding is not charged to the kernel
+        assert rel_err(a, c) <= max(TOL, 2 * rel_err(b, c)), (rel_err(a, c), rel_err(b, c))

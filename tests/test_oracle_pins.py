@@ -70,6 +70,32 @@ def test_rk4_38_rule_is_order_4():
     assert all(3.7 < s < 4.4 for s in slopes), slopes
 
 
+@pytest.mark.parametrize("method,order", [("euler", 1), ("midpoint", 2)])
+def test_euler_and_midpoint_orders(method, order):
+    torch.manual_seed(3)
+    A = torch.randn(4, 4, dtype=torch.float64)
+    y0 = torch.randn(1, 4, dtype=torch.float64)
+    errs = []
+    for n in (32, 64, 128, 256):
+        t = torch.linspace(0, 1, n + 1, dtype=torch.float64)
+        sol = tdq.odeint(Lin(A), y0, t, method=method)
+        errs.append(float((sol[-1] - _expm_traj(A, y0, t[-1:])[0]).abs().max()))
+    slopes = [np.log2(errs[i] / errs[i + 1]) for i in range(3)]
+    assert all(order - 0.3 < s < order + 0.4 for s in slopes), slopes
+
+
+def test_midpoint_evaluates_the_field_at_the_half_step():
+    seen = []
+
+    class F(torch.nn.Module):
+        def forward(self, t, y):
+            seen.append(float(t))
+            return -y
+
+    tdq.odeint(F(), torch.ones(1, 1, dtype=torch.float64), torch.tensor([0.0, 0.4], dtype=torch.float64), method="midpoint")
+    assert np.allclose(seen, [0.0, 0.2])
+
+
 def test_rk4_is_the_38_rule_not_classic():
     """One step of y' = y: 3/8 rule and classic RK4 agree to O(h^5) but differ in rounding-free rational
     arithmetic for a nonlinear field; check the stage times 1/3, 2/3 are what the field sees."""
