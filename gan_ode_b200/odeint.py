@@ -57,6 +57,12 @@ config = _Config()
 def recognise_field(func):
     """Return (W1, b1, W2, b2) if `func` is the reference's ODEFunc structure, else raise NotImplementedError."""
     fn = getattr(func, "fn", None)
+    mods = getattr(fn, "_modules", None) if type(fn) is nn.Sequential else None   # fast path: no Sequential.__getitem__
+    if mods is not None and len(mods) == 3:
+        l0, act, l2 = mods.get("0"), mods.get("1"), mods.get("2")
+        if (type(l0) is nn.Linear and type(act) is nn.Tanh and type(l2) is nn.Linear and l0.bias is not None
+                and l2.bias is not None and l0.out_features == l2.in_features and l0.in_features == l2.out_features):
+            return l0.weight, l0.bias, l2.weight, l2.bias
     ok = (isinstance(fn, nn.Sequential) and len(fn) == 3 and isinstance(fn[0], nn.Linear)
           and isinstance(fn[1], nn.Tanh) and isinstance(fn[2], nn.Linear)
           and fn[0].bias is not None and fn[2].bias is not None
@@ -69,7 +75,28 @@ def recognise_field(func):
     return fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias
 
 
+_SIZE_CACHE = {}
+_SUPPORTED = set()   # (D, H, precision) triples the library has confirmed
+
+
+def _rk4_sizes(L, B, D, H, T):
+    """(param count, backward workspace bytes) — two ctypes calls, cached per shape."""
+    k = (B, D, H, T)
+    v = _SIZE_CACHE.get(k)
+    if v is None:
+        v = (L.gode_param_count(D, H), L.gode_rk4_bwd_workspace_bytes(B, D, H, T))
+        if len(_SIZE_CACHE) < 256:
+            _SIZE_CACHE[k] = v
+    return v
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> int:
+    """cudaStream_t of torch's current stream on the current device (the raw getter skips building a Stream object)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -113,6 +140,20 @@ def _host_steps(t: torch.Tensor):
     decreasing grid is integrated as increasing -t with the field negated (fsign = -1).  dt_j = t[j+1]-t[j] is
     taken in t's own dtype and then rounded to fp32, which is what multiplying it into fp32 state does upstream."""
     tn = t.detach().numpy()
+    key = (tn.dtype.str, tn.tobytes())
+    hit = _HOST_STEPS_CACHE.get(key)
+    if hit is not None:
+        return hit
+    out = _host_steps_uncached(tn)
+    if len(_HOST_STEPS_CACHE) < 64:
+        _HOST_STEPS_CACHE[key] = out
+    return out
+
+
+_HOST_STEPS_CACHE = {}   # immutable values (numpy arrays are never written after creation); bounded
+
+
+def _host_steps_uncached(tn):
     d = np.diff(tn)
     if (d > 0).all():
         fsign = 1.0
@@ -142,6 +183,8 @@ def _alloc_traj(T, B, D, layout, like):
 
 def _grad_in_layout(g: torch.Tensor, layout):
     """Upstream gradient as a contiguous buffer in the kernel's layout (zero-copy when it already is)."""
+    if layout == _lib.LAYOUT_TBD and g.dtype is torch.float32 and g.is_contiguous() and not (g.data_ptr() & 15):
+        return g   # the common case (autograd hands a fresh contiguous tensor): no ops at all
     g = g.detach()
     if g.dtype != torch.float32:
         g = g.float()
@@ -213,9 +256,11 @@ class _Rk4(torch.autograd.Function):
             B, _, D = buf.shape
         H = W1c.shape[0]
         g = _grad_in_layout(grad_traj, meta["layout"])
-        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=buf.device)
-        grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=buf.device)
-        ws_bytes = L.gode_rk4_bwd_workspace_bytes(B, D, H, T)
+        n_param, ws_bytes = _rk4_sizes(L, B, D, H, T)
+        # one allocation for both gradient outputs (grad_p first: it stays 16-byte aligned for the all-reduce kernels)
+        n_pad = (n_param + 3) & ~3
+        gbuf = torch.empty(n_pad + B * D, dtype=torch.float32, device=buf.device)
+        grad_p, grad_y0 = gbuf[:n_param], gbuf[n_pad:].view(B, D)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
@@ -535,9 +580,11 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
     if prec_name not in _lib.PREC:
         raise ValueError("options['precision'] must be one of {}".format(sorted(_lib.PREC)))
     prec = _lib.PREC[prec_name]
-    if not _lib.lib().gode_supported(D, H, prec) or not _lib.lib().gode_supported(D, H, _lib.PREC["fp32"]):
-        raise NotImplementedError("no sm_100a kernel compiled for ODEFunc(dim={}, dim_hidden={}) at precision {}; "
-                                  "there is no fallback".format(D, H, prec_name))
+    if (D, H, prec) not in _SUPPORTED:
+        if not _lib.lib().gode_supported(D, H, prec) or not _lib.lib().gode_supported(D, H, _lib.PREC["fp32"]):
+            raise NotImplementedError("no sm_100a kernel compiled for ODEFunc(dim={}, dim_hidden={}) at precision {}; "
+                                      "there is no fallback".format(D, H, prec_name))
+        _SUPPORTED.add((D, H, prec))
     layout = _layout_code(options.get("layout", config.layout))
     if t.is_cuda and t.device != y0.device:
         warnings.warn("t is not on the same device as y0. Coercing to y0.device.")
