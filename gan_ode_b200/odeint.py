@@ -297,14 +297,48 @@ def _dt_arg(dt):
     return dt.data_ptr(), 1
 
 
+def _substepped(apply_fixed, y0, t, step_size, layout_name):
+    """options={'step_size': h} of torchdiffeq's fixed-grid solvers (solvers.py::FixedGridODESolver): integrate on the grid
+    t0, t0+h, t0+2h, ... (last point clamped to t[-1]) and LINEARLY interpolate the requested times between grid states
+    (`_linear_interp`; a requested time that IS a grid point returns that state exactly).  The fine-grid solve is one
+    kernel launch; the interpolation is a handful of differentiable torch ops, so gradients reach the kernel's backward as
+    an upstream gradient on the fine grid.  Offered for `odeint` (backprop-through-solver), where this is exact; the
+    adjoint variant re-solves sub-stepped intervals without resetting the state at the inner grid points and is not built."""
+    tc = t.detach().cpu()
+    sign = 1.0 if bool(tc[-1] > tc[0]) else -1.0
+    ts = tc * sign                                   # torchdiffeq integrates a decreasing grid as increasing -t
+    h = torch.as_tensor(step_size, dtype=ts.dtype)
+    niters = int(torch.ceil((ts[-1] - ts[0]) / h + 1).item())
+    grid = torch.arange(0, niters, dtype=ts.dtype) * h + ts[0]
+    grid[-1] = ts[-1]
+    fine = apply_fixed(grid * sign)                  # (len(grid), B, D), always time-major here
+    outs = [fine[0]]
+    k = 0
+    for j in range(1, len(ts)):
+        while not bool(grid[k + 1] >= ts[j]):
+            k += 1
+        t0, t1, tj = grid[k], grid[k + 1], ts[j]
+        if bool(tj == t1):
+            outs.append(fine[k + 1])
+        elif bool(tj == t0):
+            outs.append(fine[k])
+        else:
+            slope = float((tj - t0) / (t1 - t0))
+            outs.append(fine[k] + slope * (fine[k + 1] - fine[k]))
+    sol = torch.stack(outs, 0)
+    if layout_name == "btd":
+        sol = sol.transpose(0, 1).contiguous().transpose(0, 1)
+    return sol
+
+
 def _rk4_dt(t: torch.Tensor, options, device):
     """Step table of torchdiffeq's fixed-grid driver: grid == t when no step_size is given, dt_j = t[j+1]-t[j] in t's
     dtype, multiplied into fp32 state (=> rounded to fp32).  Decreasing t gives negative dt, which is bit-identical
     to upstream's (-t, -f) rewrite for the 3/8 rule (negation is exact).  A host t gives a host table that rides in
     the kernel launch parameters (no copy, no sync); a device t stays on the device (monotonicity then unchecked
     unless options['check'])."""
-    if options.get("step_size") is not None or options.get("grid_constructor") is not None:
-        raise NotImplementedError("step_size / grid_constructor sub-stepping is not on the gan-ode hot path (SURVEY §8f-4)")
+    if options.get("grid_constructor") is not None:
+        raise NotImplementedError("grid_constructor is not supported (options['step_size'] is, for odeint)")
     if not t.is_cuda:
         _, dt, _ = _host_steps(t)
         if len(dt) > _lib.MAX_HOST_STEPS:
@@ -592,15 +626,24 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
     meta = dict(T=len(t), layout=layout, precision=prec, adjoint=adjoint, check=bool(options.get("check", False)),
                 bwd_precision=options.get("bwd_precision"))
 
-    if method == "rk4":
-        dt = _rk4_dt(t, options, y0.device)
-        return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
+    if method in ("rk4", "euler", "midpoint"):
+        if method != "rk4":   # torchdiffeq's other fixed-grid methods on the same field
+            if (D, H) != (16, 16) or prec != _lib.PREC["fp32"]:
+                raise NotImplementedError('method "{}" exists for the reference shape D=H=16 in fp32 only'.format(method))
+            meta["method"] = _lib.METHODS[method]
+        step_size = options.get("step_size")
+        if step_size is not None:
+            if adjoint:
+                raise NotImplementedError("options['step_size'] is supported for odeint (backprop-through-solver) only")
+            sub = dict(options)
+            sub.pop("step_size")
 
-    if method in ("euler", "midpoint"):   # torchdiffeq's other fixed-grid methods on the same field
-        if (D, H) != (16, 16) or prec != _lib.PREC["fp32"]:
-            raise NotImplementedError('method "{}" exists for the reference shape D=H=16 in fp32 only'.format(method))
+            def apply_fixed(grid):
+                m = dict(meta, T=len(grid), layout=_lib.LAYOUT_TBD)
+                return _Rk4.apply(y0, _rk4_dt(grid, sub, y0.device), m, W1, b1, W2, b2)
+
+            return _substepped(apply_fixed, y0, t, step_size, options.get("layout", config.layout))
         dt = _rk4_dt(t, options, y0.device)
-        meta["method"] = _lib.METHODS[method]
         return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
 
     if method == "dopri5":

@@ -901,3 +901,28 @@ def test_euler_and_midpoint_match_oracle(method, adjoint, B, tname):
     r64 = run(tdq, clone_to(f, "cpu", torch.float64), y0, g, torch.float64)[1]
     for a, b, c in zip(out_g, ref_g, r64):   # the fp32 oracle's own rounding is not charged to the kernel
         assert rel_err(a, c) <= max(TOL, 2 * rel_err(b, c)), (rel_err(a, c), rel_err(b, c))
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler", "midpoint"])
+@pytest.mark.parametrize("h,tname", [(1.0 / 45, "lin16"), (0.07, "lin16"), (0.11, "decreasing")])
+def test_step_size_substepping_matches_oracle(method, h, tname):
+    """options={'step_size': h}: fine-grid solve + linear interpolation of the requested times (solvers.py
+    FixedGridODESolver), for odeint (backprop-through-solver)."""
+    _need_gpu()
+    f = make_field(seed=int(h * 1000))
+    t = _t16() if tname == "lin16" else torch.tensor([1.0, 0.8, 0.75, 0.4, 0.1, 0.0])
+    y0 = torch.randn(33, 16)
+    g = torch.randn(len(t), 33, 16)
+
+    def run(mod, field, y, gg):
+        y = y.clone().requires_grad_(True)
+        sol = mod.odeint(field, y, t, method=method, options={"step_size": h})
+        return sol.detach(), torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq, f, y0, g)
+    out_sol, out_g = run(gode, clone_to(f, DEV), y0.to(DEV), g.to(DEV))
+    assert rel_err(out_sol, ref_sol) <= TOL
+    for a, b in zip(out_g, ref_g):
+        assert rel_err(a, b) <= 2e-5, rel_err(a, b)
+    with pytest.raises(NotImplementedError):
+        gode.odeint_adjoint(clone_to(f, DEV), y0.to(DEV), t, method=method, options={"step_size": h})
