@@ -441,8 +441,6 @@ int tc_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W
   const bool tf32 = precision == GODE_PREC_TF32;
   if (D == 16 && H == 16) {
     if (tf32) return launch_tc_rk4_fwd<16, 16, true>(a, st);
-    const char* old = getenv("GODE_TC_SMALL_OLD");  // developer A/B switch
-    if (old && old[0] == '1') return launch_tc_rk4_fwd<16, 16, false>(a, st);
     return launch_tc_rk4_fwd_bf16_lean(a, st);
   }
   return GODE_ERR_SHAPE;

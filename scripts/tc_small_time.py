@@ -1,4 +1,4 @@
-"""Developer timing probe: bf16 tcgen05 rk4 forward at D=H=16, B = 1M (GODE_TC_SMALL_OLD=1 selects the previous kernel)."""
+"""Developer timing probe: bf16 tcgen05 rk4 forward at D=H=16, B = 1M."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
