@@ -193,15 +193,29 @@ int gru_jump_bwd(const float* x, const float* h, const float* w_ih, const float*
 int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
                const GodeAdaptiveOpts* opts, float* codes, float* seg, unsigned char* logs, float* ckpt, double* acc,
-               void* workspace, size_t ws_bytes, cudaStream_t st) {
+               int32_t* n_acc, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
   const double t01[2] = {0.0, 1.0};
   const int cap = opts->log_capacity, kc = opts->ckpt_capacity;
   const size_t ls = odernn_log_stride(cap), bd = (size_t)B * D;
+  const bool per_traj = opts->norm_scope == GODE_NORM_TRAJ;
+  GodeAdaptiveOpts ot = *opts;
+  ot.log_capacity = 0;  // per-trajectory mode keeps no per-attempt logs here
   for (int f = 0; f < F; ++f) {
     const float* y0 = f == 0 ? h0 : codes + (size_t)(f - 1) * bd;
     unsigned char* lg = logs + (size_t)f * ls;
     float* tr = seg + (size_t)f * 2 * bd;
+    if (per_traj) {  // every trajectory its own (t, dt): no grid-wide reduction, ordinary launch (dopri5_traj_small.cu)
+      double* a0 = kc > 0 ? acc + (size_t)f * 2 * kc * B : nullptr;
+      int rc = dopri5_traj_small_fwd(y0, W1, b1, W2, b2, t01, B, D, H, 2, &ot, GODE_LAYOUT_TBD, tr,
+                                     reinterpret_cast<GodeStepLog*>(lg), n_acc + (size_t)f * B, n_acc + (size_t)F * B, nullptr,
+                                     nullptr, nullptr, kc > 0 ? ckpt + (size_t)f * kc * bd : nullptr, a0,
+                                     kc > 0 ? a0 + (size_t)kc * B : nullptr, st);
+      if (rc) return rc;
+      rc = gru_jump_fwd(eps + (size_t)f * bd, tr + bd, w_ih, w_hh, b_ih, b_hh, B, D, codes + (size_t)f * bd, st);
+      if (rc) return rc;
+      continue;
+    }
     int rc = dopri5_small_fwd(y0, W1, b1, W2, b2, t01, B, D, H, 2, opts, GODE_LAYOUT_TBD, tr,
                               reinterpret_cast<GodeStepLog*>(lg), reinterpret_cast<double*>(lg + 64),
                               reinterpret_cast<double*>(lg + 64 + 8 * (size_t)cap), reinterpret_cast<float*>(lg + 64 + 16 * (size_t)cap),
@@ -220,8 +234,8 @@ int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* 
 int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
                int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
-               const double* acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch,
-               void* workspace, size_t ws_bytes, cudaStream_t st) {
+               const double* acc, const int32_t* n_acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru,
+               float* scratch, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
   const double t01[2] = {0.0, 1.0};
   const int P1 = H * D + H + D * H + D, kc = ckpt_capacity;
@@ -241,6 +255,15 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
                           grad_gru, f != F - 1, gru_ws, ws_bytes - dp_ws, st);
     if (rc) return rc;
     const unsigned char* lg = logs + (size_t)f * log_stride;
+    if (n_acc) {  // per-trajectory step control: replay every trajectory's own accepted steps
+      const double* a0 = acc + (size_t)f * 2 * kc * B;
+      rc = dopri5_traj_small_bwd(gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD,
+                                 reinterpret_cast<const GodeStepLog*>(lg), n_acc + (size_t)f * B, ckpt + (size_t)f * kc * bd, a0,
+                                 a0 + (size_t)kc * B, kc, 1.0f, f == 0 ? grad_h0 : carry, slots + (size_t)f * P1, workspace,
+                                 dp_ws, st);
+      if (rc) return rc;
+      continue;
+    }
     rc = dopri5_small_backprop_bwd(gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD,
                                    reinterpret_cast<const GodeStepLog*>(lg), ckpt + (size_t)f * kc * bd,
                                    acc + (size_t)f * 2 * kc, acc + (size_t)f * 2 * kc + kc, kc, 1.0f,

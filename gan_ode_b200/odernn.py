@@ -5,7 +5,9 @@ through `install_shims()` — 16 fused dopri5 launches plus `nn.GRUCell` in PyTo
 for the same computation: `odernn_codes(ode_fn, gru, h0, eps)` enqueues all F (solve, jump) pairs from C
 (`gode_odernn_fwd`), the GRU jump is a CUDA kernel of this library, and the backward (`gode_odernn_bwd`) walks the frames
 in reverse on the device.  Step control, tolerances and results are those of F separate `odeint` calls with torchdiffeq's
-defaults; gradients are the discrete adjoint of the recorded solves (see odeint._solve).
+defaults; gradients are the discrete adjoint of the recorded solves (see odeint._solve).  `options={'norm': 'trajectory'}`
+(opt-in, not what torchdiffeq does for a batch) gives every trajectory its own step control: no grid-wide reduction per
+attempted step, ordinary launches, any batch size.
 """
 from __future__ import annotations
 
@@ -98,22 +100,25 @@ class _OdeRnn(torch.autograd.Function):
         codes = torch.empty((F, B, D), dtype=torch.float32, device=dev)
         seg = torch.empty((F, 2, B, D), dtype=torch.float32, device=dev)
         logs = torch.empty(F * stride, dtype=torch.uint8, device=dev)
+        per_traj = o.norm_scope == _lib.NORM_TRAJ
         ckpt = torch.empty((F, max(kc, 1), B, D), dtype=torch.float32, device=dev) if keep else None
-        acc = torch.empty((F, 2, max(kc, 1)), dtype=torch.float64, device=dev) if keep else None
+        acc = (torch.empty((F, 2, max(kc, 1)) + ((B,) if per_traj else ()), dtype=torch.float64, device=dev)) if keep else None
+        n_acc = torch.empty((F + 1, B), dtype=torch.int32, device=dev) if per_traj else None
         wsb = L.gode_odernn_workspace_bytes(B, D, H)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         _lib.check(L.gode_odernn_fwd(*[v.data_ptr() for v in ts], B, D, H, F, C.byref(opts), codes.data_ptr(),
-                                     seg.data_ptr(), logs.data_ptr(), _ptr(ckpt), _ptr(acc), ws.data_ptr(), wsb, _stream()),
+                                     seg.data_ptr(), logs.data_ptr(), _ptr(ckpt), _ptr(acc), _ptr(n_acc), ws.data_ptr(), wsb,
+                                     _stream()),
                    "gode_odernn_fwd")
         _LAST[0] = OdeRnnLog(logs, stride, F)
         ctx.meta, ctx.kc = meta, kc
-        ctx.save_for_backward(seg, logs, ckpt, acc, *ts[1:])
+        ctx.save_for_backward(seg, logs, ckpt, acc, n_acc, *ts[1:])
         return codes
 
     @staticmethod
     def backward(ctx, grad_codes):
         L = _lib.lib()
-        seg, logs, ckpt, acc, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
+        seg, logs, ckpt, acc, n_acc, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
         if ckpt is None:
             raise _lib.GodeError("ODE-RNN forward ran without checkpoints (inputs did not require grad)")
         F, _, B, D = seg.shape
@@ -132,7 +137,7 @@ class _OdeRnn(torch.autograd.Function):
         _lib.check(L.gode_odernn_bwd(g.data_ptr(), eps.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                      w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), B, D, H, F,
                                      o.log_capacity, ctx.kc, seg.data_ptr(), logs.data_ptr(), ckpt.data_ptr(), acc.data_ptr(),
-                                     gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
+                                     _ptr(n_acc), gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
                                      ws.data_ptr(), wsb, _stream()), "gode_odernn_bwd")
         from .odeint import _maybe_allreduce
         _maybe_allreduce(gode_)
@@ -158,8 +163,6 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
         raise NotImplementedError("the fused ODE-RNN kernels exist for the reference shape D=H=16, GRUCell(16,16)")
     options = {} if options is None else dict(options)
     o = _adaptive_opts(rtol, atol, options, 1.0)
-    if o.norm_scope != _lib.NORM_BATCH:
-        raise NotImplementedError("the fused ODE-RNN uses torchdiffeq's batch-global step control")
     keep = torch.is_grad_enabled() and any(t.requires_grad for t in (h0, eps, W1, b1, W2, b2) + tuple(gp))
     meta = dict(opts=o, keep=keep)
     return _OdeRnn.apply(h0, eps, meta, W1, b1, W2, b2, *gp)

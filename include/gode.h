@@ -219,21 +219,25 @@ int gode_gru_jump_bwd(const float* x, const float* h, const float* w_ih, const f
  * (the reference's torch.cat(...).view(-1, D), models/mocogan_ode_rnn.py:51-52, is its (B,F,D) transpose).
  * Saved for the backward (all caller-allocated, device): seg (F,2,B,D) = each solve's [input copy, h']; logs = F slots of
  * gode_odernn_log_stride(opts->log_capacity) bytes ([GodeStepLog | attempt arrays], as gode_dopri5_fwd lays them out);
- * ckpt (F, ckpt_capacity, B, D) and acc (F, 2, ckpt_capacity) doubles, or NULL with opts->ckpt_capacity = 0 (no backward). */
+ * ckpt (F, ckpt_capacity, B, D) and acc (F, 2, ckpt_capacity) doubles, or NULL with opts->ckpt_capacity = 0 (no backward).
+ * opts->norm_scope = GODE_NORM_TRAJ (opt-in): every trajectory controls its own step (gode_dopri5_traj_fwd); then n_acc is
+ * an (F + 1, B) int32 buffer (accepted steps per frame and trajectory + one scratch row) and acc is (F, 2, ckpt_capacity, B);
+ * with GODE_NORM_BATCH n_acc may be NULL.  The same n_acc / acc go to gode_odernn_bwd (n_acc = NULL selects batch mode). */
 size_t gode_odernn_log_stride(int log_capacity);
 size_t gode_odernn_workspace_bytes(int B, int D, int H);
 int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                     const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H,
                     int F, const GodeAdaptiveOpts* opts, float* codes, float* seg, void* logs, float* ckpt, double* acc,
-                    void* workspace, size_t ws_bytes, gode_stream_t stream);
+                    int32_t* n_acc, void* workspace, size_t ws_bytes, gode_stream_t stream);
 /* Reverse-mode through the F (solve, jump) pairs: GRU VJP, then the discrete adjoint of that frame's recorded solve.
  * grad_eps may be NULL.  grad_ode ([W1|b1|W2|b2]) and grad_gru are OVERWRITTEN (per-frame slots summed in frame order).
  * scratch: (3*B*D + F*gode_param_count(D,H)) floats. */
 int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
                     int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
-                    const float* ckpt, const double* acc, float* grad_h0, float* grad_eps, float* grad_ode,
-                    float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, gode_stream_t stream);
+                    const float* ckpt, const double* acc, const int32_t* n_acc, float* grad_h0, float* grad_eps,
+                    float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes,
+                    gode_stream_t stream);
 
 /* ---- e: data-parallel exchange ------------------------------------------------------------------------------------ */
 /* One-shot all-reduce (sum, in place) of `n` floats over peer memory (NVLink / NVSwitch), the fused alternative to

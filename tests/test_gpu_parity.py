@@ -926,3 +926,65 @@ def test_step_size_substepping_matches_oracle(method, h, tname):
         assert rel_err(a, b) <= 2e-5, rel_err(a, b)
     with pytest.raises(NotImplementedError):
         gode.odeint_adjoint(clone_to(f, DEV), y0.to(DEV), t, method=method, options={"step_size": h})
+
+
+def test_odernn_fused_sampler_per_trajectory_step_control(monkeypatch):
+    """options={'norm': 'trajectory'} on the fused sampler: every trajectory's frames are solved under its own controller.
+    Oracle = the reference loop on the CPU restatement run with B = 1 per trajectory (there batch-global == per-trajectory);
+    and the same computation unfused (per-trajectory odeint + gru_jump per frame) on the GPU."""
+    _need_gpu()
+    import sys
+    import types
+    from tests.caller_model import LatentMotionODERNN
+
+    torch.manual_seed(11)
+    F, B = 3, 6
+    cpu_model = LatentMotionODERNN(16, F)
+    gpu_model = LatentMotionODERNN(16, F)
+    gpu_model.load_state_dict(cpu_model.state_dict())
+    gpu_model.to(DEV)
+    h0 = torch.randn(B, 16) * torch.linspace(0.3, 2.5, B).view(-1, 1)
+    eps, w = torch.randn(F, B, 16), torch.randn(B, F, 16)
+
+    shim = types.ModuleType("torchdiffeq")
+    shim.odeint, shim.odeint_adjoint = tdq.odeint, tdq.odeint_adjoint
+    monkeypatch.setitem(sys.modules, "torchdiffeq", shim)
+    ref = torch.empty(B, F, 16)
+    for b in range(B):
+        r = cpu_model.sample_z_m(1, h0=h0[b:b + 1], eps=eps[:, b:b + 1])
+        ref[b] = r.detach()
+        (r * w[b]).sum().backward()           # parameter gradients accumulate over the trajectories
+    monkeypatch.delitem(sys.modules, "torchdiffeq")
+
+    opt = {"norm": "trajectory"}
+    h0g, epsg = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+    codes = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg, options=opt)
+    out = codes.transpose(0, 1)
+    (out * w.to(DEV)).sum().backward()
+    assert rel_err(out, ref) <= 2e-5
+    for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        assert rel_err(p.grad, q.grad) <= 1e-3, (n, rel_err(p.grad, q.grad))
+    fused = {n: p.grad.clone() for n, p in gpu_model.named_parameters()}
+    assert all(l["status"] == 0 for l in gode.odernn.last_log().frames())
+
+    gpu_model.zero_grad()
+    h0u, epsu = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+    h, hs = h0u, []
+    t01 = torch.tensor([0.0, 1.0])
+    for fr in range(F):
+        h = gode.odeint(gpu_model.ode_fn, h, t01, method="dopri5", options=opt)[-1]
+        h = gode.gru_jump(epsu[fr], h, gpu_model.recurrent)
+        hs.append(h)
+    out_u = torch.stack(hs, 1)
+    (out_u * w.to(DEV)).sum().backward()
+    assert rel_err(out, out_u) <= 1e-6
+    assert rel_err(h0g.grad, h0u.grad) <= 2e-5 and rel_err(epsg.grad, epsu.grad) <= 2e-5
+    for n, p in gpu_model.named_parameters():
+        assert rel_err(fused[n], p.grad) <= 5e-5, (n, rel_err(fused[n], p.grad))
+
+    # a batch too large for the cooperative batch-global kernel runs in this mode
+    Bb = 20000
+    hb, eb = torch.randn(Bb, 16, device=DEV, requires_grad=True), torch.randn(2, Bb, 16, device=DEV)
+    cb = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, hb, eb, rtol=1e-5, atol=1e-5, options=opt)
+    cb.sum().backward()
+    assert torch.isfinite(cb).all() and torch.isfinite(hb.grad).all()
