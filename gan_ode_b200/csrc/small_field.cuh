@@ -221,8 +221,8 @@ struct GradAcc {
 
 template <int N>
 __device__ __forceinline__ void axpy_line(float (&acc)[N], float s, const float* __restrict__ line) {
-#pragma unroll
   const float2 ss = make_float2(s, s);
+#pragma unroll
   for (int i = 0; i < N; i += 4) {  // packed FMAs: same arithmetic per element as the scalar form, half the issue slots
     const float4 v = *reinterpret_cast<const float4*>(line + i);
     const float2 lo = __ffma2_rn(ss, make_float2(v.x, v.y), make_float2(acc[i], acc[i + 1]));

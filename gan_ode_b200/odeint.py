@@ -48,6 +48,8 @@ class _Config:
     # parameter-gradient buffer the backward kernel writes is all-reduced (sum) in place on the same stream.
     # None: off.  True: the default process group.  A ProcessGroup: that group.
     grad_allreduce = None
+    # odeint_adjoint + dopri5: 'continuous' = torchdiffeq's adjoint re-solve; 'discrete' = gradient of the recorded steps
+    dopri5_adjoint = "continuous"
 
 
 config = _Config()
@@ -478,6 +480,86 @@ class _Dopri5(torch.autograd.Function):
         return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
 
 
+_LAST_ADJ_LOG = [None]
+
+
+def last_adjoint_log() -> Optional[StepLog]:
+    """Step log of the most recent continuous dopri5 adjoint solve (attempts of all intervals back to back; `t0` is not
+    recorded).  Reading synchronises."""
+    return _LAST_ADJ_LOG[0]
+
+
+class _Dopri5Adjoint(torch.autograd.Function):
+    """odeint_adjoint with the adaptive solver as torchdiffeq computes it: forward gode_dopri5_fwd (nothing kept but the
+    outputs), backward gode_dopri5_adjoint_bwd — per output interval a fresh dopri5 solve of (y, a, theta_bar) backwards in
+    time under the default adjoint norm (adjoint.py)."""
+
+    @staticmethod
+    def forward(ctx, y0, meta, W1, b1, W2, b2):
+        L = _lib.lib()
+        B, D = y0.shape
+        H = W1.shape[0]
+        T = meta["T"]
+        dev = y0.device
+        y0c, W1c, b1c, W2c, b2c = (_f32c(x) for x in (y0, W1, b1, W2, b2))
+        buf, view = _alloc_traj(T, B, D, meta["layout"], y0)
+        o = meta["opts"]
+        cap = o.log_capacity
+        raw = torch.empty(_log_layout(cap), dtype=torch.uint8, device=dev)
+        base = raw.data_ptr()
+        opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
+        opts.ckpt_capacity = 0
+        ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        tarr = meta["t64"]
+        _lib.check(L.gode_dopri5_fwd(
+            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
+            meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
+            None, None, None, _ptr(ws), ws_bytes, _stream()), "gode_dopri5_fwd")
+        log = StepLog(raw, cap)
+        _LAST_LOG[0] = log
+        if meta["check"]:
+            raise_for_status(log.status)
+        ctx.meta, ctx.tarr = meta, tarr
+        ctx.save_for_backward(buf, W1c, b1c, W2c, b2c)
+        return view
+
+    @staticmethod
+    def backward(ctx, grad_traj):
+        L = _lib.lib()
+        buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
+        meta = ctx.meta
+        T = meta["T"]
+        B, D = (buf.shape[1], buf.shape[2]) if meta["layout"] == _lib.LAYOUT_TBD else (buf.shape[0], buf.shape[2])
+        H = W1c.shape[0]
+        dev = buf.device
+        g = _grad_in_layout(grad_traj, meta["layout"])
+        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=dev)
+        grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=dev)
+        ao = meta["adj_opts"]
+        cap = ao.log_capacity
+        raw = torch.zeros(_log_layout(cap), dtype=torch.uint8, device=dev)
+        base = raw.data_ptr()
+        ws_bytes = L.gode_dopri5_adjoint_workspace_bytes(B, D, H)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = L.gode_dopri5_adjoint_bwd(
+            _ptr(buf), _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
+            meta["layout"], C.byref(ao), _ptr(grad_y0), _ptr(grad_p), base, base + 64 + 8 * cap, base + 64 + 16 * cap,
+            base + 64 + 20 * cap, _ptr(ws), ws_bytes, _stream())
+        if rc == _lib.ERR_COOP:
+            raise GodeError("the continuous dopri5 adjoint keeps the whole batch co-resident (at most 9472 trajectories per "
+                            "GPU); shard the batch, or pass options={'adjoint': 'discrete'} for the gradient of the recorded "
+                            "steps (gode_dopri5_backprop_bwd)")
+        _lib.check(rc, "gode_dopri5_adjoint_bwd")
+        log = StepLog(raw, cap)
+        _LAST_ADJ_LOG[0] = log
+        if meta["check"]:
+            raise_for_status(log.status)
+        needs = ctx.needs_input_grad
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6])
+        return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
+
+
 class TrajStepLog:
     """Host view of a per-trajectory dopri5 solve: `n_accepted`, `n_attempts` are (B,) arrays; `dt`, `error_ratio`,
     `accepted` are (n_max, B) arrays of per-attempt records (rows beyond a trajectory's own n_attempts are undefined).
@@ -601,7 +683,7 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
 
 
 # ------------------------------------------------------------------------------------------------------------
-def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
+def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
     W1, b1, W2, b2 = recognise_field(func)
     _check_common(y0, t)
     options = {} if options is None else dict(options)
@@ -651,10 +733,10 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
             raise NotImplementedError("the fused dopri5 kernels exist for the reference shape D=H=16 only")
         if prec != _lib.PREC["fp32"]:
             raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
-        # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): the gradient is computed by
-        # reverse-mode through the recorded accepted steps (the DISCRETE adjoint of the forward solve) instead of
-        # torchdiffeq's continuous adjoint re-solve; the two agree to O(tolerance).  The continuous dopri5 adjoint
-        # kernel is listed in DESIGN.md §8.
+        # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): by default torchdiffeq's continuous
+        # adjoint (gode_dopri5_adjoint_bwd).  options={'adjoint': 'discrete'} (or config.dopri5_adjoint) instead
+        # differentiates the recorded accepted steps (gode_dopri5_backprop_bwd): one replay, no second adaptive solve, any
+        # batch the forward holds; the two gradients agree to O(tolerance).
         # torchdiffeq: t -> float64 for adaptive solvers; the grid rides in the launch parameters (syncs iff t is on GPU)
         t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
@@ -663,6 +745,19 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool):
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
         if meta["opts"].norm_scope == _lib.NORM_TRAJ:
             return _Dopri5Traj.apply(y0, meta, W1, b1, W2, b2)
+        mode = options.get("adjoint", config.dopri5_adjoint)
+        if mode not in ("continuous", "discrete"):
+            raise ValueError("options['adjoint'] must be 'continuous' or 'discrete'")
+        if adjoint and mode == "continuous" and meta["keep_ckpt"]:
+            a_rtol, a_atol, a_options = adj if adj is not None else (None, None, None)
+            if a_options is None:   # adjoint.py: the forward options without its norm
+                a_options = {k: v for k, v in options.items() if k in ("first_step", "safety", "ifactor", "dfactor",
+                                                                      "min_step", "max_step", "max_num_steps", "log_capacity")}
+            elif "norm" in a_options:
+                raise NotImplementedError("a custom adjoint norm is not supported: the kernel uses torchdiffeq's default")
+            meta["adj_opts"] = _adaptive_opts(rtol if a_rtol is None else a_rtol, atol if a_atol is None else a_atol,
+                                              dict(a_options), fsign)
+            return _Dopri5Adjoint.apply(y0, meta, W1, b1, W2, b2)
         return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
 
     raise NotImplementedError('method "{}" is not built (rk4, euler, midpoint and dopri5 are; SURVEY §8f-4)'.format(method))
@@ -681,7 +776,8 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
                    adjoint_params=None):
     """torchdiffeq.odeint_adjoint for the reference's ODEFunc.  method='rk4': the backward pass is torchdiffeq's
     continuous adjoint re-solved per output interval with the same method (adjoint.py), fused into one kernel.
-    method='dopri5' (default): forward as odeint; backward = discrete adjoint through the recorded steps (see _solve)."""
+    method='dopri5' (default): the same continuous adjoint with the adaptive solver (adjoint_rtol / adjoint_atol /
+    adjoint_options as upstream), or options={'adjoint': 'discrete'} for the gradient of the recorded steps (see _solve)."""
     if event_fn is not None:
         raise NotImplementedError("event handling is not on the gan-ode hot path")
     if adjoint_params is None and not isinstance(func, nn.Module):
@@ -690,14 +786,14 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
                          "then it is allowable to set `adjoint_params=()`.")
     if adjoint_method is not None and adjoint_method != (method or "dopri5"):
         raise NotImplementedError("adjoint_method must equal method on the fused path")
-    for name, val, fwd in (("adjoint_rtol", adjoint_rtol, rtol), ("adjoint_atol", adjoint_atol, atol)):
-        if val is not None and val != fwd:
-            raise NotImplementedError("{} different from the forward tolerance is not supported".format(name))
-    if adjoint_options:
-        raise NotImplementedError("adjoint_options are not supported on the fused path")
+    is_dopri5 = (method or "dopri5") == "dopri5"
+    if not is_dopri5:   # fixed grid: the adjoint re-solve uses the forward grid, tolerances are not used
+        if adjoint_options:
+            raise NotImplementedError("adjoint_options are not supported with a fixed-grid method on the fused path")
     if adjoint_params is not None:
         mine = [p for p in recognise_field(func)]
         given = [p for p in adjoint_params]
         if len(given) != len(mine) or any(a is not b for a, b in zip(given, mine)):
             raise NotImplementedError("adjoint_params must be func's own parameters (or None)")
-    return _solve(func, y0, t, rtol, atol, method, options, adjoint=True)
+    return _solve(func, y0, t, rtol, atol, method, options, adjoint=True,
+                  adj=(adjoint_rtol, adjoint_atol, adjoint_options) if is_dopri5 else None)

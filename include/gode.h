@@ -163,6 +163,25 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                              const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
                              void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- a4 with the adaptive solver: torchdiffeq's continuous adjoint, method = adjoint_method = 'dopri5' ------------- */
+/* Replaces OdeintAdjointMethod.backward for the call `odeint(self.ode_fn, h, tensor([0,1]))` of the ODE-RNN sampler
+ * (models/mocogan_ode_rnn.py:47-48; `odeint` there is odeint_adjoint, :4).  Per output interval, from the last to the first:
+ * a fresh dopri5 solve of the augmented state (y, a, theta_bar) against the forward direction — initial-step heuristic and
+ * error ratios under torchdiffeq's default adjoint norm max(rms(y), rms(a), max over the four parameter tensors of
+ * rms(theta_bar_k)); dense-output value at the interval's end; then y <- stored forward value, a += grad_traj[i-1].
+ * traj / grad_traj: (T,B,D) or (B,T,D) per `layout`; t_host: the forward grid as passed to gode_dopri5_fwd (increasing,
+ * opts->fsign = -1 if the caller's t was decreasing); opts: ADJOINT tolerances and controller options (rtol, atol,
+ * first_step, safety, ifactor, dfactor, min/max_step, max_num_steps, log_capacity for the optional att_* arrays, which
+ * hold the attempts of all intervals back to back; NULL = no log).  log (optional): status / attempts / accepted / nfe
+ * summed over the intervals, dt0 of the last one.  One cooperative launch: the batch must be co-resident (<= 9472
+ * trajectories; GODE_ERR_COOP beyond).  workspace: gode_dopri5_adjoint_workspace_bytes(B,D,H) bytes.  Deterministic. */
+size_t gode_dopri5_adjoint_workspace_bytes(int B, int D, int H);
+int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                            const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                            const GodeAdaptiveOpts* opts, float* grad_y0, float* grad_params, GodeStepLog* log,
+                            double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
+                            gode_stream_t stream);
+
 /* ---- a5 (opt-in): dopri5 with PER-TRAJECTORY step control (GODE_NORM_TRAJ) ----------------------------------- */
 /* Every trajectory has its own (t, dt), RMS error norm over its own D components and accept/reject sequence — what
  * torchdiffeq computes when called with B = 1 per trajectory.  No grid-wide reduction, ordinary launch, any B.
