@@ -144,9 +144,9 @@ size_t gode_dopri5_adjoint_workspace_bytes(int B, int D, int H) { return dopri5_
 
 int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
-                            const GodeAdaptiveOpts* opts, float* grad_y0, float* grad_params, GodeStepLog* log,
-                            double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
-                            gode_stream_t stream) {
+                            const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
+                            GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace,
+                            size_t ws_bytes, gode_stream_t stream) {
   if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !t_host || !opts || !grad_y0 || !grad_params ||
       !workspace)
     return GODE_ERR_ARG;
@@ -154,7 +154,8 @@ int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const flo
   for (int i = 1; i < T; ++i)
     if (!(t_host[i] > t_host[i - 1])) return GODE_ERR_ARG;
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
-  return dopri5_small_adjoint_bwd(traj, grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, opts, grad_y0, grad_params,
+  if (param_mask < 0 || param_mask > 15) return GODE_ERR_ARG;
+  return dopri5_small_adjoint_bwd(traj, grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, opts, param_mask, grad_y0, grad_params,
                                   log, att_dt, att_er, att_acc, workspace, ws_bytes, (cudaStream_t)stream);
 }
 

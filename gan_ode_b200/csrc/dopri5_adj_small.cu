@@ -41,6 +41,7 @@ struct Dp5AdjArgs {
   float* totals;    // [VT]
   GodeAdaptiveOpts o;
   int B, T, layout;
+  int param_mask;  // bit k: parameter tensor k (W1, b1, W2, b2) is an adjoint parameter, i.e. enters the norm (adjoint.py)
   double t[kAdjMaxT];  // forward grid, increasing (already negated by the host for a decreasing t, o.fsign = -1)
 };
 
@@ -317,8 +318,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) dopri5_adjoint_bwd_kernel(const
       for (int q = 1; q < WARPS; ++q) t4[k] += s_r4[q * 4 + k];
     }
     __syncthreads();
-    return fmaxf(fmaxf(sqrtf(t4[0] / (float)(H * D)), sqrtf(t4[1] / (float)H)),
-                 fmaxf(sqrtf(t4[2] / (float)(D * H)), sqrtf(t4[3] / (float)D)));
+    const int m = p.param_mask;
+    return fmaxf(fmaxf(m & 1 ? sqrtf(t4[0] / (float)(H * D)) : 0.f, m & 2 ? sqrtf(t4[1] / (float)H) : 0.f),
+                 fmaxf(m & 4 ? sqrtf(t4[2] / (float)(D * H)) : 0.f, m & 8 ? sqrtf(t4[3] / (float)D) : 0.f));
   };
 
   float y[S::DL], a[S::DL], ky[7][S::DL], ka[7][S::DL], r2[Q];
@@ -617,8 +619,8 @@ size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H) {
 
 int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
                              const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
-                             const GodeAdaptiveOpts* opts, float* grad_y0, float* grad_params, GodeStepLog* log,
-                             double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
+                             const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
+                             GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
                              cudaStream_t st) {
   if (T > kAdjMaxT) return GODE_ERR_T_TOO_LONG;
   if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
@@ -627,7 +629,7 @@ int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const fl
   Dp5AdjArgs a{};
   a.traj = traj; a.grad_traj = grad_traj; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
   a.grad_y0 = grad_y0; a.grad_params = grad_params; a.log = log; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
-  a.o = *opts; a.B = B; a.T = T; a.layout = layout;
+  a.o = *opts; a.B = B; a.T = T; a.layout = layout; a.param_mask = param_mask;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
   auto kern = dopri5_adjoint_bwd_kernel<16, 16, 8, WARPS>;
   const size_t smem = sizeof(float) * A::kSmemFloats;

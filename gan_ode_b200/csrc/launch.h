@@ -65,8 +65,8 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
 size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H);
 int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
                              const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
-                             const GodeAdaptiveOpts* opts, float* grad_y0, float* grad_params, GodeStepLog* log,
-                             double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
+                             const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
+                             GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
                              cudaStream_t st);
 int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,

@@ -35,7 +35,7 @@ class GraphedSolveStep:
         dev = torch.device(device) if device is not None else W1.device
         assert dev.type == "cuda", "GraphedSolveStep needs the ODEFunc on a CUDA device"
         self.func, self.t, self.device = func, t, dev
-        self.params = [p for p in _api.recognise_field(func)]
+        self.params = _api.field_parameters(func)
         self._solve = _api.odeint_adjoint if adjoint else _api.odeint
         self._kw = dict(method=method, rtol=rtol, atol=atol, options=options)
         T = len(t)

@@ -65,6 +65,12 @@ def recognise_field(func):
         if (type(l0) is nn.Linear and type(act) is nn.Tanh and type(l2) is nn.Linear and l0.bias is not None
                 and l2.bias is not None and l0.out_features == l2.in_features and l0.in_features == l2.out_features):
             return l0.weight, l0.bias, l2.weight, l2.bias
+    if mods is not None and len(mods) == 2:
+        # models/mocogan_mnist.py:6-16: f(x) = tanh(W x + b).  Runs on the same kernels as W2 tanh(W1 x + b1) + b2 with
+        # W2 = I, b2 = 0 — bit-exact in fp32 (sum of h_d and exact zeros); the two constants take no gradient.
+        l0, act = mods.get("0"), mods.get("1")
+        if (type(l0) is nn.Linear and type(act) is nn.Tanh and l0.bias is not None and l0.in_features == l0.out_features):
+            return (l0.weight, l0.bias) + _identity_layer(l0.in_features, l0.weight.device)
     ok = (isinstance(fn, nn.Sequential) and len(fn) == 3 and isinstance(fn[0], nn.Linear)
           and isinstance(fn[1], nn.Tanh) and isinstance(fn[2], nn.Linear)
           and fn[0].bias is not None and fn[2].bias is not None
@@ -72,9 +78,26 @@ def recognise_field(func):
     if not ok:
         raise NotImplementedError(
             "gan_ode_b200 fuses the solver with the reference's ODEFunc (models/mocogan_ode.py:6-17): func.fn must be "
-            "nn.Sequential(nn.Linear(D,H), nn.Tanh(), nn.Linear(H,D)); got {!r}. There is no generic fallback."
+            "nn.Sequential(nn.Linear(D,H), nn.Tanh(), nn.Linear(H,D)) — or nn.Sequential(nn.Linear(D,D), nn.Tanh()), "
+            "models/mocogan_mnist.py:6-16; got {!r}. There is no generic fallback."
             .format(type(func).__name__))
     return fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias
+
+
+_IDENTITY = {}
+
+
+def _identity_layer(D, device):
+    k = (D, str(device))
+    v = _IDENTITY.get(k)
+    if v is None:
+        v = _IDENTITY[k] = (torch.eye(D, dtype=torch.float32, device=device), torch.zeros(D, dtype=torch.float32, device=device))
+    return v
+
+
+def field_parameters(func):
+    """The nn.Parameters of a recognised field, in parameters() order (the single-layer field has two)."""
+    return [q for q in recognise_field(func) if isinstance(q, nn.Parameter)]
 
 
 _SIZE_CACHE = {}
@@ -544,7 +567,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         rc = L.gode_dopri5_adjoint_bwd(
             _ptr(buf), _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
-            meta["layout"], C.byref(ao), _ptr(grad_y0), _ptr(grad_p), base, base + 64 + 8 * cap, base + 64 + 16 * cap,
+            meta["layout"], C.byref(ao), meta["param_mask"], _ptr(grad_y0), _ptr(grad_p), base, base + 64 + 8 * cap, base + 64 + 16 * cap,
             base + 64 + 20 * cap, _ptr(ws), ws_bytes, _stream())
         if rc == _lib.ERR_COOP:
             raise GodeError("the continuous dopri5 adjoint keeps the whole batch co-resident (at most 9472 trajectories per "
@@ -755,6 +778,8 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
                                                                       "min_step", "max_step", "max_num_steps", "log_capacity")}
             elif "norm" in a_options:
                 raise NotImplementedError("a custom adjoint norm is not supported: the kernel uses torchdiffeq's default")
+            # adjoint.py: adjoint_params = the parameters with requires_grad; only those are in the augmented state / norm
+            meta["param_mask"] = sum(1 << k for k, q in enumerate((W1, b1, W2, b2)) if q.requires_grad)
             meta["adj_opts"] = _adaptive_opts(rtol if a_rtol is None else a_rtol, atol if a_atol is None else a_atol,
                                               dict(a_options), fsign)
             return _Dopri5Adjoint.apply(y0, meta, W1, b1, W2, b2)
@@ -791,7 +816,7 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
         if adjoint_options:
             raise NotImplementedError("adjoint_options are not supported with a fixed-grid method on the fused path")
     if adjoint_params is not None:
-        mine = [p for p in recognise_field(func)]
+        mine = field_parameters(func)
         given = [p for p in adjoint_params]
         if len(given) != len(mine) or any(a is not b for a, b in zip(given, mine)):
             raise NotImplementedError("adjoint_params must be func's own parameters (or None)")

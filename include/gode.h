@@ -173,14 +173,15 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
  * opts->fsign = -1 if the caller's t was decreasing); opts: ADJOINT tolerances and controller options (rtol, atol,
  * first_step, safety, ifactor, dfactor, min/max_step, max_num_steps, log_capacity for the optional att_* arrays, which
  * hold the attempts of all intervals back to back; NULL = no log).  log (optional): status / attempts / accepted / nfe
- * summed over the intervals, dt0 of the last one.  One cooperative launch: the batch must be co-resident (<= 9472
+ * summed over the intervals, dt0 of the last one.  param_mask: bit k set = parameter tensor k (W1, b1, W2, b2) is an adjoint
+ * parameter (adjoint.py keeps those with requires_grad) and enters the norm; 15 = all.  One cooperative launch: the batch must be co-resident (<= 9472
  * trajectories; GODE_ERR_COOP beyond).  workspace: gode_dopri5_adjoint_workspace_bytes(B,D,H) bytes.  Deterministic. */
 size_t gode_dopri5_adjoint_workspace_bytes(int B, int D, int H);
 int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
-                            const GodeAdaptiveOpts* opts, float* grad_y0, float* grad_params, GodeStepLog* log,
-                            double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
-                            gode_stream_t stream);
+                            const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
+                            GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace,
+                            size_t ws_bytes, gode_stream_t stream);
 
 /* ---- a5 (opt-in): dopri5 with PER-TRAJECTORY step control (GODE_NORM_TRAJ) ----------------------------------- */
 /* Every trajectory has its own (t, dt), RMS error norm over its own D components and accept/reject sequence — what

@@ -183,17 +183,18 @@ def test_cuda_dopri5_backprop_matches_golden():
 
 
 @pytest.mark.gpu
-def test_cuda_dopri5_adjoint_default_tolerances_matches_golden():
-    """The ODE-RNN call: forward within fp32 noise of the oracle; gradients (discrete adjoint here, continuous adjoint
-    in the fixture) agree to O(tolerance)."""
+@pytest.mark.parametrize("mode,tol", [("continuous", 5e-5), ("discrete", 1e-3)])
+def test_cuda_dopri5_adjoint_default_tolerances_matches_golden(mode, tol):
+    """The ODE-RNN call: forward within fp32 noise of the oracle; gradients by the continuous adjoint kernel (the algorithm
+    of the fixture) and, opt-in, by the discrete adjoint of the recorded steps (equal to O(tolerance))."""
     _need_gpu()
     import gan_ode_b200 as gode
     z = load("dopri5_adjoint_default_tol_B4")
-    sol, grads = run_ode(gode, z, True, dict(), dev=DEV)
+    sol, grads = run_ode(gode, z, True, dict(options={"adjoint": mode}), dev=DEV)
     assert rel_err(sol, T(z["sol"])) <= 1e-5
-    assert rel_err(grads[0], T(z["grad_y0"])) <= 1e-3
+    assert rel_err(grads[0], T(z["grad_y0"])) <= tol
     for g, n in zip(grads[1:], PN):
-        assert rel_err(g, T(z["grad_" + n])) <= 1e-3, n
+        assert rel_err(g, T(z["grad_" + n])) <= tol, n
 
 
 @pytest.mark.gpu
@@ -234,7 +235,8 @@ def test_cuda_caller_reproduces_reference_run_odernn(cuda_as_torchdiffeq):
     _need_gpu()
     z = load("reference_sample_z_m_odernn")
     m = _caller_rnn(z, DEV)
-    _check_caller(z, m, m.sample_z_m(z["h0"].shape[0], h0=T(z["h0"]), eps=T(z["eps"])), 2e-5, 1e-3, DEV)
+    # through the shim the backward is the continuous dopri5 adjoint, as in the run that made the fixture
+    _check_caller(z, m, m.sample_z_m(z["h0"].shape[0], h0=T(z["h0"]), eps=T(z["eps"])), 2e-5, 1e-4, DEV)
 
 
 @pytest.mark.gpu

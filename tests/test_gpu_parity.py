@@ -1076,3 +1076,43 @@ def test_odernn_fused_sampler_per_trajectory_step_control(monkeypatch):
     cb = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, hb, eb, rtol=1e-5, atol=1e-5, options=opt)
     cb.sum().backward()
     assert torch.isfinite(cb).all() and torch.isfinite(hb.grad).all()
+
+
+# ---- f4: the single-layer field of models/mocogan_mnist.py:6-16, f(x) = tanh(W x + b) ---------------------------------------
+class _OneLayerField(torch.nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.fn = torch.nn.Sequential(torch.nn.Linear(dim, dim), torch.nn.Tanh())
+
+    def forward(self, t, x):
+        return self.fn(x)
+
+
+@pytest.mark.parametrize("method,adjoint", [("rk4", True), ("rk4", False), ("dopri5", True), ("dopri5", False)])
+def test_single_layer_tanh_field(method, adjoint):
+    """Runs on the two-layer kernels with W2 = I, b2 = 0 (exact in fp32); gradients for the two real parameters only.  In the
+    dopri5 adjoint the two constants are not adjoint parameters, so they stay out of the step-control norm (param_mask)."""
+    _need_gpu()
+    import copy
+    torch.manual_seed(5)
+    f = _OneLayerField(16)
+    with torch.no_grad():
+        for q in f.parameters():
+            q.mul_(2.0)
+    fg = copy.deepcopy(f).to(DEV)
+    t = _t16() if method == "rk4" else torch.tensor([0.0, 0.5, 1.0])
+    y0, g = torch.randn(50, 16), torch.randn(len(t), 50, 16)
+    kw = dict(method=method) if method == "rk4" else dict(method=method, rtol=1e-6, atol=1e-7)
+
+    def run(mod, field, y, gg):
+        y = y.clone().requires_grad_(True)
+        sol = (mod.odeint_adjoint if adjoint else mod.odeint)(field, y, t, **kw)
+        grads = torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+        return sol.detach(), grads
+
+    ref_sol, ref = run(tdq, f, y0, g)
+    out_sol, out = run(gode, fg, y0.to(DEV), g.to(DEV))
+    assert len(out) == 3
+    assert rel_err(out_sol, ref_sol) <= (TOL if method == "rk4" else 2e-5)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) <= (2e-5 if method == "rk4" else 1e-4), rel_err(a, b)

@@ -50,6 +50,17 @@ def test_field_recognition():
 
     with pytest.raises(NotImplementedError):
         gode.recognise_field(Wrong())
+
+    class OneLayer(torch.nn.Module):   # models/mocogan_mnist.py:6-16
+        def __init__(self):
+            super().__init__()
+            self.fn = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.Tanh())
+
+    one = OneLayer()
+    W1, b1, W2, b2 = gode.recognise_field(one)
+    assert W1 is one.fn[0].weight and torch.equal(W2, torch.eye(16)) and not W2.requires_grad and not b2.any()
+    from gan_ode_b200.odeint import field_parameters
+    assert [id(q) for q in field_parameters(one)] == [id(q) for q in one.parameters()]
     f, g = recognise_sde(SDEFunc(16, 16))
     assert f[0].shape == (16, 16) and g[2].shape == (16, 16)
     with pytest.raises(NotImplementedError):
