@@ -62,7 +62,7 @@ _SIGS = {
     "gode_odernn_log_stride": (C.c_size_t, [_I]),
     "gode_odernn_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_odernn_fwd": (_I, [_P] * 10 + [_I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts)] + [_P] * 7 + [C.c_size_t, _P]),
-    "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 11 + [C.c_size_t, _P]),
+    "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 12 + [C.c_size_t, _P]),
     "gode_fixed_fwd": (_I, [_I] + [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "gode_fixed_adjoint_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_fixed_backprop_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),

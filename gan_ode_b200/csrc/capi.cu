@@ -264,15 +264,16 @@ int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const fl
 int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
                     int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
-                    const float* ckpt, const double* acc, const int32_t* n_acc, float* grad_h0, float* grad_eps,
-                    float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes,
-                    gode_stream_t stream) {
-  if (!grad_codes || !eps || !W1 || !b1 || !W2 || !b2 || !w_ih || !w_hh || !b_ih || !b_hh || !seg || !logs || !ckpt ||
-      !acc || !grad_h0 || !grad_ode || !grad_gru || !scratch || !workspace || B <= 0 || F < 1 || ckpt_capacity <= 0)
+                    const float* ckpt, const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts,
+                    float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
+                    size_t ws_bytes, gode_stream_t stream) {
+  if (!grad_codes || !eps || !W1 || !b1 || !W2 || !b2 || !w_ih || !w_hh || !b_ih || !b_hh || !seg || !grad_h0 ||
+      !grad_ode || !grad_gru || !scratch || !workspace || B <= 0 || F < 1)
     return GODE_ERR_ARG;
+  if (!adjoint_opts && (!logs || !ckpt || !acc || ckpt_capacity <= 0)) return GODE_ERR_ARG;
   return odernn_bwd(grad_codes, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh, B, D, H, F, ckpt_capacity, seg,
                     reinterpret_cast<const unsigned char*>(logs), odernn_log_stride(log_capacity), ckpt, acc, n_acc,
-                    grad_h0, grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes, (cudaStream_t)stream);
+                    adjoint_opts, grad_h0, grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* pads_dev, int rank, int world, int cap,

@@ -14,9 +14,9 @@
 //
 // One cooperative launch for the whole backward.  A trajectory is split over 8 lanes as in the other small-field kernels;
 // y, a and their seven stage derivatives stay in registers.  The theta-part of a stage is the outer products
-// delta (x) u, delta, cot (x) h, cot of one trajectory: 68 values per lane, summed over the 4 trajectories of the warp by a
-// two-level reduce-scatter (shuffles) so that each lane keeps 17 of the warp's 544 values, and folded with the three tableau
-// weights into per-warp accumulators in shared memory.  At the end of an attempt: warps -> CTA partial row in global memory,
+// delta (x) u, delta, cot (x) h, cot summed over the warp's 4 trajectories; their gather lines lie side by side in shared
+// memory, so each lane forms one weight row (+ its bias) of the warp's sum directly — 17 of the warp's 544 values, no
+// exchange — and folds it with the three tableau weights into per-warp accumulators in shared memory.  At the end of an attempt: warps -> CTA partial row in global memory,
 // grid barrier, the float4 columns of the partial matrix are dealt to the warps of the grid and summed in a fixed order,
 // grid barrier, every CTA reads the 2184 totals and evaluates the theta-part of the norm itself (same code on the same data:
 // bit-identical in every CTA, so the accept/reject branch is uniform).  Deterministic: no atomics anywhere.
@@ -102,26 +102,24 @@ template <int D, int H, int L, int WARPS>
 struct AdjLayout {
   using S = Shape<D, H, L>;
   static constexpr int P = S::P;
-  static constexpr int Q = P / 32;                   // values of the warp's theta sum kept by one lane
-  static constexpr int NH = S::HL * D + S::HL;       // a lane's layer-1 slots (rows of W1 + b1) == its layer-2 slots
+  static constexpr int Q = D + 1;                    // values of the warp's theta sum owned by one lane: a weight row + its bias
   static constexpr int VT = kAdjNV * P + kAdjNS;
-  static_assert(S::G == 4 && S::HL == S::DL && D == H, "the reduce-scatter is written for 4 trajectories per warp, D == H");
-  static_assert(NH == 2 * Q && VT % 4 == 0 && P % 4 == 0, "slot bookkeeping");
+  static_assert(D == H && H == 16 && 32 * Q == P, "lanes 0..15 own (W1 row j | b1[j]), lanes 16..31 own (W2 row d | b2[d])");
+  static_assert(VT % 4 == 0 && P % 4 == 0, "float4 columns");
   static constexpr int kSmemFloats = WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats +
                                      SmemRowWeights<D, H, L>::kFloats +
                                      kAdjNV * WARPS * P + 2 * P + VT + WARPS * kAdjNS + WARPS * 4;
-  // native index n = lane*Q + q of the reduce-scattered layout -> index in the flat [W1|b1|W2|b2] vector, tensor id 0..3
+  // native index n = lane*Q + q -> index in the flat [W1|b1|W2|b2] vector, tensor id 0..3
   __device__ static __forceinline__ int canon(int n, int& tensor) {
-    const int lane = n / Q, q = n % Q, g = lane / L, l = lane % L;
-    const int half = g & 1, s = (g >> 1) * Q + q;
-    if (half == 0) {
-      if (s < S::HL * D) { tensor = 0; return (l * S::HL + s / D) * D + s % D; }
+    const int lane = n / Q, q = n % Q, r = lane & 15;
+    if (lane < 16) {
+      if (q < D) { tensor = 0; return r * D + q; }
       tensor = 1;
-      return H * D + l * S::HL + (s - S::HL * D);
+      return H * D + r;
     }
-    if (s < S::DL * H) { tensor = 2; return H * D + H + (l * S::DL + s / H) * H + s % H; }
+    if (q < H) { tensor = 2; return H * D + H + r * H + q; }
     tensor = 3;
-    return H * D + H + D * H + l * S::DL + (s - S::DL * H);
+    return H * D + H + D * H + r;
   }
 };
 
@@ -142,7 +140,6 @@ __global__ void __launch_bounds__(WARPS * 32, 2) dopri5_adjoint_bwd_kernel(const
   float* s_sc = s_tot + VT;                            // [WARPS][kAdjNS]
   float* s_r4 = s_sc + WARPS * kAdjNS;                 // [WARPS][4]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
-  const bool half = g & 1, quarter = (g >> 1) & 1;
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
@@ -198,30 +195,30 @@ __global__ void __launch_bounds__(WARPS * 32, 2) dopri5_adjoint_bwd_kernel(const
 #pragma unroll
     for (int dl = 0; dl < S::DL; ++dl) ka[dl] = dot_smem<H>(cw.w1t + (dl * L + l) * S::HS, ln.dl);
     GADJ_TICK(tc_v);
-    // theta-part: layer-1 slots delta (x) u | delta, layer-2 slots cot (x) h | cot.  Level 1 of the reduce-scatter pairs
-    // trajectories g and g^1: even g keeps the layer-1 half, odd g the layer-2 half.
-    float r1[A::NH];
+    // theta-part, summed over the warp's trajectories without any exchange: the lines of all G trajectories sit side by side
+    // in this warp's shared-memory block, so lane r < 16 forms row r of dW1 = sum_g delta_g[r] u_g (and db1[r]), lane 16 + r
+    // row r of dW2 = sum_g cot_g[r] h_g (and db2[r]) with broadcast reads — 17 of the warp's 544 values per lane.
+    {
+      const float* wl = s_lines + warp * BL::kFloatsPerWarp;
+      const bool lower = lane < 16;
+      const int r = lane & 15;
+      const float* sv = lower ? wl + S::G * (2 * S::YS + S::HS) + r : wl + S::G * (S::YS + S::HS) + r;  // delta_g[r] : cot_g[r]
+      const float* lv = lower ? wl : wl + S::G * S::YS;                                              // u_g : h_g
+      const int svs = lower ? S::HS : S::YS, lvs = lower ? S::YS : S::HS;
 #pragma unroll
-    for (int jl = 0; jl < S::HL; ++jl) {
+      for (int q = 0; q < Q; ++q) r2[q] = 0.f;
 #pragma unroll
-      for (int i = 0; i < D; i += 4) {
-        const float4 yv = *reinterpret_cast<const float4*>(ln.y + i);
-        const float4 hv = *reinterpret_cast<const float4*>(ln.h + i);
-        const float y4[4] = {yv.x, yv.y, yv.z, yv.w}, h4[4] = {hv.x, hv.y, hv.z, hv.w};
+      for (int gg = 0; gg < S::G; ++gg) {
+        const float sg = sv[gg * svs];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float v1 = delta[jl] * y4[e], v2 = cot[jl] * h4[e];
-          r1[jl * D + i + e] = (half ? v2 : v1) + __shfl_xor_sync(0xffffffffu, half ? v1 : v2, L);
+        for (int i = 0; i < D; i += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(lv + gg * lvs + i);
+          r2[i] = fmaf(sg, v.x, r2[i]); r2[i + 1] = fmaf(sg, v.y, r2[i + 1]);
+          r2[i + 2] = fmaf(sg, v.z, r2[i + 2]); r2[i + 3] = fmaf(sg, v.w, r2[i + 3]);
         }
+        r2[D] += sg;
       }
     }
-#pragma unroll
-    for (int jl = 0; jl < S::HL; ++jl)
-      r1[S::HL * D + jl] = (half ? cot[jl] : delta[jl]) + __shfl_xor_sync(0xffffffffu, half ? delta[jl] : cot[jl], L);
-    // level 2 pairs g and g^2: the lower pair keeps the first Q of the half, the upper pair the rest
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-      r2[q] = (quarter ? r1[Q + q] : r1[q]) + __shfl_xor_sync(0xffffffffu, quarter ? r1[q] : r1[Q + q], 2 * L);
     __syncwarp();  // all lanes are done with ln.y / ln.h before the next evaluation overwrites them
     GADJ_TICK(tc_t);
   };

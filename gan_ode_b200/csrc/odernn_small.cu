@@ -165,9 +165,17 @@ int gru_grid(int B) {
 
 size_t odernn_log_stride(int log_capacity) { return align256(64 + (size_t)21 * (size_t)(log_capacity > 0 ? log_capacity : 0)); }
 
+// workspace head shared by the per-frame solver launches: forward, replay backward, continuous adjoint
+static size_t odernn_solver_ws(int B, int D, int H) {
+  size_t m = dopri5_small_workspace_bytes(B, D, H);
+  const size_t bw = bwd_workspace_bytes(H * D + H + D * H + D), ad = dopri5_small_adjoint_workspace_bytes(B, D, H);
+  if (bw > m) m = bw;
+  if (ad > m) m = ad;
+  return align256(m);
+}
+
 size_t odernn_workspace_bytes(int B, int D, int H) {
-  const size_t dp = dopri5_small_workspace_bytes(B, D, H), bw = bwd_workspace_bytes(H * D + H + D * H + D);
-  return align256(dp > bw ? dp : bw) + sizeof(float) * (size_t)GP * (size_t)(sm_count() * 4) + 256;
+  return odernn_solver_ws(B, D, H) + sizeof(float) * (size_t)GP * (size_t)(sm_count() * 4) + 256;
 }
 
 int gru_jump_fwd(const float* x, const float* h, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -234,8 +242,8 @@ int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* 
 int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
                int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
-               const double* acc, const int32_t* n_acc, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru,
-               float* scratch, void* workspace, size_t ws_bytes, cudaStream_t st) {
+               const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts, float* grad_h0, float* grad_eps,
+               float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
   const double t01[2] = {0.0, 1.0};
   const int P1 = H * D + H + D * H + D, kc = ckpt_capacity;
@@ -243,8 +251,7 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
   float* carry = scratch;
   float* gtraj = scratch + bd;
   float* slots = scratch + 3 * bd;
-  const size_t dp_ws = align256(ws_bytes > 0 ? (dopri5_small_workspace_bytes(B, D, H) > bwd_workspace_bytes(P1)
-                                                   ? dopri5_small_workspace_bytes(B, D, H) : bwd_workspace_bytes(P1)) : 0);
+  const size_t dp_ws = odernn_solver_ws(B, D, H);
   if (ws_bytes < dp_ws + sizeof(float) * (size_t)GP * (size_t)gru_grid(B)) return GODE_ERR_WORKSPACE;
   void* gru_ws = reinterpret_cast<unsigned char*>(workspace) + dp_ws;
   cudaMemsetAsync(gtraj, 0, sizeof(float) * bd, st);  // no gradient reaches the solve's copy of its own input
@@ -255,6 +262,13 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
                           grad_gru, f != F - 1, gru_ws, ws_bytes - dp_ws, st);
     if (rc) return rc;
     const unsigned char* lg = logs + (size_t)f * log_stride;
+    if (adjoint_opts) {  // torchdiffeq's continuous adjoint of this frame's solve (dopri5_adj_small.cu); needs no checkpoints
+      rc = dopri5_small_adjoint_bwd(tr, gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD, adjoint_opts, 15,
+                                    f == 0 ? grad_h0 : carry, slots + (size_t)f * P1, nullptr, nullptr, nullptr, nullptr,
+                                    workspace, dp_ws, st);
+      if (rc) return rc;
+      continue;
+    }
     if (n_acc) {  // per-trajectory step control: replay every trajectory's own accepted steps
       const double* a0 = acc + (size_t)f * 2 * kc * B;
       rc = dopri5_traj_small_bwd(gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD,

@@ -5,7 +5,8 @@ through `install_shims()` — 16 fused dopri5 launches plus `nn.GRUCell` in PyTo
 for the same computation: `odernn_codes(ode_fn, gru, h0, eps)` enqueues all F (solve, jump) pairs from C
 (`gode_odernn_fwd`), the GRU jump is a CUDA kernel of this library, and the backward (`gode_odernn_bwd`) walks the frames
 in reverse on the device.  Step control, tolerances and results are those of F separate `odeint` calls with torchdiffeq's
-defaults; gradients are the discrete adjoint of the recorded solves (see odeint._solve).  `options={'norm': 'trajectory'}`
+defaults; gradients are the discrete adjoint of the recorded solves (see odeint._solve), or with
+`options={'adjoint': 'continuous'}` torchdiffeq's continuous adjoint per frame, as the reference loop computes them.  `options={'norm': 'trajectory'}`
 (opt-in, not what torchdiffeq does for a batch) gives every trajectory its own step control: no grid-wide reduction per
 attempted step, ordinary launches, any batch size.
 """
@@ -92,7 +93,7 @@ class _OdeRnn(torch.autograd.Function):
         dev = h0.device
         ts = [_f32c(v) for v in (h0, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh)]
         o = meta["opts"]
-        keep = meta["keep"]
+        keep = meta["keep"] and meta["adj_opts"] is None    # the continuous adjoint needs the frame end points only
         opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
         kc = o.ckpt_capacity if keep else 0
         opts.ckpt_capacity = kc
@@ -119,7 +120,8 @@ class _OdeRnn(torch.autograd.Function):
     def backward(ctx, grad_codes):
         L = _lib.lib()
         seg, logs, ckpt, acc, n_acc, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
-        if ckpt is None:
+        ao = ctx.meta["adj_opts"]
+        if ckpt is None and ao is None:
             raise _lib.GodeError("ODE-RNN forward ran without checkpoints (inputs did not require grad)")
         F, _, B, D = seg.shape
         H = W1.shape[0]
@@ -136,8 +138,8 @@ class _OdeRnn(torch.autograd.Function):
         o = ctx.meta["opts"]
         _lib.check(L.gode_odernn_bwd(g.data_ptr(), eps.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                      w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), B, D, H, F,
-                                     o.log_capacity, ctx.kc, seg.data_ptr(), logs.data_ptr(), ckpt.data_ptr(), acc.data_ptr(),
-                                     _ptr(n_acc), gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
+                                     o.log_capacity, ctx.kc, seg.data_ptr(), logs.data_ptr(), _ptr(ckpt), _ptr(acc),
+                                     _ptr(n_acc), C.byref(ao) if ao is not None else None, gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
                                      ws.data_ptr(), wsb, _stream()), "gode_odernn_bwd")
         from .odeint import _maybe_allreduce
         _maybe_allreduce(gode_)
@@ -164,5 +166,13 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
     options = {} if options is None else dict(options)
     o = _adaptive_opts(rtol, atol, options, 1.0)
     keep = torch.is_grad_enabled() and any(t.requires_grad for t in (h0, eps, W1, b1, W2, b2) + tuple(gp))
-    meta = dict(opts=o, keep=keep)
+    mode = options.get("adjoint", "discrete")
+    if mode not in ("continuous", "discrete"):
+        raise ValueError("options['adjoint'] must be 'continuous' or 'discrete'")
+    adj = None
+    if mode == "continuous":
+        if o.norm_scope != _lib.NORM_BATCH:
+            raise NotImplementedError("the continuous adjoint uses torchdiffeq's batch-global norm")
+        adj = _adaptive_opts(rtol, atol, {k: v for k, v in options.items() if k != "norm"}, 1.0)
+    meta = dict(opts=o, keep=keep, adj_opts=adj)
     return _OdeRnn.apply(h0, eps, meta, W1, b1, W2, b2, *gp)

@@ -251,13 +251,15 @@ int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const fl
                     int32_t* n_acc, void* workspace, size_t ws_bytes, gode_stream_t stream);
 /* Reverse-mode through the F (solve, jump) pairs: GRU VJP, then the discrete adjoint of that frame's recorded solve.
  * grad_eps may be NULL.  grad_ode ([W1|b1|W2|b2]) and grad_gru are OVERWRITTEN (per-frame slots summed in frame order).
- * scratch: (3*B*D + F*gode_param_count(D,H)) floats. */
+ * scratch: (3*B*D + F*gode_param_count(D,H)) floats.  adjoint_opts non-NULL: each frame's solve is differentiated by
+ * torchdiffeq's continuous adjoint instead (gode_dopri5_adjoint_bwd with these tolerances / controller options, what the
+ * reference loop computes); logs / ckpt / acc are then unused and may be NULL, and B is limited as there. */
 int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
                     int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
-                    const float* ckpt, const double* acc, const int32_t* n_acc, float* grad_h0, float* grad_eps,
-                    float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes,
-                    gode_stream_t stream);
+                    const float* ckpt, const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts,
+                    float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
+                    size_t ws_bytes, gode_stream_t stream);
 
 /* ---- e: data-parallel exchange ------------------------------------------------------------------------------------ */
 /* One-shot all-reduce (sum, in place) of `n` floats over peer memory (NVLink / NVSwitch), the fused alternative to

@@ -29,9 +29,9 @@ def timeit(fn, n=7):
     return sorted(ts)[n // 2]
 
 
-def fused(bwd):
+def fused(bwd, mode="discrete"):
     m.zero_grad()
-    codes = gode.odernn_codes(m.ode_fn, m.recurrent, h0, eps)
+    codes = gode.odernn_codes(m.ode_fn, m.recurrent, h0, eps, options={"adjoint": mode})
     if bwd:
         (codes.transpose(0, 1).reshape(-1, 16) * w).sum().backward()
 
@@ -47,8 +47,13 @@ gode.install_shims()
 with torch.no_grad():
     tf0, tu0 = timeit(lambda: fused(False)), timeit(lambda: unfused(False))
 tf1, tu1 = timeit(lambda: fused(True)), timeit(lambda: unfused(True))
+tfc = timeit(lambda: fused(True, "continuous"))
+gode.config.dopri5_adjoint = "discrete"
+tud = timeit(lambda: unfused(True))
+gode.config.dopri5_adjoint = "continuous"
 fr = gode.odernn.last_log().frames()
 att = sum(f["n_attempts"] for f in fr)
 print("B=%d F=%d attempted steps (sum over frames) %d, accepted %d" % (B, F, att, sum(f["n_accepted"] for f in fr)))
 print("forward      fused %.3f ms | shim loop %.3f ms" % (tf0, tu0))
-print("fwd+bwd      fused %.3f ms | shim loop %.3f ms  -> %.3e trajectory-steps/s fused" % (tf1, tu1, B * att / tf1 * 1e3))
+print("fwd+bwd      fused %.3f ms | shim loop %.3f ms  -> %.3e trajectory-steps/s fused   (discrete gradient | continuous adjoint)" % (tf1, tu1, B * att / tf1 * 1e3))
+print("fwd+bwd      fused, continuous adjoint %.3f ms | shim loop, discrete gradient %.3f ms" % (tfc, tud))

@@ -933,6 +933,17 @@ def test_odernn_fused_sampler_matches_oracle_and_unfused_path(monkeypatch):
     codes2 = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg)
     assert torch.equal(codes, codes2)
 
+    # options={'adjoint': 'continuous'}: the frame loop in C with torchdiffeq's continuous adjoint per frame — the algorithm
+    # of the oracle run above, so the gradients agree an order of magnitude tighter than the discrete ones
+    gpu_model.zero_grad()
+    h0c, epsc = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+    codes_c = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0c, epsc, options={"adjoint": "continuous"})
+    assert torch.equal(codes_c, codes)
+    (codes_c.transpose(0, 1).reshape(-1, 16) * w.to(DEV)).sum().backward()
+    for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        assert rel_err(p.grad, q.grad) <= 1e-4, (n, rel_err(p.grad, q.grad))
+    assert rel_err(h0c.grad, h0u.grad) <= 1e-4 and rel_err(epsc.grad, epsu.grad) <= 1e-4
+
 
 @pytest.mark.parametrize("D,H", [(64, 256), (16, 16)])
 @pytest.mark.parametrize("case", ["btd_decreasing", "two_points", "long_grid_device_dt"])
