@@ -21,6 +21,7 @@
 // grid barrier, every CTA reads the 2184 totals and evaluates the theta-part of the norm itself (same code on the same data:
 // bit-identical in every CTA, so the accept/reject branch is uniform).  Deterministic: no atomics anywhere.
 #include <stdio.h>
+#include <stdlib.h>
 #include <type_traits>
 #include "dopri5_common.cuh"
 
@@ -123,8 +124,8 @@ struct AdjLayout {
   }
 };
 
-template <int D, int H, int L, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) dopri5_adjoint_bwd_kernel(const __grid_constant__ Dp5AdjArgs p) {
+template <int D, int H, int L, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(const __grid_constant__ Dp5AdjArgs p) {
   using S = Shape<D, H, L>;
   using BL = BwdLines<D, H, L>;
   using A = AdjLayout<D, H, L, WARPS>;
@@ -614,29 +615,18 @@ size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H) {
   return align256(grid_sync_bytes(grid)) + align256(sizeof(float) * (size_t)grid * A::VT) + align256(sizeof(float) * A::VT);
 }
 
-int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
-                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
-                             const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
-                             GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
-                             cudaStream_t st) {
-  if (T > kAdjMaxT) return GODE_ERR_T_TOO_LONG;
-  if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
+template <int L, int MINB>
+static int launch_adj(Dp5AdjArgs& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   constexpr int WARPS = kAdjWarps;
-  using A = AdjLayout<16, 16, 8, WARPS>;
-  Dp5AdjArgs a{};
-  a.traj = traj; a.grad_traj = grad_traj; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
-  a.grad_y0 = grad_y0; a.grad_params = grad_params; a.log = log; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
-  a.o = *opts; a.B = B; a.T = T; a.layout = layout; a.param_mask = param_mask;
-  for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
-  auto kern = dopri5_adjoint_bwd_kernel<16, 16, 8, WARPS>;
+  using A = AdjLayout<16, 16, L, WARPS>;
+  auto kern = dopri5_adjoint_bwd_kernel<16, 16, L, WARPS, MINB>;
   const size_t smem = sizeof(float) * A::kSmemFloats;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(1000 + (int)e);
-  const int grid = adj_grid<16, 16, 8, WARPS>(B);
+  const int grid = adj_grid<16, 16, L, WARPS>(a.B);
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, smem, limit_cache);
   if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
-  if (ws_bytes < dopri5_small_adjoint_workspace_bytes(B, D, H)) return GODE_ERR_WORKSPACE;
   char* base = reinterpret_cast<char*>(workspace);
   grid_sync_bind(a.gs, base);
   a.partials = reinterpret_cast<float*>(base + align256(grid_sync_bytes(grid)));
@@ -647,6 +637,31 @@ int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const fl
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
+}
+
+int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                             const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                             const GodeAdaptiveOpts* opts, int param_mask, float* grad_y0, float* grad_params,
+                             GodeStepLog* log, double* att_dt, float* att_er, uint8_t* att_acc, void* workspace, size_t ws_bytes,
+                             cudaStream_t st) {
+  if (T > kAdjMaxT) return GODE_ERR_T_TOO_LONG;
+  if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
+  if (ws_bytes < dopri5_small_adjoint_workspace_bytes(B, D, H)) return GODE_ERR_WORKSPACE;
+  Dp5AdjArgs a{};
+  a.traj = traj; a.grad_traj = grad_traj; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
+  a.grad_y0 = grad_y0; a.grad_params = grad_params; a.log = log; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
+  a.o = *opts; a.B = B; a.T = T; a.layout = layout; a.param_mask = param_mask;
+  for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
+  // 8 lanes per trajectory (32 per CTA) has the shortest stage chain and wins while its CTAs get an SM each; beyond that
+  // (B > 4736) 4 lanes (64 per CTA, one CTA per SM up to 9472) is faster: 0.64 vs 0.78 ms at B = 8192, 0.61 vs 0.53 ms at
+  // B = 4096 (scripts/dp5_adj_lanes.py).  Developer switch GODE_ADJ_LANES = '8' | '4' forces the first choice.
+  const char* force = getenv("GODE_ADJ_LANES");
+  const bool first8 = force ? force[0] == '8' : B <= 32 * sm_count();
+  int rc = first8 ? launch_adj<8, 2>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
+  if (rc != GODE_ERR_COOP) return rc;
+  rc = launch_adj<4, 1>(a, workspace, ws_bytes, st);
+  if (rc != GODE_ERR_COOP || first8) return rc;
+  return launch_adj<8, 2>(a, workspace, ws_bytes, st);
 }
 
 }  // namespace gode

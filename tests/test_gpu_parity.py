@@ -579,7 +579,8 @@ def test_dopri5_continuous_adjoint_same_step_sequence_as_oracle():
     assert rl.accepted == log.accepted
     assert abs(rl.dt0 - log.dt0) <= 1e-3 * rl.dt0
     for a, e in zip(log.error_ratio, rl.error_ratio):
-        assert abs(a - e) <= 2e-2 * max(e, 1e-2), (a, e)
+        # (the first attempt after the initial-step heuristic has an error estimate at fp32 rounding level: ratio ~1e-3)
+        assert abs(a - e) <= 2e-2 * max(e, 5e-2), (a, e)
     for a, b in zip(out, ref):
         assert rel_err(a, b) <= 3e-5, rel_err(a, b)     # 4x stiffer field: fp32 rounding is amplified along the solve
 
