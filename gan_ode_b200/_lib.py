@@ -17,7 +17,7 @@ LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
 MAX_HOST_STEPS = 255
 
-ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_CKPT_OVERFLOW = 1, 2, 4, 8
+ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_CKPT_OVERFLOW, ST_PEER_TIMEOUT = 1, 2, 4, 8, 16
 
 
 class GodeStepLog(C.Structure):
@@ -30,6 +30,11 @@ class GodeAdaptiveOpts(C.Structure):
                 ("ifactor", C.c_double), ("dfactor", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double),
                 ("max_num_steps", C.c_int32), ("norm_scope", C.c_int32), ("log_capacity", C.c_int32),
                 ("ckpt_capacity", C.c_int32), ("fsign", C.c_float), ("_pad", C.c_int32)]
+
+
+class GodeWorld(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("total_B", C.c_int64), ("slots_dev", C.c_void_p),
+                ("launch_ctr", C.c_void_p)]
 
 
 class GodeError(RuntimeError):
@@ -50,6 +55,8 @@ _SIGS = {
     "gode_rk4_backprop_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_dopri5_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_dopri5_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 + [C.c_size_t, _P]),
+    "gode_dopri5_fwd_world": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 +
+                              [C.c_size_t, C.POINTER(GodeWorld), _P]),
     "gode_dopri5_adjoint_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_dopri5_adjoint_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 7 + [C.c_size_t, _P]),
     "gode_dopri5_backprop_bwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P, C.c_size_t, _P]),

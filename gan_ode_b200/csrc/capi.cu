@@ -127,6 +127,26 @@ int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const flo
                           att_acc, ckpt, acc_t0, acc_dt, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_dopri5_fwd_world(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                          float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
+                          float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes,
+                          const GodeWorld* world, gode_stream_t stream) {
+  if (bad_common(y0, W1, b1, W2, b2, B, T, out_layout) || !t_host || !opts || !traj || !log || !workspace || !world)
+    return GODE_ERR_ARG;
+  if (world->world < 1 || world->world > 32 || world->rank < 0 || world->rank >= world->world || world->total_B < B ||
+      !world->slots_dev || !world->launch_ctr)
+    return GODE_ERR_ARG;
+  if (opts->log_capacity > 0 && (!att_t0 || !att_dt || !att_er || !att_acc)) return GODE_ERR_ARG;
+  if (opts->ckpt_capacity > 0 && (!ckpt || !acc_t0 || !acc_dt)) return GODE_ERR_ARG;
+  if (opts->norm_scope != GODE_NORM_BATCH) return GODE_ERR_ARG;
+  for (int i = 1; i < T; ++i)
+    if (!(t_host[i] > t_host[i - 1])) return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_small_fwd(y0, W1, b1, W2, b2, t_host, B, D, H, T, opts, out_layout, traj, log, att_t0, att_dt, att_er,
+                          att_acc, ckpt, acc_t0, acc_dt, workspace, ws_bytes, (cudaStream_t)stream, world);
+}
+
 int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,
                              const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
                              const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,

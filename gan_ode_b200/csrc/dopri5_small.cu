@@ -27,11 +27,83 @@ struct Dp5Args {
   GridSyncWs gs;              // grid all-reduce slots, zeroed by the host wrapper
   GodeAdaptiveOpts o;
   int B, T, layout;
+  // world-scope norm (gode_dopri5_fwd_world): off when w_world <= 1
+  int w_rank, w_world;
+  long long w_total_B;
+  unsigned long long* const* w_slots;
+  unsigned int* w_launch_ctr;
   double t[kMaxT];
 };
 
 __device__ __forceinline__ size_t toff(int layout, int s, int b, int B, int T, int D) {
   return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
+}
+
+// ---- world-scope norm: exchange of the per-rank totals over NVLink peer memory, inside the solver kernel ----------------
+// Every thread of the grid enters with the same per-rank totals v[] (grid_allreduce_sum) and leaves with the totals over
+// all ranks.  CTA 0 stores one tagged word {fp32 value | tag} per value into slot [rank] of EVERY rank's exchange buffer
+// (st.relaxed.sys: an aligned 8-byte store is single-copy atomic, value and tag cannot be seen torn, so no fence); warp 0
+// of every CTA polls its OWN GPU's buffer — remote writes land there — until the `world` words carry this epoch's tag, and
+// adds them in rank order.  The tag is the epoch number, counted ACROSS launches (the counter lives in device memory; every
+// rank runs the same sequence of world-scope solves with the same number of reductions, because they share the step
+// control), so tags stay unique under CUDA-graph replay and the parity double-buffering argument carries over launch
+// boundaries: a peer publishes epoch e+2 only after it finished e+1, which needs this rank's e+1 word, which is stored only
+// after every CTA here has passed its epoch-e poll.  A peer that never shows up trips a 10 s timeout instead of hanging.
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int NV>
+__device__ __forceinline__ void world_allreduce_sum(double (&v)[NV], const Dp5Args& p, unsigned int& wepoch, int& status,
+                                                    int lane, int warp) {
+  __shared__ double s_w[kGsMaxVals];
+  __shared__ int s_late;
+  ++wepoch;
+  const unsigned int tag = wepoch;
+  const int par = (int)(wepoch & 1u), W = p.w_world;
+  if (blockIdx.x == 0 && warp == 0) {
+    for (int idx = lane; idx < W * NV; idx += 32) {
+      const int r = idx / NV, k = idx % NV;
+      st_relaxed_sys_u64(p.w_slots[r] + (size_t)(par * kGsMaxVals + k) * W + p.w_rank,
+                         (unsigned long long)__float_as_uint((float)v[k]) | ((unsigned long long)tag << 32));
+    }
+  }
+  if (warp == 0) {
+    const unsigned long long* mine = p.w_slots[p.w_rank] + (size_t)par * kGsMaxVals * W;
+    const unsigned long long t_start = global_ns();
+    bool late = false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      float mine_v = 0.f;
+      if (lane < W) {
+        unsigned long long x = ld_relaxed_sys_u64(mine + (size_t)k * W + lane);
+        while ((unsigned int)(x >> 32) != tag) {
+          if (global_ns() - t_start > 10000000000ull) { late = true; break; }
+          x = ld_relaxed_sys_u64(mine + (size_t)k * W + lane);
+        }
+        mine_v = __uint_as_float((unsigned int)x);
+      }
+      double s = 0.0;
+      for (int r = 0; r < W; ++r) s += (double)__shfl_sync(0xffffffffu, mine_v, r);
+      if (lane == 0) s_w[k] = s;
+    }
+    const bool any_late = __any_sync(0xffffffffu, late);
+    if (lane == 0) s_late = any_late ? 1 : 0;
+  }
+  __syncthreads();  // (the next write to s_w is separated from these reads by the barriers of the next grid reduction)
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = s_w[k];
+  if (s_late) status |= GODE_ST_PEER_TIMEOUT;
 }
 
 template <int D, int H, int L, int WARPS>
@@ -48,9 +120,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   const int b = (blockIdx.x * WARPS + warp) * S::G + g;
   const bool valid = b < p.B;
   const bool logger = (blockIdx.x == 0 && tid == 0);
-  const double n_elem = (double)p.B * (double)D;
+  const bool world = p.w_world > 1;
+  const double n_elem = (double)(world ? p.w_total_B : (long long)p.B) * (double)D;
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
-  unsigned int epoch = 0;
+  // cumulative world epoch: read before the first grid-wide reduction; CTA 0 writes it back after the last one
+  unsigned int epoch = 0, wepoch = world ? *reinterpret_cast<volatile unsigned int*>(p.w_launch_ctr) : 0u;
 
   float y0[S::DL], k[7][S::DL], hk[S::HL];
 #pragma unroll
@@ -79,6 +153,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       }
     }
     grid_allreduce_sum<3, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
+    if (world) world_allreduce_sum<3>(v, p, wepoch, status, lane, warp);
     if (v[2] > 0.0) status |= GODE_ST_NONFINITE;
     if (p.o.first_step > 0.0) {
       dt = p.o.first_step;
@@ -97,6 +172,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         if (valid) v2[0] += (double)r * (double)r;
       }
       grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, epoch, lane, warp);
+      if (world) world_allreduce_sum<1>(v2, p, wepoch, status, lane, warp);
       const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
@@ -138,6 +214,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       if (valid) v[0] += (double)r * (double)r;
     }
     grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
+    if (world) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
     const float er = (float)sqrt(v[0] / n_elem);
     bool accept = er <= 1.f;
     if (dt > p.o.max_step) accept = false;
@@ -204,6 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     p.log->n_accepted = n_acc;
     p.log->nfe = nfe;
     p.log->t_final = t0;
+    if (world) *p.w_launch_ctr = wepoch;
   }
 }
 
@@ -464,9 +542,14 @@ static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
 int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
                      const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
                      float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
-                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st) {
+                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st,
+                     const GodeWorld* world) {
   if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
   Dp5Args a{};
+  if (world) {
+    a.w_rank = world->rank; a.w_world = world->world; a.w_total_B = world->total_B;
+    a.w_slots = reinterpret_cast<unsigned long long* const*>(world->slots_dev); a.w_launch_ctr = world->launch_ctr;
+  }
   a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.log = log;
   a.att_t0 = att_t0; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
   a.ckpt = ckpt; a.acc_t0 = acc_t0; a.acc_dt = acc_dt;

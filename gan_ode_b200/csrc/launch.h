@@ -60,7 +60,8 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H);
 int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
                      const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
                      float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
-                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st);
+                     float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st,
+                     const GodeWorld* world = nullptr);
 // dopri5_adj_small.cu — torchdiffeq's continuous adjoint with the adaptive solver
 size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H);
 int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,

@@ -91,3 +91,48 @@ def enable_p2p_allreduce(group=None, cap: int = 65536) -> bool:
         sys.stderr.write("[gan_ode_b200] peer-memory all-reduce unavailable ({}); using NCCL\n".format(str(e)[:200]))
         _api.config.grad_allreduce = True if group is None else group
         return False
+
+
+class WorldNorm:
+    """Exchange buffers for dopri5 with a world-scope error norm (gode_dopri5_fwd_world): every rank's step controller
+    sees the RMS norm over the trajectories of all ranks, the partial sums travel as tagged words over NVLink peer memory
+    inside the solver kernel.  torch's symmetric memory provides the peer mapping only."""
+
+    def __init__(self, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 32:
+            raise RuntimeError("world-scope norm supports up to 32 ranks")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        words = 2 * 4 * self.world                      # include/gode.h GODE_WORLD_SLOT_WORDS
+        self.buf = symm_mem.empty(2 * words, dtype=torch.int32, device=dev)   # uint64 words as pairs of int32
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._totals = {}
+        torch.cuda.synchronize()
+        self.hdl.barrier()
+
+    def total_batch(self, B: int) -> int:
+        """Trajectories over all ranks when this rank holds B (one small all-reduce per distinct B, cached)."""
+        v = self._totals.get(B)
+        if v is None:
+            t = torch.tensor([B], dtype=torch.int64, device=self.buf.device)
+            dist.all_reduce(t, group=self.group)
+            v = self._totals[B] = int(t.item())
+        return v
+
+    def struct(self, B: int):
+        from . import _lib
+        w = _lib.GodeWorld()
+        w.rank, w.world, w.total_B = self.rank, self.world, self.total_batch(B)
+        w.slots_dev, w.launch_ctr = self.hdl.buffer_ptrs_dev, self.counter.data_ptr()
+        return w
+
+
+def enable_world_norm(group=None) -> "WorldNorm":
+    """Make options={'norm': 'world'} available to odeint / odeint_adjoint(method='dopri5') on this process group."""
+    _api.config.world_norm = WorldNorm(group)
+    return _api.config.world_norm

@@ -50,6 +50,8 @@ class _Config:
     grad_allreduce = None
     # odeint_adjoint + dopri5: 'continuous' = torchdiffeq's adjoint re-solve; 'discrete' = gradient of the recorded steps
     dopri5_adjoint = "continuous"
+    # options={'norm': 'world'}: set by gan_ode_b200.dist.enable_world_norm() (exchange buffers in NVLink peer memory)
+    world_norm = None
 
 
 config = _Config()
@@ -426,6 +428,8 @@ def raise_for_status(status: int):
         raise AssertionError("underflow in dt")
     if status & _lib.ST_MAX_STEPS:
         raise AssertionError("max_num_steps exceeded")
+    if status & _lib.ST_PEER_TIMEOUT:
+        raise GodeError("world-scope norm: a peer rank did not publish its partial sum within 10 s")
     if status & _lib.ST_CKPT_OVERFLOW:
         raise GodeError("more accepted steps than options['ckpt_capacity']; raise gan_ode_b200.config.ckpt_capacity")
 
@@ -461,11 +465,15 @@ class _Dopri5(torch.autograd.Function):
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         tarr = meta["t64"]
-        _lib.check(L.gode_dopri5_fwd(
-            _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
-            meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
-            _ptr(ckpt), _ptr(acc), (acc.data_ptr() + 8 * max(kc, 1)) if keep else None, _ptr(ws), ws_bytes, _stream()),
-            "gode_dopri5_fwd")
+        args = (_ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
+                meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
+                _ptr(ckpt), _ptr(acc), (acc.data_ptr() + 8 * max(kc, 1)) if keep else None, _ptr(ws), ws_bytes)
+        wn = meta.get("world")
+        if wn is not None:   # error norm over the trajectories of all ranks, exchanged inside the kernel over peer memory
+            wstruct = wn.struct(B)
+            _lib.check(L.gode_dopri5_fwd_world(*args, C.byref(wstruct), _stream()), "gode_dopri5_fwd_world")
+        else:
+            _lib.check(L.gode_dopri5_fwd(*args, _stream()), "gode_dopri5_fwd")
         log = StepLog(raw, cap)
         _LAST_LOG[0] = log
         if meta["check"]:
@@ -695,9 +703,10 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
     o.max_step = float(options.get("max_step", float("inf")))
     o.max_num_steps = int(min(options.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
     norm = options.get("norm", None)
-    if norm is not None and norm not in ("batch", "rms", "trajectory", "per_trajectory"):
+    if norm is not None and norm not in ("batch", "rms", "trajectory", "per_trajectory", "world"):
         raise NotImplementedError("custom error norms are not supported by the fused dopri5 kernels: 'batch' (torchdiffeq's "
-                                  "batch-global RMS, default) or 'trajectory' (per-trajectory step control)")
+                                  "batch-global RMS, default), 'world' (the same over all data-parallel ranks) or "
+                                  "'trajectory' (per-trajectory step control)")
     o.norm_scope = _lib.NORM_TRAJ if norm in ("trajectory", "per_trajectory") else _lib.NORM_BATCH
     o.log_capacity = int(options.get("log_capacity", config.log_capacity))
     o.ckpt_capacity = int(options.get("ckpt_capacity", config.ckpt_capacity))
@@ -771,6 +780,13 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
         mode = options.get("adjoint", config.dopri5_adjoint)
         if mode not in ("continuous", "discrete"):
             raise ValueError("options['adjoint'] must be 'continuous' or 'discrete'")
+        if options.get("norm") == "world":
+            if config.world_norm is None:
+                raise GodeError("options['norm']='world' needs gan_ode_b200.dist.enable_world_norm() on every rank first")
+            if adjoint and mode == "continuous":
+                raise NotImplementedError("the world-scope norm exists for the forward solve and its recorded-step gradient: "
+                                          "use odeint, or odeint_adjoint with options['adjoint']='discrete'")
+            meta["world"] = config.world_norm
         if adjoint and mode == "continuous" and meta["keep_ckpt"]:
             a_rtol, a_atol, a_options = adj if adj is not None else (None, None, None)
             if a_options is None:   # adjoint.py: the forward options without its norm

@@ -72,7 +72,8 @@ enum {
   GODE_ST_DT_UNDERFLOW = 1, /* torchdiffeq: assert t0 + dt > t0, 'underflow in dt'         */
   GODE_ST_NONFINITE = 2,    /* torchdiffeq: assert isfinite(y0), 'non-finite values in state' */
   GODE_ST_MAX_STEPS = 4,    /* torchdiffeq: 'max_num_steps exceeded'                       */
-  GODE_ST_CKPT_OVERFLOW = 8 /* more accepted steps than checkpoint / log capacity          */
+  GODE_ST_CKPT_OVERFLOW = 8, /* more accepted steps than checkpoint / log capacity         */
+  GODE_ST_PEER_TIMEOUT = 16 /* world-scope norm: a peer rank did not publish within 10 s   */
 };
 
 #define GODE_MAX_HOST_STEPS 255
@@ -153,6 +154,32 @@ int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const flo
                     int out_layout, float* traj, GodeStepLog* log, double* att_t0, double* att_dt,
                     float* att_er, uint8_t* att_acc, float* ckpt, double* acc_t0, double* acc_dt,
                     void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* ---- e (optional): dopri5 with a WORLD-scope error norm ---------------------------------------------------------- */
+/* Data-parallel ranks each hold a shard of the batch; with this entry point the step controller sees the RMS norm over
+ * the trajectories of ALL ranks, so N ranks take the (t, dt) sequence one process would take on the whole batch
+ * (torchdiffeq's batch-global norm).  The exchange is fused into the solver kernel: after the grid-wide
+ * reduction of an attempt, CTA 0 stores this rank's partial as one tagged 64-bit word {fp32 | tag} into slot [rank] of
+ * EVERY peer's exchange buffer over NVLink peer memory, and warp 0 of every CTA polls its own GPU's buffer until the
+ * `world` words of this epoch are there, then adds them in rank order (identical on every rank).  No NCCL call, no host
+ * round trip; parity double-buffering as in the intra-grid reduction.
+ * slots_dev: device array[world] of device pointers, entry r = rank r's exchange buffer (GODE_WORLD_SLOT_WORDS(world)
+ * uint64 words, zero-initialised once, mapped into this process: symmetric memory); launch_ctr: device word in local
+ * memory, zero-initialised once, holding the cumulative count of exchanges (advanced by the kernel: tags stay unique
+ * under CUDA-graph replay).  Every rank must
+ * launch the same sequence of world-scope solves.  total_B: trajectories over all ranks. */
+#define GODE_WORLD_SLOT_WORDS(world) (2 * 4 * (world))
+typedef struct GodeWorld {
+  int32_t rank, world;
+  int64_t total_B;
+  void* const* slots_dev;
+  uint32_t* launch_ctr;
+} GodeWorld;
+int gode_dopri5_fwd_world(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts,
+                          int out_layout, float* traj, GodeStepLog* log, double* att_t0, double* att_dt,
+                          float* att_er, uint8_t* att_acc, float* ckpt, double* acc_t0, double* acc_dt,
+                          void* workspace, size_t ws_bytes, const GodeWorld* world, gode_stream_t stream);
 
 /* ---- A.5: dopri5 backprop-through-solver ------------------------------------------------------ */
 /* Replays the accepted steps recorded by gode_dopri5_fwd in reverse (dt sequence treated as data),

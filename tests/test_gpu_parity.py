@@ -1128,3 +1128,14 @@ def test_single_layer_tanh_field(method, adjoint):
     assert rel_err(out_sol, ref_sol) <= (TOL if method == "rk4" else 2e-5)
     for a, b in zip(out, ref):
         assert rel_err(a, b) <= (2e-5 if method == "rk4" else 1e-4), rel_err(a, b)
+
+
+def test_world_norm_needs_its_exchange_buffers():
+    _need_gpu()
+    f = clone_to(make_field(), DEV)
+    y0 = torch.randn(8, 16, device=DEV)
+    if gode.config.world_norm is None:
+        with pytest.raises(gode.GodeError, match="enable_world_norm"):
+            gode.odeint(f, y0, _t16(), method="dopri5", options={"norm": "world"})
+    with pytest.raises(NotImplementedError):
+        gode.odeint(f, y0, _t16(), method="dopri5", options={"norm": "max"})
