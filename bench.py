@@ -255,10 +255,14 @@ def run_gpu(args):
         os.dup2(2, 1)
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
-        from gan_ode_b200.dist import enable_p2p_allreduce
-        p2p = False if args.nccl_allreduce else enable_p2p_allreduce()
-        if not p2p:
-            gode.config.grad_allreduce = True
+        from gan_ode_b200.dist import enable_fused_grad_exchange, enable_p2p_allreduce
+        # parameter-gradient exchange, in order of preference: fused into the backward kernel's reduction tail over NVLink
+        # peer memory; one-shot peer-memory kernel behind the backward; ncclAllReduce
+        fused = args.grad_exchange == "fused" and enable_fused_grad_exchange()
+        if not fused:
+            p2p = args.grad_exchange != "nccl" and enable_p2p_allreduce()
+            if not p2p:
+                gode.config.grad_allreduce = True
     n_gpus = world
 
     f, y0, grad, t = make_inputs(seed=rank, device=dev)
@@ -394,8 +398,8 @@ def run_gpu(args):
     if rank == 0:
         k = max(10, min(args.steps, 50))
         ef = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)]
-        prev = gode.config.grad_allreduce
-        gode.config.grad_allreduce = None
+        prev, prev_x = gode.config.grad_allreduce, gode.config.grad_exchange   # rank 0 alone: no exchange in here
+        gode.config.grad_allreduce = gode.config.grad_exchange = None
         for e0, e1, e2 in ef:
             flush.fill_(1)
             torch.cuda._sleep(400000)  # keep the GPU busy while the host enqueues, so events bracket kernels only
@@ -405,7 +409,7 @@ def run_gpu(args):
             torch.autograd.grad(sol, [y0r] + params, grad)
             e2.record()
         torch.cuda.synchronize()
-        gode.config.grad_allreduce = prev
+        gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
         fwd_us = sorted(e0.elapsed_time(e1) for e0, e1, _ in ef)[k // 2] * 1e3
         bwd_us = sorted(e1.elapsed_time(e2) for _, e1, e2 in ef)[k // 2] * 1e3
         row = B_PER_GPU * D * 4
@@ -471,12 +475,15 @@ def run_gpu(args):
                                             attempted_steps=n_att, accepted_steps=n_acc,
                                             parallelism="dp{}".format(n_gpus),
                                             grad_allreduce=("none (1 GPU)" if n_gpus == 1 else
-                                                            "fused one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
+                                                            "fused into the backward kernel's reduction tail over NVLink peer memory "
+                                                            "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
+                                                            "one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
                                                             if callable(gode.config.grad_allreduce) else "ncclAllReduce")),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
                 "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
-        "gpu_launches": (2 + (1 if n_gpus > 1 and callable(gode.config.grad_allreduce) else 0)) * args.steps,
+        "gpu_launches": (2 + (1 if n_gpus > 1 and gode.config.grad_exchange is None and callable(gode.config.grad_allreduce)
+                              else 0)) * args.steps,
         "eager_ms_per_step": eager_ms / args.steps,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
     }
@@ -493,10 +500,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--grad-exchange", choices=("fused", "p2p", "nccl"), default="fused",
+                    help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "
                     "of the fused peer-memory kernel")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch / wide-field side measurements")
     args = ap.parse_args()
+    if args.nccl_allreduce:
+        args.grad_exchange = "nccl"
     if args.impl == "reference":
         run_reference(args)
         return

@@ -160,6 +160,23 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_dopri5_backprop_bwd_world(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                                   const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                                   int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                                   size_t ws_bytes, const GodeWorld* exchange, gode_stream_t stream) {
+  if (bad_common(grad_traj, W1, b1, W2, b2, B, T, layout) || !t_host || !log || !ckpt || !acc_t0 || !acc_dt ||
+      ckpt_capacity <= 0 || !grad_y0 || !grad_params || !workspace || !exchange)
+    return GODE_ERR_ARG;
+  if (exchange->world < 1 || exchange->world > 64 || exchange->rank < 0 || exchange->rank >= exchange->world ||
+      !exchange->slots_dev || !exchange->launch_ctr)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_small_backprop_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, ckpt, acc_t0, acc_dt,
+                                   ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream,
+                                   exchange);
+}
+
 size_t gode_dopri5_adjoint_workspace_bytes(int B, int D, int H) { return dopri5_small_adjoint_workspace_bytes(B, D, H); }
 
 int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,

@@ -579,9 +579,13 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
                               const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
-                              size_t ws_bytes, cudaStream_t st) {
+                              size_t ws_bytes, cudaStream_t st, const GodeWorld* xchg) {
   if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
   Dp5Args a{};
+  if (xchg) {
+    a.ws.w_rank = xchg->rank; a.ws.w_world = xchg->world; a.ws.w_ctr = xchg->launch_ctr;
+    a.ws.w_slots = reinterpret_cast<unsigned long long* const*>(xchg->slots_dev);
+  }
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.grad_traj = grad_traj; a.log = const_cast<GodeStepLog*>(log);
   a.ckpt = const_cast<float*>(ckpt); a.acc_t0 = const_cast<double*>(acc_t0); a.acc_dt = const_cast<double*>(acc_dt);
   a.o.ckpt_capacity = ckpt_capacity; a.o.fsign = fsign; a.grad_y0 = grad_y0; a.grad_params = grad_params;

@@ -283,7 +283,26 @@ __device__ __forceinline__ void regather(const BwdLines<D, H, L>& ln, int l, con
 struct ReduceWs {
   GridSyncWs gs;    // zeroed by the host wrapper before launch
   float* partials;  // [gridDim.x][P]
+  // data-parallel exchange fused into the tail of the reduction (w_world > 1, see reduce_param_grads): every rank's
+  // buffer [2 parities][w_world][P] of tagged 64-bit words, peer-mapped; w_ctr: cumulative launch count in device memory
+  int w_rank, w_world;
+  unsigned long long* const* w_slots;
+  unsigned int* w_ctr;
 };
+
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 template <int D, int H, int L, int WARPS>
 __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float* smem_red /* [WARPS][P] */,
@@ -331,8 +350,11 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
     for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
     __stcg(mine + p, s);
   }
+  const bool xchg = ws.w_world > 1;
+  const unsigned int wtag = xchg ? *reinterpret_cast<volatile unsigned int*>(ws.w_ctr) + 1u : 0u;  // read before the barrier
   unsigned int epoch = 0;
   grid_barrier(ws.gs, epoch);
+  if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;  // every thread of the grid has read it
   // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
   // in order, then a shuffle tree.  No block-level synchronisation.
   const int nb = gridDim.x;
@@ -348,6 +370,33 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
     for (int off = 16; off >= 1; off >>= 1) {
       s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
       s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+    }
+    if (xchg) {
+      const int W = ws.w_world, par = (int)(wtag & 1u), j = lane & 3;
+      const float mine = j == 0 ? s.x : j == 1 ? s.y : j == 2 ? s.z : s.w;
+      const unsigned long long word = (unsigned long long)__float_as_uint(mine) | ((unsigned long long)wtag << 32);
+      for (int r = lane >> 2; r < W; r += 8)
+        st_sys_u64(ws.w_slots[r] + ((size_t)(par * W + ws.w_rank) * P + 4 * p4 + j), word);
+      const unsigned long long* home = ws.w_slots[ws.w_rank] + (size_t)par * W * P + 4 * p4 + j;
+      const unsigned long long t_start = global_timer_ns();
+      float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r0 = 0; r0 < W; r0 += 8) {
+        const int r = r0 + (lane >> 2);
+        float val = 0.f;
+        if (r < W) {
+          unsigned long long x = ld_sys_u64(home + (size_t)r * P);
+          while ((unsigned int)(x >> 32) != wtag) {
+            if (global_timer_ns() - t_start > 10000000000ull) { x = 0x7fc00000ull; break; }  // dead peer: NaN, not a hang
+            x = ld_sys_u64(home + (size_t)r * P);
+          }
+          val = __uint_as_float((unsigned int)x);
+        }
+        for (int rr = 0; rr < 8 && r0 + rr < W; ++rr) {  // rank order
+          tot.x += __shfl_sync(0xffffffffu, val, rr * 4 + 0); tot.y += __shfl_sync(0xffffffffu, val, rr * 4 + 1);
+          tot.z += __shfl_sync(0xffffffffu, val, rr * 4 + 2); tot.w += __shfl_sync(0xffffffffu, val, rr * 4 + 3);
+        }
+      }
+      s = tot;
     }
     if (lane == 0) reinterpret_cast<float4*>(grad_params)[p4] = s;
   }

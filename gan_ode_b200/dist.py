@@ -136,3 +136,49 @@ def enable_world_norm(group=None) -> "WorldNorm":
     """Make options={'norm': 'world'} available to odeint / odeint_adjoint(method='dopri5') on this process group."""
     _api.config.world_norm = WorldNorm(group)
     return _api.config.world_norm
+
+
+class FusedGradExchange:
+    """Exchange buffers for the parameter-gradient all-reduce fused into the backward kernel's reduction tail
+    (gode_dopri5_backprop_bwd_world): tagged words over NVLink peer memory, no separate all-reduce launch."""
+
+    def __init__(self, group=None, max_params: int = 1088):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = dist.group.WORLD if group is None else group
+        self.world, self.rank, self.max_params = dist.get_world_size(group), dist.get_rank(group), int(max_params)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self._bufs = {}
+        self._symm, self._group, self._dev = symm_mem, group, dev
+
+    def struct(self, P: int):
+        """GodeWorld for a gradient of P floats (one buffer + launch counter per distinct P, created collectively on first
+        use: every rank reaches this call in the same order)."""
+        from . import _lib
+        ent = self._bufs.get(P)
+        if ent is None:
+            buf = self._symm.empty(2 * 2 * self.world * P, dtype=torch.int32, device=self._dev)   # uint64 words
+            buf.zero_()
+            hdl = self._symm.rendezvous(buf, self._group)
+            ctr = torch.zeros(1, dtype=torch.int32, device=self._dev)
+            torch.cuda.synchronize()
+            hdl.barrier()
+            ent = self._bufs[P] = (buf, hdl, ctr)
+        w = _lib.GodeWorld()
+        w.rank, w.world, w.total_B = self.rank, self.world, 0
+        w.slots_dev, w.launch_ctr = ent[1].buffer_ptrs_dev, ent[2].data_ptr()
+        return w
+
+
+def enable_fused_grad_exchange(group=None) -> bool:
+    """dopri5 backprop-through-solver: all-reduce the parameter gradient inside the backward kernel.  Other backward kernels
+    keep using config.grad_allreduce (set it as well).  Returns False if symmetric memory is unavailable."""
+    try:
+        ex = FusedGradExchange(group)
+        ex.struct(544)      # the reference shape: create its buffers now, outside any graph capture
+        _api.config.grad_exchange = ex
+        return True
+    except Exception as e:  # noqa: BLE001
+        import sys
+        sys.stderr.write("[gan_ode_b200] fused gradient exchange unavailable ({})\n".format(str(e)[:200]))
+        _api.config.grad_exchange = None
+        return False

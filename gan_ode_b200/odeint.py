@@ -52,6 +52,8 @@ class _Config:
     dopri5_adjoint = "continuous"
     # options={'norm': 'world'}: set by gan_ode_b200.dist.enable_world_norm() (exchange buffers in NVLink peer memory)
     world_norm = None
+    # dopri5 backprop: parameter-gradient all-reduce fused into the backward kernel (dist.enable_fused_grad_exchange())
+    grad_exchange = None
 
 
 config = _Config()
@@ -236,8 +238,9 @@ def _maybe_allreduce(flat):
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=None if g is True else g)
 
 
-def _split_params(flat, D, H, needs):
-    _maybe_allreduce(flat)
+def _split_params(flat, D, H, needs, reduced=False):
+    if not reduced:
+        _maybe_allreduce(flat)
     n1 = H * D
     outs = (flat[:n1].view(H, D), flat[n1:n1 + H], flat[n1 + H:n1 + H + D * H].view(D, H), flat[n1 + H + D * H:])
     return tuple(o if need else None for o, need in zip(outs, needs))
@@ -501,13 +504,17 @@ class _Dopri5(torch.autograd.Function):
         grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
-        _lib.check(L.gode_dopri5_backprop_bwd(
-            _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
-            meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
-            C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes, _stream()),
-            "gode_dopri5_backprop_bwd")
+        args = (_ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
+                meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
+                C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes)
+        ex = config.grad_exchange
+        if ex is not None:   # the all-reduce over ranks happens inside the kernel's reduction tail (NVLink peer memory)
+            xs = ex.struct(grad_p.numel())
+            _lib.check(L.gode_dopri5_backprop_bwd_world(*args, C.byref(xs), _stream()), "gode_dopri5_backprop_bwd_world")
+        else:
+            _lib.check(L.gode_dopri5_backprop_bwd(*args, _stream()), "gode_dopri5_backprop_bwd")
         needs = ctx.needs_input_grad
-        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6])
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6], reduced=ex is not None)
         return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
 
 

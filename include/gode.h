@@ -190,6 +190,21 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                              const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
                              void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- e: gode_dopri5_backprop_bwd with the data-parallel all-reduce of grad_params fused into its reduction tail ------ */
+/* Same computation; in addition grad_params leaves the kernel summed over all ranks (rank-order sum, bit-identical on every
+ * rank): the warp that finishes a float4 column of the parameter gradient stores it as tagged 64-bit words into every
+ * peer's exchange buffer over NVLink peer memory and gathers the peers' words for that column — no separate all-reduce
+ * launch.  exchange: rank / world; slots_dev[r] = rank r's buffer of GODE_GRAD_SLOT_WORDS(world, gode_param_count(D,H))
+ * uint64 words, zero-initialised once and peer-mapped; launch_ctr: zero-initialised device word in local memory (cumulative
+ * launch count, CUDA-graph replayable); total_B unused.  Every rank must launch the same sequence.  grad_y0 stays local. */
+#define GODE_GRAD_SLOT_WORDS(world, P) (2 * (size_t)(world) * (size_t)(P))
+int gode_dopri5_backprop_bwd_world(const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                                   const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                                   const GodeStepLog* log, const float* ckpt, const double* acc_t0,
+                                   const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0,
+                                   float* grad_params, void* workspace, size_t ws_bytes, const GodeWorld* exchange,
+                                   gode_stream_t stream);
+
 /* ---- a4 with the adaptive solver: torchdiffeq's continuous adjoint, method = adjoint_method = 'dopri5' ------------- */
 /* Replaces OdeintAdjointMethod.backward for the call `odeint(self.ode_fn, h, tensor([0,1]))` of the ODE-RNN sampler
  * (models/mocogan_ode_rnn.py:47-48; `odeint` there is odeint_adjoint, :4).  Per output interval, from the last to the first:

@@ -70,6 +70,36 @@ if rank == 0:
 gode.config.grad_allreduce = None
 
 
+# ---- parameter-gradient all-reduce fused into the backward kernel (gode_dopri5_backprop_bwd_world) vs ncclAllReduce -------
+def grads_with(mode):
+    gode.config.grad_allreduce = True if mode == "nccl" else None
+    gode.config.grad_exchange = fused_ex if mode == "fused" else None
+    outs = []
+    for rep in range(3):
+        yy = y_full[lo:hi].clone().requires_grad_(True)
+        so = gode.odeint(f, yy, t, method="dopri5", rtol=1e-5, atol=1e-5)
+        outs.append(torch.autograd.grad((so * g_full[:, lo:hi]).sum(), [yy] + list(f.parameters())))
+    torch.cuda.synchronize()
+    gode.config.grad_allreduce = gode.config.grad_exchange = None
+    return outs
+
+
+assert gdist.enable_fused_grad_exchange()
+fused_ex = gode.config.grad_exchange
+gode.config.grad_exchange = None
+g_nccl, g_fused = grads_with("nccl"), grads_with("fused")
+flat = torch.cat([x.reshape(-1) for x in g_fused[-1][1:]])
+gathered_g = [torch.empty_like(flat) for _ in range(world)]
+dist.all_gather(gathered_g, flat)
+if rank == 0:
+    fe = dict(vs_nccl=max(rel_err(a, b) for a, b in zip(g_fused[-1][1:], g_nccl[-1][1:])),
+              repeatable=all(torch.equal(a, b) for a, b in zip(g_fused[0][1:], g_fused[-1][1:])),
+              identical_on_all_ranks=all(torch.equal(x, gathered_g[0]) for x in gathered_g),
+              grad_y0_local=bool(torch.equal(g_fused[-1][0], g_nccl[-1][0])))
+    res["fused_grad_exchange"] = fe
+    res["ok"] = ok = bool(ok and fe["vs_nccl"] < 1e-5 and fe["repeatable"] and fe["identical_on_all_ranks"] and fe["grad_y0_local"])
+
+
 def timed(opts, Bt=4096, n=20):
     yt = torch.randn(Bt, 16, device=dev)
     with torch.no_grad():
@@ -91,6 +121,9 @@ tl, nl = timed({})
 if rank == 0:
     res["fwd_us_B4096_per_rank"] = dict(world_norm=round(tw, 1), attempts_world=na, per_rank_norm=round(tl, 1), attempts_local=nl)
     os.write(out_fd, (json.dumps(res) + "\n").encode())
+okt = torch.tensor([1 if ok else 0], device=dev)
+dist.broadcast(okt, 0)
+ok = bool(okt.item())
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
