@@ -232,6 +232,22 @@ def measure_extras(gode, dev):
         "trajectory_steps_per_s": B4 * 15 / (sec_f + sec_b), "fwd_ms": sec_f * 1e3, "bwd_ms": sec_b * 1e3, "tflops": tfl,
         "frac_of_measured_bf16_gemm": tfl / bf16}
     del yw, gw, solw
+    # configs[2]: the ODE-RNN sampler, 16 frames of [dopri5 solve over [0,1] at torchdiffeq's default tolerances -> GRU jump],
+    # B = 8192: one fused call per direction (gradient of the recorded steps) and the same with torchdiffeq's continuous
+    # adjoint re-solve per frame (what the reference loop computes; also what it gets through the import shim)
+    rnn = torch.nn.GRUCell(16, 16).to(dev)
+    Br, Fr = 8192, 16
+    h0 = torch.randn(Br, 16, device=dev, requires_grad=True)
+    eps = torch.randn(Fr, Br, 16, device=dev)
+    wgt = torch.randn(Fr, Br, 16, device=dev)
+    for mode in ("discrete", "continuous"):
+        def rnn_step():
+            codes = gode.odernn_codes(f16, rnn, h0, eps, options={"adjoint": mode})
+            torch.autograd.grad((codes * wgt).sum(), [h0] + list(f16.parameters()) + list(rnn.parameters()))
+        sec = timeit(rnn_step)
+        att = sum(fr["n_attempts"] for fr in gode.odernn.last_log().frames())
+        out["odernn_fwd_bwd_B8192_F16_%s_adjoint" % mode] = {"ms": sec * 1e3, "attempted_steps_fwd": att,
+                                                             "trajectory_steps_per_s": Br * att / sec}
     return out
 
 

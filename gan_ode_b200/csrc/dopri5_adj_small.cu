@@ -660,8 +660,12 @@ int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const fl
   int rc = first8 ? launch_adj<8, 2>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
   if (rc != GODE_ERR_COOP) return rc;
   rc = launch_adj<4, 1>(a, workspace, ws_bytes, st);
-  if (rc != GODE_ERR_COOP || first8) return rc;
-  return launch_adj<8, 2>(a, workspace, ws_bytes, st);
+  if (rc != GODE_ERR_COOP) return rc;
+  if (!first8) {
+    rc = launch_adj<8, 2>(a, workspace, ws_bytes, st);
+    if (rc != GODE_ERR_COOP) return rc;
+  }
+  return launch_adj<2, 1>(a, workspace, ws_bytes, st);  // 128 trajectories per CTA: holds 18 944
 }
 
 }  // namespace gode

@@ -585,7 +585,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
             meta["layout"], C.byref(ao), meta["param_mask"], _ptr(grad_y0), _ptr(grad_p), base, base + 64 + 8 * cap, base + 64 + 16 * cap,
             base + 64 + 20 * cap, _ptr(ws), ws_bytes, _stream())
         if rc == _lib.ERR_COOP:
-            raise GodeError("the continuous dopri5 adjoint keeps the whole batch co-resident (at most 9472 trajectories per "
+            raise GodeError("the continuous dopri5 adjoint keeps the whole batch co-resident (at most 18944 trajectories per "
                             "GPU); shard the batch, or pass options={'adjoint': 'discrete'} for the gradient of the recorded "
                             "steps (gode_dopri5_backprop_bwd)")
         _lib.check(rc, "gode_dopri5_adjoint_bwd")

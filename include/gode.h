@@ -216,7 +216,7 @@ int gode_dopri5_backprop_bwd_world(const float* grad_traj, const float* W1, cons
  * first_step, safety, ifactor, dfactor, min/max_step, max_num_steps, log_capacity for the optional att_* arrays, which
  * hold the attempts of all intervals back to back; NULL = no log).  log (optional): status / attempts / accepted / nfe
  * summed over the intervals, dt0 of the last one.  param_mask: bit k set = parameter tensor k (W1, b1, W2, b2) is an adjoint
- * parameter (adjoint.py keeps those with requires_grad) and enters the norm; 15 = all.  One cooperative launch: the batch must be co-resident (<= 9472
+ * parameter (adjoint.py keeps those with requires_grad) and enters the norm; 15 = all.  One cooperative launch: the batch must be co-resident (<= 18944
  * trajectories; GODE_ERR_COOP beyond).  workspace: gode_dopri5_adjoint_workspace_bytes(B,D,H) bytes.  Deterministic. */
 size_t gode_dopri5_adjoint_workspace_bytes(int B, int D, int H);
 int gode_dopri5_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,

@@ -598,15 +598,21 @@ def test_dopri5_continuous_adjoint_own_tolerances_and_limits():
     # (B,T,D) layout and a device-resident t
     _, out_btd = run(gode.odeint_adjoint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"layout": "btd"}, _t_on_dev=True, **kw)
     assert all(torch.equal(a, b) for a, b in zip(out, out_btd))
-    # the whole batch must be co-resident: beyond that the error names the alternative
+    # the whole batch must be co-resident: 8 lanes per trajectory up to 4736, then 4 lanes (9472), then 2 lanes (18 944);
+    # beyond that the error names the alternative
     fg = clone_to(f, DEV)
     yb = torch.randn(12000, 16, device=DEV, requires_grad=True)
     sol = gode.odeint_adjoint(fg, yb, t, rtol=1e-4, atol=1e-4)
+    gc = torch.autograd.grad(sol.sum(), [yb] + list(fg.parameters()))
+    assert gode.last_adjoint_log().status == 0
+    sol = gode.odeint_adjoint(fg, yb, t, rtol=1e-4, atol=1e-4, options={"adjoint": "discrete"})
+    gd = torch.autograd.grad(sol.sum(), [yb] + list(fg.parameters()))
+    for a, b in zip(gc, gd):
+        assert rel_err(a, b) <= 5e-3, rel_err(a, b)      # two gradients of a solve at tolerance 1e-4
+    yb = torch.randn(20000, 16, device=DEV, requires_grad=True)
+    sol = gode.odeint_adjoint(fg, yb, t, rtol=1e-4, atol=1e-4)
     with pytest.raises(gode.GodeError, match="discrete"):
         sol.sum().backward()
-    sol = gode.odeint_adjoint(fg, yb, t, rtol=1e-4, atol=1e-4, options={"adjoint": "discrete"})
-    sol.sum().backward()
-    assert torch.isfinite(yb.grad).all()
 
 
 # ---- neural SDE: Euler–Maruyama + Philox (a7) -------------------------------------------------------------------------------
