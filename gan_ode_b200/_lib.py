@@ -57,6 +57,7 @@ _SIGS = {
     "gode_dopri5_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 + [C.c_size_t, _P]),
     "gode_dopri5_fwd_world": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 +
                               [C.c_size_t, C.POINTER(GodeWorld), _P]),
+    "gode_rk4_bwd_world": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, C.POINTER(GodeWorld), _P]),
     "gode_dopri5_backprop_bwd_world": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P, C.c_size_t,
                                             C.POINTER(GodeWorld), _P]),
     "gode_dopri5_adjoint_workspace_bytes": (C.c_size_t, [_I, _I, _I]),

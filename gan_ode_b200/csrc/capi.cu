@@ -105,6 +105,21 @@ int gode_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float
                         grad_y0, grad_params, workspace, ws_bytes, stream);
 }
 
+int gode_rk4_bwd_world(int adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                       const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                       int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                       const GodeWorld* exchange, gode_stream_t stream) {
+  if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !dt || !grad_y0 || !grad_params || !workspace ||
+      !exchange)
+    return GODE_ERR_ARG;
+  if (exchange->world < 1 || exchange->world > 64 || exchange->rank < 0 || exchange->rank >= exchange->world ||
+      !exchange->slots_dev || !exchange->launch_ctr)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_bwd(adjoint != 0, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
+                       grad_params, workspace, ws_bytes, (cudaStream_t)stream, GODE_METHOD_RK4, exchange);
+}
+
 size_t gode_dopri5_workspace_bytes(int B, int D, int H) {
   const size_t a = dopri5_small_workspace_bytes(B, D, H), b = bwd_workspace_bytes(gode_param_count(D, H));
   return a > b ? a : b;

@@ -54,7 +54,7 @@ int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method = GODE_METHOD_RK4);
+                  int method = GODE_METHOD_RK4, const GodeWorld* xchg = nullptr);
 
 size_t dopri5_small_workspace_bytes(int B, int D, int H);
 int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,

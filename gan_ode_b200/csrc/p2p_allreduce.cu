@@ -12,6 +12,7 @@
 // Parity double-buffering: a rank can be at most one epoch ahead of a peer (it needs the peer's flag of epoch e to finish
 // e, and the peer raises the flag of e+1 only after its own epoch-e kernel has retired), so epoch e+1 never overwrites
 // slots an epoch-e reader still needs.  The epoch counter lives in device memory, so the launch is CUDA-graph replayable.
+// A peer that does not raise its flag within 10 s turns the result into NaN instead of a hung GPU.
 #include "launch.h"
 
 namespace gode {
@@ -45,12 +46,26 @@ __global__ void __launch_bounds__(512) p2p_allreduce_kernel(float* __restrict__ 
   }
   __threadfence_system();
   __syncthreads();
+  __shared__ int s_dead;
+  if (tid == 0) s_dead = 0;
+  __syncthreads();
   if (tid < world) {
     st_release_sys(pads[tid] + par * world + rank, e);
     const unsigned int* mine = pads[rank] + par * world + tid;
-    while (ld_acquire_sys(mine) != e) { }
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (ld_acquire_sys(mine) != e) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 10000000000ull) { s_dead = 1; break; }  // a peer that never arrives: NaN out, do not hang the GPU
+    }
   }
   __syncthreads();
+  if (s_dead) {
+    for (int i = tid; i < n; i += blockDim.x) data[i] = __int_as_float(0x7fc00000);
+    if (tid == 0) *epoch_ctr = e;
+    return;
+  }
   const float* base = bufs[rank] + (size_t)par * world * (size_t)cap;
   for (int i = tid; i < n; i += blockDim.x) {
     float s = 0.f;

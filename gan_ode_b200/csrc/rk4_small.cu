@@ -374,8 +374,12 @@ int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method) {
+                  int method, const GodeWorld* xchg) {
   Rk4Args a{};
+  if (xchg) {  // all-reduce over ranks fused into the reduction tail (small_field.cuh::reduce_param_grads)
+    a.ws.w_rank = xchg->rank; a.ws.w_world = xchg->world; a.ws.w_ctr = xchg->launch_ctr;
+    a.ws.w_slots = reinterpret_cast<unsigned long long* const*>(xchg->slots_dev);
+  }
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj_in = traj; a.grad_traj = grad_traj; a.grad_y0 = grad_y0;
   a.grad_params = grad_params; a.B = B; a.T = T; a.layout = layout;
   if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;

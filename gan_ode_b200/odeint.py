@@ -304,7 +304,14 @@ class _Rk4(torch.autograd.Function):
                 bwd_prec = _lib.PREC["bf16"]
             elif (D, H) == (16, 16) and want == "bf16":            # opt-in for the reference shape (tc_rk4_adj_small.cu)
                 bwd_prec = _lib.PREC["bf16"]
-        if meta.get("method", 0):
+        ex = config.grad_exchange
+        fused = (ex is not None and not meta.get("method", 0) and bwd_prec == _lib.PREC["fp32"] and (D, H) == (16, 16))
+        if fused:    # all-reduce over ranks inside the kernel's reduction tail (NVLink peer memory)
+            xs = ex.struct(n_param)
+            rc = L.gode_rk4_bwd_world(1 if meta["adjoint"] else 0, buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(),
+                                      W2c.data_ptr(), b2c.data_ptr(), dt_ptr, dt_dev, B, D, H, T, meta["layout"],
+                                      grad_y0.data_ptr(), grad_p.data_ptr(), ws.data_ptr(), ws_bytes, C.byref(xs), _stream())
+        elif meta.get("method", 0):
             fn = L.gode_fixed_adjoint_bwd if meta["adjoint"] else L.gode_fixed_backprop_bwd
             rc = fn(meta["method"], buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(),
                     b2c.data_ptr(), dt_ptr, dt_dev, B, D, H, T, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
@@ -316,7 +323,7 @@ class _Rk4(torch.autograd.Function):
         if rc:
             _lib.check(rc, "gode_rk4_bwd")
         needs = ctx.needs_input_grad
-        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[3:7])
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[3:7], reduced=fused)
         return (grad_y0 if needs[0] else None), None, None, gW1, gb1, gW2, gb2
 
 

@@ -205,6 +205,13 @@ int gode_dopri5_backprop_bwd_world(const float* grad_traj, const float* W1, cons
                                    float* grad_params, void* workspace, size_t ws_bytes, const GodeWorld* exchange,
                                    gode_stream_t stream);
 
+/* The same fused exchange for the FP32 rk4 backward kernels of the reference shape (D = H = 16): gode_rk4_adjoint_bwd
+ * (adjoint != 0) or gode_rk4_backprop_bwd (adjoint == 0) with grad_params summed over all ranks inside the kernel. */
+int gode_rk4_bwd_world(int adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                       const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                       int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                       const GodeWorld* exchange, gode_stream_t stream);
+
 /* ---- a4 with the adaptive solver: torchdiffeq's continuous adjoint, method = adjoint_method = 'dopri5' ------------- */
 /* Replaces OdeintAdjointMethod.backward for the call `odeint(self.ode_fn, h, tensor([0,1]))` of the ODE-RNN sampler
  * (models/mocogan_ode_rnn.py:47-48; `odeint` there is odeint_adjoint, :4).  Per output interval, from the last to the first:

@@ -71,13 +71,18 @@ gode.config.grad_allreduce = None
 
 
 # ---- parameter-gradient all-reduce fused into the backward kernel (gode_dopri5_backprop_bwd_world) vs ncclAllReduce -------
-def grads_with(mode):
-    gode.config.grad_allreduce = True if mode == "nccl" else None
+def grads_with(mode, solver="dopri5"):
+    gode.config.grad_allreduce = True if mode == "nccl" else (p2p if mode == "p2p" else None)
     gode.config.grad_exchange = fused_ex if mode == "fused" else None
     outs = []
     for rep in range(3):
         yy = y_full[lo:hi].clone().requires_grad_(True)
-        so = gode.odeint(f, yy, t, method="dopri5", rtol=1e-5, atol=1e-5)
+        if solver == "dopri5":
+            so = gode.odeint(f, yy, t, method="dopri5", rtol=1e-5, atol=1e-5)
+        elif solver == "rk4_adjoint":
+            so = gode.odeint_adjoint(f, yy, t, method="rk4")
+        else:
+            so = gode.odeint(f, yy, t, method="rk4")
         outs.append(torch.autograd.grad((so * g_full[:, lo:hi]).sum(), [yy] + list(f.parameters())))
     torch.cuda.synchronize()
     gode.config.grad_allreduce = gode.config.grad_exchange = None
@@ -87,6 +92,15 @@ def grads_with(mode):
 assert gdist.enable_fused_grad_exchange()
 fused_ex = gode.config.grad_exchange
 gode.config.grad_exchange = None
+assert gdist.enable_p2p_allreduce()
+p2p = gode.config.grad_allreduce
+gode.config.grad_allreduce = None
+rk4_err = {}
+for solver in ("rk4_adjoint", "rk4_backprop"):
+    a_, b_, c_ = grads_with("nccl", solver), grads_with("fused", solver), grads_with("p2p", solver)
+    rk4_err[solver] = dict(fused_vs_nccl=max(rel_err(x, y_) for x, y_ in zip(b_[-1][1:], a_[-1][1:])),
+                           p2p_vs_nccl=max(rel_err(x, y_) for x, y_ in zip(c_[-1][1:], a_[-1][1:])),
+                           repeatable=all(torch.equal(x, y_) for x, y_ in zip(b_[0][1:], b_[-1][1:])))
 g_nccl, g_fused = grads_with("nccl"), grads_with("fused")
 flat = torch.cat([x.reshape(-1) for x in g_fused[-1][1:]])
 gathered_g = [torch.empty_like(flat) for _ in range(world)]
@@ -97,7 +111,9 @@ if rank == 0:
               identical_on_all_ranks=all(torch.equal(x, gathered_g[0]) for x in gathered_g),
               grad_y0_local=bool(torch.equal(g_fused[-1][0], g_nccl[-1][0])))
     res["fused_grad_exchange"] = fe
-    res["ok"] = ok = bool(ok and fe["vs_nccl"] < 1e-5 and fe["repeatable"] and fe["identical_on_all_ranks"] and fe["grad_y0_local"])
+    res["rk4_grad_exchange"] = rk4_err
+    res["ok"] = ok = bool(ok and fe["vs_nccl"] < 1e-5 and fe["repeatable"] and fe["identical_on_all_ranks"] and fe["grad_y0_local"]
+                          and all(v["fused_vs_nccl"] < 1e-5 and v["p2p_vs_nccl"] < 1e-5 and v["repeatable"] for v in rk4_err.values()))
 
 
 def timed(opts, Bt=4096, n=20):
