@@ -74,8 +74,11 @@ __device__ __forceinline__ void world_allreduce_sum(double (&v)[NV], const Dp5Ar
   if (blockIdx.x == 0 && warp == 0) {
     for (int idx = lane; idx < W * NV; idx += 32) {
       const int r = idx / NV, k = idx % NV;
+      float val = 0.f;  // (no dynamic index into v: that would put the caller's array into local memory)
+#pragma unroll
+      for (int kk = 0; kk < NV; ++kk) val = k == kk ? (float)v[kk] : val;
       st_relaxed_sys_u64(p.w_slots[r] + (size_t)(par * kGsMaxVals + k) * W + p.w_rank,
-                         (unsigned long long)__float_as_uint((float)v[k]) | ((unsigned long long)tag << 32));
+                         (unsigned long long)__float_as_uint(val) | ((unsigned long long)tag << 32));
     }
   }
   if (warp == 0) {
@@ -106,7 +109,10 @@ __device__ __forceinline__ void world_allreduce_sum(double (&v)[NV], const Dp5Ar
   if (s_late) status |= GODE_ST_PEER_TIMEOUT;
 }
 
-template <int D, int H, int L, int WARPS>
+// WORLD: world-scope norm compiled in (gode_dopri5_fwd_world).  A template parameter, not a runtime flag: the mere presence
+// of the exchange code cost the ordinary solve 4 us of 30 at the bench shape (measured), so the default instantiation is
+// kept free of it.
+template <int D, int H, int L, int WARPS, bool WORLD>
 __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_constant__ Dp5Args p) {
   using S = Shape<D, H, L>;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
@@ -120,11 +126,12 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   const int b = (blockIdx.x * WARPS + warp) * S::G + g;
   const bool valid = b < p.B;
   const bool logger = (blockIdx.x == 0 && tid == 0);
-  const bool world = p.w_world > 1;
+  constexpr bool world = WORLD;
   const double n_elem = (double)(world ? p.w_total_B : (long long)p.B) * (double)D;
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
   // cumulative world epoch: read before the first grid-wide reduction; CTA 0 writes it back after the last one
-  unsigned int epoch = 0, wepoch = world ? *reinterpret_cast<volatile unsigned int*>(p.w_launch_ctr) : 0u;
+  unsigned int epoch = 0, wepoch = 0;
+  if constexpr (WORLD) wepoch = *reinterpret_cast<volatile unsigned int*>(p.w_launch_ctr);
 
   float y0[S::DL], k[7][S::DL], hk[S::HL];
 #pragma unroll
@@ -153,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       }
     }
     grid_allreduce_sum<3, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
-    if (world) world_allreduce_sum<3>(v, p, wepoch, status, lane, warp);
+    if constexpr (WORLD) world_allreduce_sum<3>(v, p, wepoch, status, lane, warp);
     if (v[2] > 0.0) status |= GODE_ST_NONFINITE;
     if (p.o.first_step > 0.0) {
       dt = p.o.first_step;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         if (valid) v2[0] += (double)r * (double)r;
       }
       grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, epoch, lane, warp);
-      if (world) world_allreduce_sum<1>(v2, p, wepoch, status, lane, warp);
+      if constexpr (WORLD) world_allreduce_sum<1>(v2, p, wepoch, status, lane, warp);
       const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       if (valid) v[0] += (double)r * (double)r;
     }
     grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
-    if (world) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
+    if constexpr (WORLD) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
     const float er = (float)sqrt(v[0] / n_elem);
     bool accept = er <= 1.f;
     if (dt > p.o.max_step) accept = false;
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     p.log->n_accepted = n_acc;
     p.log->nfe = nfe;
     p.log->t_final = t0;
-    if (world) *p.w_launch_ctr = wepoch;
+    if constexpr (WORLD) *p.w_launch_ctr = wepoch;
   }
 }
 
@@ -492,10 +499,10 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   return align256(grid_sync_bytes(dp5_fwd_grid<16, 16, 8>(B)));
 }
 
-template <int D, int H, int L, int WARPS = kDp5Warps>
-static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+template <int D, int H, int L, int WARPS, bool WORLD>
+static int launch_dp5_fwd_k(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   const int grid = dp5_fwd_grid<D, H, L, WARPS>(a.B);
-  auto kern = dopri5_fwd_kernel<D, H, L, WARPS>;
+  auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD>;
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
@@ -507,6 +514,12 @@ static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, 0, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
+}
+
+template <int D, int H, int L, int WARPS = kDp5Warps>
+static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  return a.w_world > 1 ? launch_dp5_fwd_k<D, H, L, WARPS, true>(a, workspace, ws_bytes, st)
+                       : launch_dp5_fwd_k<D, H, L, WARPS, false>(a, workspace, ws_bytes, st);
 }
 
 template <int D, int H, int L, int WARPS = 4>
