@@ -371,14 +371,21 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
       s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
       s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
     }
-    if (xchg) {
+    if (xchg) {  // publish this column to every rank (self included); gathered below once all of the warp's columns are out
       const int W = ws.w_world, par = (int)(wtag & 1u), j = lane & 3;
       const float mine = j == 0 ? s.x : j == 1 ? s.y : j == 2 ? s.z : s.w;
       const unsigned long long word = (unsigned long long)__float_as_uint(mine) | ((unsigned long long)wtag << 32);
       for (int r = lane >> 2; r < W; r += 8)
         st_sys_u64(ws.w_slots[r] + ((size_t)(par * W + ws.w_rank) * P + 4 * p4 + j), word);
+    } else if (lane == 0) {
+      reinterpret_cast<float4*>(grad_params)[p4] = s;
+    }
+  }
+  if (xchg) {
+    const int W = ws.w_world, par = (int)(wtag & 1u), j = lane & 3;
+    const unsigned long long t_start = global_timer_ns();
+    for (int p4 = gw; p4 < P / 4; p4 += nw) {
       const unsigned long long* home = ws.w_slots[ws.w_rank] + (size_t)par * W * P + 4 * p4 + j;
-      const unsigned long long t_start = global_timer_ns();
       float4 tot = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r0 = 0; r0 < W; r0 += 8) {
         const int r = r0 + (lane >> 2);
@@ -396,9 +403,8 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
           tot.z += __shfl_sync(0xffffffffu, val, rr * 4 + 2); tot.w += __shfl_sync(0xffffffffu, val, rr * 4 + 3);
         }
       }
-      s = tot;
+      if (lane == 0) reinterpret_cast<float4*>(grad_params)[p4] = tot;
     }
-    if (lane == 0) reinterpret_cast<float4*>(grad_params)[p4] = s;
   }
 }
 
