@@ -54,9 +54,27 @@ class _Config:
     world_norm = None
     # dopri5 backprop: parameter-gradient all-reduce fused into the backward kernel (dist.enable_fused_grad_exchange())
     grad_exchange = None
+    # NVTX ranges ("gode.<solver>.fwd" / ".bwd") around the boundary calls, for `ncu --nvtx` / timeline tools; off by default
+    nvtx = False
 
 
 config = _Config()
+
+
+def _nvtx(name):
+    """Wrap an autograd forward/backward in an NVTX range when config.nvtx is set (one attribute test otherwise)."""
+    def deco(fn):
+        def wrapped(*a, **k):
+            if not config.nvtx:
+                return fn(*a, **k)
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+        return wrapped
+    return deco
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -253,6 +271,7 @@ class _Rk4(torch.autograd.Function):
     gode_rk4_backprop_bwd (autograd-through-odeint semantics), one launch."""
 
     @staticmethod
+    @_nvtx("gode.rk4.fwd")
     def forward(ctx, y0, dt, meta, W1, b1, W2, b2):
         L = _lib.lib()
         B, D = y0.shape
@@ -275,6 +294,7 @@ class _Rk4(torch.autograd.Function):
         return view
 
     @staticmethod
+    @_nvtx("gode.rk4.bwd")
     def backward(ctx, grad_traj):
         L = _lib.lib()
         buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -454,6 +474,7 @@ class _Dopri5(torch.autograd.Function):
     backward: gode_dopri5_backprop_bwd — reverse-mode through the accepted steps recorded on the device."""
 
     @staticmethod
+    @_nvtx("gode.dopri5.fwd")
     def forward(ctx, y0, meta, W1, b1, W2, b2):
         L = _lib.lib()
         B, D = y0.shape
@@ -493,6 +514,7 @@ class _Dopri5(torch.autograd.Function):
         return view
 
     @staticmethod
+    @_nvtx("gode.dopri5.bwd")
     def backward(ctx, grad_traj):
         L = _lib.lib()
         raw, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -540,6 +562,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
     time under the default adjoint norm (adjoint.py)."""
 
     @staticmethod
+    @_nvtx("gode.dopri5_adjoint.fwd")
     def forward(ctx, y0, meta, W1, b1, W2, b2):
         L = _lib.lib()
         B, D = y0.shape
@@ -570,6 +593,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
         return view
 
     @staticmethod
+    @_nvtx("gode.dopri5_adjoint.bwd")
     def backward(ctx, grad_traj):
         L = _lib.lib()
         buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -641,6 +665,7 @@ class _Dopri5Traj(torch.autograd.Function):
     gode_dopri5_traj_backprop_bwd.  Same semantics as running torchdiffeq once per trajectory."""
 
     @staticmethod
+    @_nvtx("gode.dopri5_traj.fwd")
     def forward(ctx, y0, meta, W1, b1, W2, b2):
         L = _lib.lib()
         B, D = y0.shape
@@ -677,6 +702,7 @@ class _Dopri5Traj(torch.autograd.Function):
         return view
 
     @staticmethod
+    @_nvtx("gode.dopri5_traj.bwd")
     def backward(ctx, grad_traj):
         L = _lib.lib()
         hdr, counts, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors

@@ -122,3 +122,31 @@ def test_grad_exchange_hook_prefers_the_fused_kernel_for_small_vectors_only():
         assert calls == [544]
     finally:
         api.config.grad_allreduce = prev
+
+
+def test_nvtx_wrapper_is_transparent_to_autograd():
+    """config.nvtx wraps the autograd forward/backward of the boundary in NVTX ranges; with the flag off (default) the
+    wrapper must be invisible to torch.autograd.Function.apply, needs_input_grad and the gradient flow."""
+    import importlib
+    api = importlib.import_module("gan_ode_b200.odeint")
+
+    class Scale(torch.autograd.Function):
+        @staticmethod
+        @api._nvtx("test.fwd")
+        def forward(ctx, x, k):
+            ctx.k = k
+            return x * k
+
+        @staticmethod
+        @api._nvtx("test.bwd")
+        def backward(ctx, g):
+            assert ctx.needs_input_grad == (True, False)
+            return g * ctx.k, None
+
+    assert api.config.nvtx is False
+    x = torch.randn(5, requires_grad=True)
+    y = Scale.apply(x, 3.0)
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.full((5,), 3.0))
+    for cls in (api._Rk4, api._Dopri5, api._Dopri5Adjoint, api._Dopri5Traj):
+        assert cls.forward.__name__ == "forward" and cls.backward.__name__ == "backward"
