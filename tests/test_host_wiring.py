@@ -1,0 +1,174 @@
+"""Host-side wiring of the boundary, on CPU: the Python host (torchdiffeq signatures -> autograd Functions -> ctypes) is run
+end to end with the COMPUTE entry points of libgode.so replaced by recorders (the real library still answers every size /
+capability query).  Checks what crosses the C ABI — entry point, sizes, layout and precision codes, which tensors' pointers —
+and what comes back to autograd (shapes, strides, which gradients), without a GPU and without computing anything.  The
+numerical parity of the kernels themselves is the -m gpu suite."""
+import ctypes
+import importlib
+
+import pytest
+import torch
+
+import gan_ode_b200 as gode
+from gan_ode_b200 import _lib
+from tests.helpers import make_field
+
+api = importlib.import_module("gan_ode_b200.odeint")
+
+COMPUTE = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_fixed_fwd", "gode_fixed_adjoint_bwd",
+           "gode_fixed_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd", "gode_dopri5_adjoint_bwd",
+           "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd")
+
+
+class Recorder:
+    """libgode.so with the compute entry points swapped for call recorders that return 0 (GODE_OK)."""
+
+    def __init__(self):
+        self.real = _lib.lib()
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name in COMPUTE:
+            def rec(*args):
+                self.calls.append((name, args))
+                return 0
+            return rec
+        return getattr(self.real, name)
+
+
+@pytest.fixture()
+def wired(monkeypatch):
+    r = Recorder()
+    monkeypatch.setattr(_lib, "lib", lambda: r)
+    monkeypatch.setattr(api, "_stream", lambda: 0)
+
+    def cpu_ok(y0, t):   # the CUDA-only gate of _check_common is the one thing switched off here
+        assert isinstance(y0, torch.Tensor) and y0.dtype == torch.float32 and y0.dim() == 2 and len(t) >= 2
+
+    monkeypatch.setattr(api, "_check_common", cpu_ok)
+    return r
+
+
+def _ints(args):
+    return [a for a in args if isinstance(a, int) and not isinstance(a, bool)]
+
+
+def test_rk4_adjoint_call_crosses_the_abi_as_documented(wired):
+    f = make_field(seed=1)
+    y0 = torch.randn(6, 16, requires_grad=True)
+    t = torch.linspace(0, 1, 16)
+    sol = gode.odeint_adjoint(f, y0, t, method="rk4")
+    assert sol.shape == (16, 6, 16) and sol.is_contiguous()
+    (name, a), = wired.calls
+    assert name == "gode_rk4_fwd"
+    W1, b1, W2, b2 = gode.recognise_field(f)
+    assert list(a[:5]) == [y0.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()]
+    assert list(a[6:13]) == [0, 6, 16, 16, 16, _lib.PREC["fp32"], _lib.LAYOUT_TBD]     # dt on host | B D H T | precision layout
+    dt = (ctypes.c_float * 15).from_address(a[5])
+    assert list(dt) == (t[1:] - t[:-1]).tolist()                                      # step table by value, fp32
+    assert a[13] == sol.data_ptr()
+    grads = torch.autograd.grad(sol.sum(), [y0] + list(f.parameters()))
+    assert [g.shape for g in grads] == [(6, 16), (16, 16), (16,), (16, 16), (16,)]
+    name, a = wired.calls[1]
+    assert name == "gode_rk4_adjoint_bwd" and a[0] == sol.data_ptr()                   # continuous adjoint reads the stored outputs
+    # plain odeint: backprop-through-solver entry point; no gradient requested for y0 -> None comes back for it
+    wired.calls.clear()
+    sol = gode.odeint(f, y0.detach(), t, method="rk4")
+    torch.autograd.grad(sol.sum(), list(f.parameters()))
+    assert [c[0] for c in wired.calls] == ["gode_rk4_fwd", "gode_rk4_backprop_bwd"]
+
+
+def test_layout_precision_and_method_options_reach_the_abi(wired):
+    f = make_field(seed=2)
+    y0 = torch.randn(5, 16)
+    t = torch.tensor([1.0, 0.6, 0.0])                                                 # decreasing grid
+    sol = gode.odeint(f, y0, t, method="rk4", options={"layout": "btd", "precision": "bf16"})
+    name, a = wired.calls[-1]
+    assert sol.shape == (3, 5, 16) and sol.stride() == (16, 48, 1)                    # (T,B,D) view of a (B,T,D) buffer
+    assert list(a[7:13]) == [5, 16, 16, 3, _lib.PREC["bf16"], _lib.LAYOUT_BTD]
+    dt = (ctypes.c_float * 2).from_address(a[5])
+    assert list(dt) == pytest.approx([-0.4, -0.6])                                    # signed steps for a decreasing grid
+    gode.odeint(f, y0, t, method="midpoint")
+    name, a = wired.calls[-1]
+    assert name == "gode_fixed_fwd" and a[0] == _lib.METHODS["midpoint"]
+    with pytest.raises(NotImplementedError):
+        gode.odeint(f, y0, t, method="bosh3")
+    with pytest.raises(NotImplementedError):
+        gode.odeint_adjoint(f, y0, t, method="rk4", options={"step_size": 0.1})
+
+
+def test_dopri5_calls_continuous_adjoint_discrete_gradient_and_per_trajectory(wired):
+    f = make_field(seed=3)
+    t = torch.tensor([0.0, 1.0])
+
+    def names():
+        out = [c[0] for c in wired.calls]
+        wired.calls.clear()
+        return out
+
+    # the ODE-RNN call: odeint_adjoint with torchdiffeq's defaults -> forward without checkpoints + continuous adjoint
+    y0 = torch.randn(4, 16, requires_grad=True)
+    sol = gode.odeint_adjoint(f, y0, t)
+    name, a = wired.calls[0]
+    opts = a[10]._obj
+    assert (opts.rtol, opts.atol, opts.ckpt_capacity, opts.norm_scope) == (1e-7, 1e-9, 0, _lib.NORM_BATCH)
+    assert a[18] is None and a[19] is None                                            # no checkpoint buffers
+    torch.autograd.grad(sol.sum(), [y0] + list(f.parameters()))
+    name, a = wired.calls[1]
+    assert name == "gode_dopri5_adjoint_bwd" and a[0] == sol.data_ptr() and a[13] == 15  # all four tensors in the norm
+    assert (a[12]._obj.rtol, a[12]._obj.atol) == (1e-7, 1e-9)
+    names()
+    # adjoint tolerances of their own; a frozen parameter leaves the augmented state (param_mask)
+    f.fn[2].bias.requires_grad_(False)
+    sol = gode.odeint_adjoint(f, y0, t, rtol=1e-5, atol=1e-6, adjoint_rtol=1e-3, adjoint_atol=1e-4,
+                              adjoint_options={"first_step": 0.05})
+    torch.autograd.grad(sol.sum(), [y0])
+    name, a = wired.calls[1]
+    assert (a[12]._obj.rtol, a[12]._obj.atol, a[12]._obj.first_step, a[13]) == (1e-3, 1e-4, 0.05, 7)
+    f.fn[2].bias.requires_grad_(True)
+    names()
+    # opt-in gradient of the recorded steps, and odeint (backprop through the solver): checkpoints + replay kernel
+    for call in (lambda: gode.odeint_adjoint(f, y0, t, options={"adjoint": "discrete"}), lambda: gode.odeint(f, y0, t)):
+        sol = call()
+        assert wired.calls[0][1][10]._obj.ckpt_capacity == api.config.ckpt_capacity
+        torch.autograd.grad(sol.sum(), [y0])
+        assert names() == ["gode_dopri5_fwd", "gode_dopri5_backprop_bwd"]
+    # no gradient wanted: no checkpoints are kept
+    with torch.no_grad():
+        gode.odeint(f, y0, t)
+    assert wired.calls[0][1][10]._obj.ckpt_capacity == 0
+    names()
+    # per-trajectory step control
+    sol = gode.odeint(f, y0, t, options={"norm": "trajectory"})
+    torch.autograd.grad(sol.sum(), [y0])
+    assert names() == ["gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd"]
+    with pytest.raises(gode.GodeError, match="enable_world_norm"):
+        gode.odeint(f, y0, t, options={"norm": "world"})
+    with pytest.raises(ValueError):
+        gode.odeint_adjoint(f, y0, t, options={"adjoint": "exact"})
+
+
+def test_single_layer_field_and_nvtx_flag_do_not_change_what_is_called(wired, monkeypatch):
+    class OneLayer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fn = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.Tanh())
+
+        def forward(self, t, x):
+            return self.fn(x)
+
+    f = OneLayer()
+    y0 = torch.randn(3, 16, requires_grad=True)
+    t = torch.linspace(0, 1, 4)
+    pushed = []
+    monkeypatch.setattr(torch.cuda.nvtx, "range_push", lambda s: pushed.append(s))
+    monkeypatch.setattr(torch.cuda.nvtx, "range_pop", lambda: pushed.append("pop"))
+    monkeypatch.setattr(api.config, "nvtx", True)
+    sol = gode.odeint_adjoint(f, y0, t, method="rk4")
+    grads = torch.autograd.grad(sol.sum(), [y0] + list(f.parameters()))
+    assert len(grads) == 3 and grads[1].shape == (16, 16) and grads[2].shape == (16,)   # only the two real parameters
+    name, a = wired.calls[0]
+    W2 = torch.eye(16)
+    got = torch.frombuffer((ctypes.c_float * 256).from_address(a[3]), dtype=torch.float32).view(16, 16)
+    assert torch.equal(got, W2)                                                       # identity second layer goes to the kernel
+    assert pushed == ["gode.rk4.fwd", "pop", "gode.rk4.bwd", "pop"]
