@@ -161,6 +161,13 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _require_cuda(*tensors, what="y0"):
+    """The one device gate of the host side: the product path runs on the GPU or not at all."""
+    for x in tensors:
+        if not x.is_cuda:
+            raise GodeError("{} is on {}: the B200 path has no CPU fallback".format(what, x.device))
+
+
 def _check_common(y0, t):
     if not isinstance(y0, torch.Tensor):
         raise NotImplementedError("tuple-valued y0 is not on the gan-ode hot path")
@@ -175,8 +182,7 @@ def _check_common(y0, t):
         raise NotImplementedError("the fused path computes in float32 state (reference dtype); got {}".format(y0.dtype))
     if y0.dim() != 2:
         raise NotImplementedError("y0 must be (B, D) as in models/mocogan_ode.py:136-140; got {}".format(tuple(y0.shape)))
-    if not y0.is_cuda:
-        raise GodeError("y0 is on {}: the B200 path has no CPU fallback".format(y0.device))
+    _require_cuda(y0)
     if len(t) < 2:
         raise NotImplementedError("len(t) must be >= 2")
 

@@ -19,6 +19,9 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import GodeAdaptiveOpts
+import importlib
+
+_api = importlib.import_module(__package__ + ".odeint")   # (the package re-exports the FUNCTION odeint under that name)
 from .odeint import _adaptive_opts, _f32c, _ptr, _stream, config, recognise_field
 
 __all__ = ["odernn_codes", "gru_jump", "OdeRnnLog"]
@@ -156,8 +159,7 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
     `codes.transpose(0, 1).reshape(-1, D)` is the reference's `torch.cat(z_m_t[1:], dim=1).view(-1, D)` (:51-52)."""
     W1, b1, W2, b2 = recognise_field(ode_fn)
     gp = _gru_params(gru_cell)
-    if not (h0.is_cuda and eps.is_cuda):
-        raise _lib.GodeError("h0 / eps must be CUDA tensors: the B200 path has no CPU fallback")
+    _api._require_cuda(h0, eps, what="h0 / eps")
     if h0.dim() != 2 or eps.dim() != 3 or eps.shape[1:] != h0.shape:
         raise ValueError("h0 must be (B, D) and eps (F, B, D)")
     D, H = W1.shape[1], W1.shape[0]

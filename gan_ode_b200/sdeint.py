@@ -158,8 +158,7 @@ def _solve(sde, y0, ts, bm, method, dt, adaptive, options, force_keep=False):
         raise TypeError("`y0` must be a floating point Tensor")
     if y0.dim() != 2 or y0.dtype != torch.float32:
         raise NotImplementedError("y0 must be a (B, D) float32 tensor")
-    if not y0.is_cuda:
-        raise GodeError("y0 is on {}: the B200 path has no CPU fallback".format(y0.device))
+    _api._require_cuda(y0)
     if not torch.is_tensor(ts):
         ts = torch.tensor(ts, dtype=y0.dtype)
     D, H = f[0].shape[1], f[0].shape[0]

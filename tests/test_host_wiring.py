@@ -17,7 +17,8 @@ api = importlib.import_module("gan_ode_b200.odeint")
 
 COMPUTE = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_fixed_fwd", "gode_fixed_adjoint_bwd",
            "gode_fixed_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd", "gode_dopri5_adjoint_bwd",
-           "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd")
+           "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd", "gode_sde_em_fwd", "gode_sde_em_bwd", "gode_odernn_fwd",
+           "gode_odernn_bwd", "gode_gru_jump_fwd", "gode_gru_jump_bwd")
 
 
 class Recorder:
@@ -41,11 +42,9 @@ def wired(monkeypatch):
     r = Recorder()
     monkeypatch.setattr(_lib, "lib", lambda: r)
     monkeypatch.setattr(api, "_stream", lambda: 0)
+    monkeypatch.setattr(importlib.import_module("gan_ode_b200.odernn"), "_stream", lambda: 0)   # (imported by name there)
 
-    def cpu_ok(y0, t):   # the CUDA-only gate of _check_common is the one thing switched off here
-        assert isinstance(y0, torch.Tensor) and y0.dtype == torch.float32 and y0.dim() == 2 and len(t) >= 2
-
-    monkeypatch.setattr(api, "_check_common", cpu_ok)
+    monkeypatch.setattr(api, "_require_cuda", lambda *a, **k: None)   # the device gate is the one thing switched off here
     return r
 
 
@@ -172,3 +171,63 @@ def test_single_layer_field_and_nvtx_flag_do_not_change_what_is_called(wired, mo
     got = torch.frombuffer((ctypes.c_float * 256).from_address(a[3]), dtype=torch.float32).view(16, 16)
     assert torch.equal(got, W2)                                                       # identity second layer goes to the kernel
     assert pushed == ["gode.rk4.fwd", "pop", "gode.rk4.bwd", "pop"]
+
+
+def test_sde_call_carries_the_torchsde_step_grid_and_the_philox_contract(wired):
+    from gan_ode_b200.sdeint import PhiloxBrownian, TableBrownian
+    from tests.helpers import SDEFunc
+    torch.manual_seed(0)
+    sde = SDEFunc(16, 16)
+    y0 = torch.randn(7, 16, requires_grad=True)
+    ts = torch.linspace(0, 1, 16)
+    sol = gode.sdeint_adjoint(sde, y0, ts, bm=PhiloxBrownian(1234, traj_offset=70), method="euler", adjoint_method="euler", dt=2.5e-2)
+    assert sol.shape == (16, 7, 16)
+    name, a = wired.calls[0]
+    assert name == "gode_sde_em_fwd" and a[0] == y0.data_ptr()
+    assert a[4] == 41                                              # torchsde's fp32 time accumulation: 41 steps, not 40
+    assert list(a[8:12]) == [7, 16, 16, 16] and a[12] is None      # B D H T | no increment table: in-kernel Philox
+    assert (a[13], a[14]) == (1234, 70)                            # seed, global index of this shard's first trajectory
+    drift = list(a[1])
+    assert drift[0] == sde.drift_fn[0].weight.data_ptr() and list(a[2])[0] == sde.diffusion_fn[0].weight.data_ptr()
+    grads = torch.autograd.grad(sol.sum(), [y0] + list(sde.parameters()))
+    assert len(grads) == 9 and wired.calls[1][0] == "gode_sde_em_bwd" and wired.calls[1][1][14:16] == (1234, 70)
+    # given increments: the table's pointer crosses instead
+    dW = torch.randn(41, 7, 16)
+    gode.sdeint(sde, y0, ts, bm=TableBrownian(dW), method="euler", dt=2.5e-2)
+    assert wired.calls[-1][1][12] == dW.data_ptr()
+    with pytest.raises(ValueError):
+        gode.sdeint(sde, y0, ts, bm=TableBrownian(dW[:40]), method="euler", dt=2.5e-2)
+    with pytest.raises(NotImplementedError):
+        gode.sdeint(sde, y0, ts, method="milstein", dt=2.5e-2)
+
+
+def test_odernn_sampler_calls_one_entry_point_per_direction(wired):
+    f = make_field(seed=4)
+    cell = torch.nn.GRUCell(16, 16)
+    h0 = torch.randn(9, 16, requires_grad=True)
+    eps = torch.randn(5, 9, 16)
+    codes = gode.odernn_codes(f, cell, h0, eps)
+    assert codes.shape == (5, 9, 16)
+    name, a = wired.calls[0]
+    assert name == "gode_odernn_fwd" and list(a[10:14]) == [9, 16, 16, 5]           # B D H F
+    o = a[14]._obj
+    assert (o.rtol, o.atol, o.norm_scope) == (1e-7, 1e-9, _lib.NORM_BATCH) and o.ckpt_capacity > 0
+    assert a[15] == codes.data_ptr() and a[20] is None                             # no per-trajectory counts in batch mode
+    torch.autograd.grad(codes.sum(), [h0] + list(f.parameters()) + list(cell.parameters()))
+    name, a = wired.calls[1]
+    assert name == "gode_odernn_bwd" and a[20] is None and a[21] is None            # recorded-step gradient: no adjoint options
+    wired.calls.clear()
+    # torchdiffeq's continuous adjoint per frame: no checkpoints in the forward, adjoint tolerances to the backward
+    codes = gode.odernn_codes(f, cell, h0, eps, rtol=1e-6, atol=1e-8, options={"adjoint": "continuous"})
+    assert wired.calls[0][1][14]._obj.ckpt_capacity == 0
+    torch.autograd.grad(codes.sum(), [h0])
+    a = wired.calls[1][1]
+    assert (a[21]._obj.rtol, a[21]._obj.atol) == (1e-6, 1e-8)
+    wired.calls.clear()
+    # per-trajectory step control: the counts buffer crosses
+    codes = gode.odernn_codes(f, cell, h0, eps, options={"norm": "trajectory"})
+    assert wired.calls[0][1][14]._obj.norm_scope == _lib.NORM_TRAJ and wired.calls[0][1][20] is not None
+    with pytest.raises(NotImplementedError):
+        gode.odernn_codes(f, torch.nn.GRUCell(16, 16, bias=False), h0, eps)
+    out = gode.gru_jump(eps[0], h0, cell)
+    assert out.shape == (9, 16) and wired.calls[-1][0] == "gode_gru_jump_fwd"
