@@ -42,12 +42,16 @@ CONFIG = {
     "B_per_gpu": B_PER_GPU, "D": D, "H": H, "T": T, "rtol": RTOL, "atol": ATOL, "method": "dopri5",
     "backward": "backprop-through-solver", "weights": "nn.Linear default init, torch.manual_seed(0)",
     "l2": "flushed between steps (256 MiB write outside the per-step CUDA-event pairs)",
-    "parallelism": "dp",
 }
 
 
+def config_for(n_gpus):
+    """The `config` object both arms print: identical keys and values for the same --gpus N."""
+    return dict(CONFIG, global_batch=B_PER_GPU * n_gpus, parallelism="dp{}".format(n_gpus))
+
+
 def make_inputs(seed=0, device="cpu"):
-    from tests.helpers import make_field
+    from gan_ode_b200.fields import make_field   # the package's mirror of the reference modules (no oracle import here)
     f = make_field(D, H, seed=0)
     g = torch.Generator().manual_seed(1000 + seed)
     y0 = torch.randn(B_PER_GPU, D, generator=g)
@@ -87,12 +91,12 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 20))
-    val, sec, n_att = cpu_arm_time(steps, min(args.warmup, 3), threads)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)     # the same counts the GPU arm prints for these flags
+    val, sec, n_att = cpu_arm_time(steps, warmup, threads)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_for(args.gpus),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": "full workload per step (B=4096, {} attempted dopri5 steps), median of {} steps; "
                                    "torchdiffeq-restatement oracle (real torchdiffeq not installable)".format(n_att, steps)},
@@ -155,7 +159,10 @@ def peaks():
 def measure_extras(gode, dev):
     """Side measurements (not the headline): where the kernels sit against their rooflines once the batch is large
     enough to leave the latency regime.  CUDA events, GPU kept busy while the host enqueues, median of 5."""
-    from tests.helpers import make_field, clone_to
+    from gan_ode_b200.fields import make_field
+
+    def clone_to(f, device):
+        return f.to(device)
 
     def timeit(fn, n=5, warm=2):
         for _ in range(warm):
@@ -409,25 +416,86 @@ def run_gpu(args):
         e2e_s, e2e_api = e2e_eager_s, "gan_ode_b200.odeint (eager, pinned host y0)"
     clocks = sampler.stop() if sampler else None
 
-    # ---- per-kernel durations for the roofline: events around each launch while the GPU is kept busy -------------
+    # ---- N>1: the fused NVLink gradient exchange against ncclAllReduce of the local gradients (outside the timed region)
+    parity = None
+    if world > 1:
+        prev, prev_x = gode.config.grad_allreduce, gode.config.grad_exchange
+        exchanged = [g.clone() for g in step()[1:]]                      # the path the timed region ran
+        gode.config.grad_allreduce = gode.config.grad_exchange = None
+        local_g = [g.clone() for g in step()[1:]]                        # this rank's own sums, no exchange
+        gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
+        flat_x = torch.cat([g.reshape(-1) for g in exchanged])
+        flat_n = torch.cat([g.reshape(-1) for g in local_g])
+        dist.all_reduce(flat_n, op=dist.ReduceOp.SUM)                    # NCCL, the library baseline
+        gathered = [torch.empty_like(flat_x) for _ in range(world)]
+        dist.all_gather(gathered, flat_x)
+        max_rel = float((flat_x - flat_n).abs().max() / flat_n.abs().max())
+        parity = {"what": "parameter gradients of the timed step's exchange path vs ncclAllReduce(sum) of the per-rank gradients",
+                  "max_rel": max_rel, "ranks_identical": bool(all(torch.equal(x, gathered[0]) for x in gathered)),
+                  "n_floats": int(flat_x.numel()), "ok": bool(max_rel <= 1e-5)}
+
+    # ---- per-kernel durations for the roofline ---------------------------------------------------------------------------
+    # Taken from graph replays so that they add up to the step: a graph holding only the forward launch is timed exactly
+    # like the step graph (per-replay CUDA events, L2 flushed in between); the backward's share is the difference.  Eager
+    # event brackets (round 1) also caught the launch gaps and over-stated both.
     roof = None
     if rank == 0:
         k = max(10, min(args.steps, 50))
-        ef = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)]
         prev, prev_x = gode.config.grad_allreduce, gode.config.grad_exchange   # rank 0 alone: no exchange in here
         gode.config.grad_allreduce = gode.config.grad_exchange = None
-        for e0, e1, e2 in ef:
-            flush.fill_(1)
-            torch.cuda._sleep(400000)  # keep the GPU busy while the host enqueues, so events bracket kernels only
-            e0.record()
-            sol = gode.odeint(f, y0r, t, **kw)
-            e1.record()
-            torch.autograd.grad(sol, [y0r] + params, grad)
-            e2.record()
-        torch.cuda.synchronize()
+
+        def fwd_only():
+            return gode.odeint(f, y0r, t, **kw)
+
+        def graph_of(fn):
+            s_ = torch.cuda.Stream()
+            s_.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s_):
+                for _ in range(2):
+                    fn()
+            torch.cuda.current_stream().wait_stream(s_)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                keep_ = fn()
+            return g_, keep_
+
+        def replay_us(g_):
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
+            for _ in range(3):
+                g_.replay()
+            for a, b in evs:
+                flush.fill_(1)
+                a.record(); g_.replay(); b.record()
+            torch.cuda.synchronize()
+            return sorted(a.elapsed_time(b) for a, b in evs)[k // 2] * 1e3
+
+        timing_how = "CUDA-graph replays: forward-only graph; backward = (forward+backward graph) - forward"
+        try:
+            if args.no_graph:
+                raise RuntimeError("--no-graph")
+            gf, _kf = graph_of(fwd_only)
+            gs1, _ks = graph_of(step)
+            fwd_us = replay_us(gf)
+            step_us = replay_us(gs1)
+            bwd_us = max(step_us - fwd_us, 0.0)
+            del gf, gs1
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("[bench] per-kernel graph timing unavailable ({}); eager event brackets\n".format(str(e)[:200]))
+            timing_how = "eager CUDA-event brackets (includes launch gaps)"
+            ef = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(k)]
+            for e0, e1, e2 in ef:
+                flush.fill_(1)
+                torch.cuda._sleep(400000)
+                e0.record()
+                sol = gode.odeint(f, y0r, t, **kw)
+                e1.record()
+                torch.autograd.grad(sol, [y0r] + params, grad)
+                e2.record()
+            torch.cuda.synchronize()
+            fwd_us = sorted(e0.elapsed_time(e1) for e0, e1, _ in ef)[k // 2] * 1e3
+            bwd_us = sorted(e1.elapsed_time(e2) for _, e1, e2 in ef)[k // 2] * 1e3
         gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
-        fwd_us = sorted(e0.elapsed_time(e1) for e0, e1, _ in ef)[k // 2] * 1e3
-        bwd_us = sorted(e1.elapsed_time(e2) for _, e1, e2 in ef)[k // 2] * 1e3
         row = B_PER_GPU * D * 4
         fwd_bytes = row * (1 + T + n_acc)           # read y0, write T outputs, write n_acc checkpoints
         bwd_bytes = row * (T + n_acc + 1) + 4 * n_param  # read T upstream grads + n_acc checkpoints, write grad_y0 + params
@@ -443,6 +511,9 @@ def run_gpu(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                 "algorithmic_bytes_per_launch": byts, "kernel_us": dur,
                 "kernels_us": {"dopri5_fwd_kernel": fwd_us, "dopri5_backprop_bwd_kernel": bwd_us},
+                "kernel_timing": timing_how,
+                "step_bytes": fwd_bytes + bwd_bytes,
+                "step_frac": (fwd_bytes + bwd_bytes) / (total_ms / args.steps * 1e-3) / 1e9 / peak,
                 "note": "B=4096 x D=16 is 256 KB of state: the solve is a chain of {} dependent stages with a grid "
                         "barrier per attempted step, i.e. latency-bound, not bandwidth-bound".format(2 + 6 * n_att)}
 
@@ -484,24 +555,39 @@ def run_gpu(args):
         except Exception as e:  # noqa: BLE001
             extras = {"error": str(e)[:200]}
 
+    # second structured roofline entry: the contraction-bound shape (configs[3]: D=64, H=256, rk4 forward + tensor-core
+    # continuous adjoint), 64*D*H algorithmic FLOP per trajectory-step against the measured sustained BF16 GEMM rate
+    roof_tc = None
+    if isinstance(extras, dict):
+        for key, v in extras.items():
+            if key.startswith("tc_rk4_fwd_adjoint_D64_H256") and isinstance(v, dict) and "tflops" in v:
+                pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+                bf16 = float(json.load(open(pk)).get("bf16_tflops_sustained", 1348.6)) if os.path.exists(pk) else 1400.0
+                roof_tc = {"bound": "tensor", "kernel": "tc_rk4_fwd_wide2_kernel + tc_rk4_adj_wide_kernel", "workload": key,
+                           "achieved": v["tflops"], "peak": bf16, "unit": "TFLOP/s", "frac": v["tflops"] / bf16,
+                           "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if os.path.exists(pk) else "fallback",
+                           "algorithmic_flop_per_trajectory_step": 64 * 64 * 256, "traffic": None,
+                           "fwd_ms": v["fwd_ms"], "bwd_ms": v["bwd_ms"],
+                           "trajectory_steps_per_s": v["trajectory_steps_per_s"]}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": dict(CONFIG, global_batch=B_PER_GPU * n_gpus, cuda_graph=graphed,
-                                            attempted_steps=n_att, accepted_steps=n_acc,
-                                            parallelism="dp{}".format(n_gpus),
-                                            grad_allreduce=("none (1 GPU)" if n_gpus == 1 else
-                                                            "fused into the backward kernel's reduction tail over NVLink peer memory "
-                                                            "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
-                                                            "one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
-                                                            if callable(gode.config.grad_allreduce) else "ncclAllReduce")),
+        "data": "synthetic", "config": config_for(n_gpus),
+        "run": {"cuda_graph": graphed, "attempted_steps": n_att, "accepted_steps": n_acc,
+                "grad_allreduce": ("none (1 GPU)" if n_gpus == 1 else
+                                   "fused into the backward kernel's reduction tail over NVLink peer memory "
+                                   "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
+                                   "one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
+                                   if callable(gode.config.grad_allreduce) else "ncclAllReduce")},
+        "parity_check": parity,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
                 "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
         "gpu_launches": (2 + (1 if n_gpus > 1 and gode.config.grad_exchange is None and callable(gode.config.grad_allreduce)
                               else 0)) * args.steps,
         "eager_ms_per_step": eager_ms / args.steps,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extras": extras,
+        "clocks": clocks, "roofline": roof, "roofline_configs3": roof_tc, "cpu_baseline": cpu, "extras": extras,
     }
     sys.stdout.flush()
     os.write(out_fd, (json.dumps(line) + "\n").encode())

@@ -161,11 +161,54 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def _require_cuda(*tensors, what="y0"):
-    """The one device gate of the host side: the product path runs on the GPU or not at all."""
+def _require_cuda(*tensors, what="y0", weights=()):
+    """The one device gate of the host side: the product path runs on the GPU or not at all, and every pointer that
+    crosses the C ABI must belong to ONE device (a CPU-resident module, or weights on another GPU, would otherwise reach a
+    kernel as a raw host / foreign pointer and fault the whole CUDA context instead of raising here)."""
     for x in tensors:
         if not x.is_cuda:
             raise GodeError("{} is on {}: the B200 path has no CPU fallback".format(what, x.device))
+    if tensors:
+        dev = tensors[0].device
+        for x in tensors[1:]:
+            if x.device != dev:
+                raise GodeError("{}: tensors are on different devices ({} and {})".format(what, dev, x.device))
+        for w in weights:
+            if w.device != dev:
+                raise GodeError("the field's parameters are on {} but {} is on {}: move the module to the solve's device "
+                                "(there is no CPU fallback and no cross-device path)".format(w.device, what, dev))
+
+
+class _on_device:
+    """Make `device` the current CUDA device around a C-ABI call (the library launches on the current device and
+    `_stream()` returns the current device's current stream).  The common case — already current — does nothing."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, device):
+        self.idx, self.prev = device.index, None
+
+    def __enter__(self):
+        if self.idx is None:       # not a CUDA tensor: the device gate has already decided what happens
+            return
+        cur = torch.cuda.current_device()
+        if cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
+def _bwd_on_device(fn):
+    """autograd.Function.backward under the device of the incoming gradient (autograd worker threads normally have it set
+    already; a backward driven from another thread or another current device must not launch on the wrong GPU)."""
+    def wrapped(ctx, grad, *rest):
+        with _on_device(grad.device):
+            return fn(ctx, grad, *rest)
+    wrapped.__name__, wrapped.__doc__ = fn.__name__, fn.__doc__
+    return wrapped
 
 
 def _check_common(y0, t):
@@ -301,6 +344,7 @@ class _Rk4(torch.autograd.Function):
 
     @staticmethod
     @_nvtx("gode.rk4.bwd")
+    @_bwd_on_device
     def backward(ctx, grad_traj):
         L = _lib.lib()
         buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -521,6 +565,7 @@ class _Dopri5(torch.autograd.Function):
 
     @staticmethod
     @_nvtx("gode.dopri5.bwd")
+    @_bwd_on_device
     def backward(ctx, grad_traj):
         L = _lib.lib()
         raw, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -600,6 +645,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
 
     @staticmethod
     @_nvtx("gode.dopri5_adjoint.bwd")
+    @_bwd_on_device
     def backward(ctx, grad_traj):
         L = _lib.lib()
         buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -709,6 +755,7 @@ class _Dopri5Traj(torch.autograd.Function):
 
     @staticmethod
     @_nvtx("gode.dopri5_traj.bwd")
+    @_bwd_on_device
     def backward(ctx, grad_traj):
         L = _lib.lib()
         hdr, counts, ckpt, acc, W1c, b1c, W2c, b2c = ctx.saved_tensors
@@ -764,6 +811,13 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
 def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
     W1, b1, W2, b2 = recognise_field(func)
     _check_common(y0, t)
+    _require_cuda(y0, weights=(W1, b1, W2, b2))
+    with _on_device(y0.device):
+        return _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, (W1, b1, W2, b2))
+
+
+def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, weights):
+    W1, b1, W2, b2 = weights
     options = {} if options is None else dict(options)
     if method is None:
         method = "dopri5"

@@ -45,6 +45,7 @@ class _GruJump(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_api._bwd_on_device
     def backward(ctx, go):
         L = _lib.lib()
         xs = ctx.saved_tensors
@@ -62,7 +63,10 @@ class _GruJump(torch.autograd.Function):
 
 def gru_jump(x, h, cell):
     """`cell(x, h)` for an nn.GRUCell (the ODE-RNN jump, models/mocogan_ode_rnn.py:49) as one fused kernel each way."""
-    return _GruJump.apply(x, h, *_gru_params(cell))
+    gp = _gru_params(cell)
+    _api._require_cuda(x, h, what="x / h", weights=gp)
+    with _api._on_device(h.device):
+        return _GruJump.apply(x, h, *gp)
 
 
 class OdeRnnLog:
@@ -120,6 +124,7 @@ class _OdeRnn(torch.autograd.Function):
         return codes
 
     @staticmethod
+    @_api._bwd_on_device
     def backward(ctx, grad_codes):
         L = _lib.lib()
         seg, logs, ckpt, acc, n_acc, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh = ctx.saved_tensors
@@ -159,7 +164,7 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
     `codes.transpose(0, 1).reshape(-1, D)` is the reference's `torch.cat(z_m_t[1:], dim=1).view(-1, D)` (:51-52)."""
     W1, b1, W2, b2 = recognise_field(ode_fn)
     gp = _gru_params(gru_cell)
-    _api._require_cuda(h0, eps, what="h0 / eps")
+    _api._require_cuda(h0, eps, what="h0 / eps", weights=(W1, b1, W2, b2) + tuple(gp))
     if h0.dim() != 2 or eps.dim() != 3 or eps.shape[1:] != h0.shape:
         raise ValueError("h0 must be (B, D) and eps (F, B, D)")
     D, H = W1.shape[1], W1.shape[0]
@@ -177,4 +182,5 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
             raise NotImplementedError("the continuous adjoint uses torchdiffeq's batch-global norm")
         adj = _adaptive_opts(rtol, atol, {k: v for k, v in options.items() if k != "norm"}, 1.0)
     meta = dict(opts=o, keep=keep, adj_opts=adj)
-    return _OdeRnn.apply(h0, eps, meta, W1, b1, W2, b2, *gp)
+    with _api._on_device(h0.device):
+        return _OdeRnn.apply(h0, eps, meta, W1, b1, W2, b2, *gp)

@@ -116,6 +116,7 @@ class _SdeEM(torch.autograd.Function):
         return view
 
     @staticmethod
+    @_api._bwd_on_device
     def backward(ctx, grad_frames):
         L = _lib.lib()
         states, *ws = ctx.saved_tensors
@@ -158,7 +159,7 @@ def _solve(sde, y0, ts, bm, method, dt, adaptive, options, force_keep=False):
         raise TypeError("`y0` must be a floating point Tensor")
     if y0.dim() != 2 or y0.dtype != torch.float32:
         raise NotImplementedError("y0 must be a (B, D) float32 tensor")
-    _api._require_cuda(y0)
+    _api._require_cuda(y0, weights=(*f, *g))
     if not torch.is_tensor(ts):
         ts = torch.tensor(ts, dtype=y0.dtype)
     D, H = f[0].shape[1], f[0].shape[0]
@@ -181,7 +182,8 @@ def _solve(sde, y0, ts, bm, method, dt, adaptive, options, force_keep=False):
     else:
         raise NotImplementedError("bm must be None, PhiloxBrownian or TableBrownian (torchsde BrownianInterval objects "
                                   "are not reproducible from a counter stream)")
-    return _SdeEM.apply(y0, meta, *f, *g)
+    with _api._on_device(y0.device):
+        return _SdeEM.apply(y0, meta, *f, *g)
 
 
 def sdeint(sde, y0, ts, bm=None, method=None, dt=1e-3, adaptive=False, rtol=1e-5, atol=1e-4, dt_min=1e-5, options=None,

@@ -11,7 +11,7 @@ import torch
 
 import gan_ode_b200 as gode
 from oracle import torchdiffeq_restatement as tdq
-from tests.helpers import clone_to, make_field, rel_err
+from tests.helpers import clone_to, elem_close, make_field, rel_err, rowwise_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -41,6 +41,9 @@ def test_rk4_forward_matches_oracle(B, layout):
     assert out.shape == (16, B, 16)
     assert torch.equal(out[0].cpu(), y0)  # sol[0] == y0 bit-exact
     assert rel_err(out, ref) <= TOL
+    # element-wise and per-trajectory bars beside the norm-wise one (a trajectory is held to its own scale)
+    assert elem_close(out, ref)[0], elem_close(out, ref)
+    assert rowwise_rel_err(out, ref) <= 2 * TOL, rowwise_rel_err(out, ref)
 
 
 @pytest.mark.parametrize("tname", ["nonuniform", "decreasing", "two_point", "fp64"])
@@ -103,12 +106,20 @@ def _grad_case(solver_ref, solver_gpu, B, method, layout="tbd", scale=1.0, t=Non
 
 
 def _assert_grads(out, ref32, ref64, names=("y0", "W1", "b1", "W2", "b2")):
+    """Norm-wise bar AND an element-wise one: every entry within 1e-5 max|ref| + 1e-4 |ref| of the fp64
+    oracle (the absolute part widens to the fp32 oracle's own error where that is larger: parameter gradients are sums
+    over thousands of trajectories), and grad_y0 additionally per trajectory (each row against its own scale)."""
     for name, a, r32, r64 in zip(names, out, ref32, ref64):
         e_gpu_vs_ref = rel_err(a, r32)
         e_gpu = rel_err(a, r64)
         e_ref = rel_err(r32, r64)
         assert e_gpu_vs_ref <= TOL or e_gpu <= max(TOL, 2 * e_ref), \
             "{}: cuda-vs-oracle {:.2e}, cuda-vs-fp64 {:.2e}, oracle32-vs-fp64 {:.2e}".format(name, e_gpu_vs_ref, e_gpu, e_ref)
+        ok, worst = elem_close(a, r64, atol_rel=max(TOL, 2 * e_ref))
+        assert ok, "{}: element-wise bar exceeded {:.2f}x (oracle32-vs-fp64 {:.2e})".format(name, worst, e_ref)
+        if name == "y0":
+            e_row, e_row_ref = rowwise_rel_err(a, r64), rowwise_rel_err(r32, r64)
+            assert e_row <= max(2 * TOL, 2 * e_row_ref), "y0 per-trajectory {:.2e} (oracle32 {:.2e})".format(e_row, e_row_ref)
 
 
 @pytest.mark.parametrize("B", [1, 16, 37, 1024])
@@ -151,14 +162,27 @@ def test_only_requested_gradients_are_returned():
 
 
 # ---- dopri5 ----------------------------------------------------------------------------------------------------
+def _near_tie(rlog):
+    return any(abs(e - 1.0) < 1e-4 for e in rlog.error_ratio)
+
+
 def _dopri5_case(B, scale, options=None, t=None, rtol=1e-5, atol=1e-5, seed=0):
-    f = make_field(seed=seed, scale=scale)
-    torch.manual_seed(seed + 1)
-    y0 = torch.randn(B, 16)
+    """an oracle error_ratio within reduction-order noise (1e-4) of the accept threshold makes the sequence
+    comparison ill-posed.  Such an input is not skipped: the seed is bumped (decided on the CPU oracle alone, before the
+    GPU runs) until the case is well-posed, so every listed case runs and is compared."""
     t = _t16() if t is None else t
-    with torch.no_grad():
-        ref = tdq.odeint(f, y0, t, method="dopri5", rtol=rtol, atol=atol, options=options)
+    for bump in range(8):
+        f = make_field(seed=seed + 1000 * bump, scale=scale)
+        torch.manual_seed(seed + 1 + 1000 * bump)
+        y0 = torch.randn(B, 16)
+        with torch.no_grad():
+            ref = tdq.odeint(f, y0, t, method="dopri5", rtol=rtol, atol=atol, options=options)
         rlog = tdq.last_step_log()
+        if not _near_tie(rlog):
+            break
+    else:
+        raise AssertionError("no well-posed seed found in 8 tries")
+    with torch.no_grad():
         out = gode.odeint(clone_to(f, DEV), y0.to(DEV), t, method="dopri5", rtol=rtol, atol=atol, options=options)
         glog = gode.last_step_log()
         true = tdq.odeint(clone_to(f, "cpu", torch.float64), y0[:256].double(), t.double(), method="dopri5",
@@ -193,9 +217,7 @@ def _assert_same_steps(glog, rlog):
     its own log, error ratios equal to the oracle's up to fp32 reduction-order noise, and dt sequences equal to
     1e-5 wherever they are not driven by a noise-level error estimate (see oracle `_replay_dt`)."""
     assert glog.status == 0
-    near_tie = [abs(e - 1.0) < 1e-4 for e in rlog.error_ratio]
-    if any(near_tie):  # SURVEY H1: report, do not fail, when error_ratio is within reduction-order noise of 1.0
-        pytest.skip("oracle error_ratio within 1e-4 of the accept threshold; sequence comparison is ill-posed")
+    assert not _near_tie(rlog), "near-tie case reached the comparison (the seed bump in _dopri5_case should prevent it)"
     assert glog.accepted == rlog.accepted, (glog.accepted, rlog.accepted)
     assert glog.n_accepted == rlog.n_accepted and glog.nfe == rlog.nfe
     assert abs(glog.dt0 - rlog.dt0) <= 1e-5 * abs(rlog.dt0)
@@ -269,10 +291,12 @@ def test_dopri5_status_bits():
 
 
 @pytest.mark.parametrize("B,scale,opts", [(16, 1.0, None), (37, 4.0, None), (1024, 4.0, None),
-                                           (256, 8.0, {"first_step": 1.0})])
+                                           (256, 8.0, {"first_step": 1.0}),
+                                           (4096, 1.0, None), (4096, 4.0, None)])   # BASELINE.json configs[1] at its stated size
 def test_dopri5_backprop_gradients_match_autograd_through_oracle(B, scale, opts):
     """dt sequence treated as data on both sides (oracle flag _detach_dt0; SURVEY A.5 documents upstream's
-    O(tol) leak through the initial-step heuristic)."""
+    O(tol) leak through the initial-step heuristic).  The two B = 4096 cases are the workload bench.py times
+    (configs[1]: dopri5 rtol = atol = 1e-5, forward + backprop-through-solver), at scale 1 and on the stiffer field."""
     _need_gpu()
     out, r32, r64 = _grad_case(tdq.odeint, gode.odeint, B, "dopri5", scale=scale, rtol=1e-5, atol=1e-5, options=opts)
     _assert_grads(out, r32, r64)
@@ -286,6 +310,22 @@ def test_dopri5_backprop_two_point_grid():
 
 
 # ---- boundary behaviour -------------------------------------------------------------------------------------------
+def test_device_gate_cpu_field_with_cuda_state_raises_before_launch():
+    """a module left on the CPU (or on another GPU) must raise in Python, not hand a host pointer to a kernel."""
+    _need_gpu()
+    f_cpu = make_field(seed=2)
+    y0 = torch.randn(8, 16, device=DEV)
+    for call in (lambda: gode.odeint(f_cpu, y0, _t16(), method="rk4"),
+                 lambda: gode.odeint_adjoint(f_cpu, y0, _t16(), method="dopri5"),
+                 lambda: gode.odernn_codes(f_cpu, torch.nn.GRUCell(16, 16).to(DEV), y0, torch.randn(2, 8, 16, device=DEV)),
+                 lambda: gode.odernn_codes(clone_to(f_cpu, DEV), torch.nn.GRUCell(16, 16), y0, torch.randn(2, 8, 16, device=DEV))):
+        with pytest.raises(gode.GodeError, match="parameters are on cpu"):
+            call()
+    # the context is still healthy: a correct call right after works
+    out = gode.odeint(clone_to(f_cpu, DEV), y0, _t16(), method="rk4")
+    assert torch.isfinite(out).all()
+
+
 def test_unrecognised_field_raises():
     _need_gpu()
 
@@ -657,6 +697,33 @@ def test_sde_given_increments_matches_oracle(B, layout):
         assert rel_err(a, b) <= 2e-5, rel_err(a, b)
 
 
+def test_sde_given_increments_at_config4_batch():
+    """BASELINE.json configs[4] at its stated size: B = 16384 trajectories, 41 Euler-Maruyama steps of dt = 0.025, 16
+    frames, given dW.  Trajectory <= 1e-5 norm-wise, element-wise and per trajectory; gradients against the fp64 oracle
+    (the fp32 oracle's own rounding over 16384-term sums is measured and not charged to the kernel)."""
+    _need_gpu()
+    from gan_ode_b200.sdeint import step_grid
+    from oracle import torchsde_restatement as tsde
+    B = 16384
+    sde, sde_g = _sde_pair(seed=B)
+    ts = torch.linspace(0, 1, 16).float()
+    h, *_ = step_grid(ts, 2.5e-2)
+    y0 = torch.randn(B, 16)
+    g = torch.randn(16, B, 16)
+    dW = torch.randn(41, B, 16) * torch.from_numpy(h).sqrt().view(-1, 1, 1)
+    ref_sol, ref_g = _sde_run(tsde.sdeint, sde, y0, ts, g, bm=tsde.TableBrownian(dW))
+    sde64 = clone_to(sde, "cpu", torch.float64)
+    _, ref64_g = _sde_run(tsde.sdeint, sde64, y0.double(), ts.double(), g.double(), bm=tsde.TableBrownian(dW.double()))
+    out_sol, out_g = _sde_run(gode.sdeint_adjoint, sde_g, y0.to(DEV), ts, g.to(DEV),
+                              bm=gode.TableBrownian(dW.to(DEV)), adjoint_method="euler",
+                              options={"adjoint": "discrete"})
+    assert out_sol.shape == (16, B, 16) and torch.equal(out_sol[0].cpu(), y0)
+    assert rel_err(out_sol, ref_sol) <= TOL
+    assert elem_close(out_sol, ref_sol)[0] and rowwise_rel_err(out_sol, ref_sol) <= 5 * TOL, \
+        (elem_close(out_sol, ref_sol), rowwise_rel_err(out_sol, ref_sol))
+    _assert_grads(out_g, ref_g, ref64_g, names=["y0"] + [n for n, _ in sde.named_parameters()])
+
+
 def test_sde_philox_stream_matches_cpu_contract_and_is_shard_invariant():
     _need_gpu()
     import numpy as np
@@ -950,6 +1017,51 @@ def test_odernn_fused_sampler_matches_oracle_and_unfused_path(monkeypatch):
     for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
         assert rel_err(p.grad, q.grad) <= 1e-4, (n, rel_err(p.grad, q.grad))
     assert rel_err(h0c.grad, h0u.grad) <= 1e-4 and rel_err(epsc.grad, epsu.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("mode", ["continuous", "discrete"])
+def test_odernn_fused_sampler_at_config2_batch(monkeypatch, mode):
+    """BASELINE.json configs[2] at its stated batch: B = 8192 trajectories through the fused ODE-RNN sampler (3 frames of
+    [dopri5 over [0,1] at torchdiffeq's default tolerances -> GRU jump], models/mocogan_ode_rnn.py:45-52) against the
+    reference loop on the CPU oracle (continuous adjoint).  'continuous' is the same algorithm as the oracle's; 'discrete'
+    (the sampler's default) is the gradient of the recorded steps and agrees to O(tolerance)."""
+    _need_gpu()
+    import sys
+    import types
+    from tests.caller_model import LatentMotionODERNN
+
+    torch.manual_seed(11)
+    F, B = 3, 8192
+    cpu_model = LatentMotionODERNN(16, F)
+    gpu_model = LatentMotionODERNN(16, F)
+    gpu_model.load_state_dict(cpu_model.state_dict())
+    gpu_model.to(DEV)
+    h0, eps, w = torch.randn(B, 16), torch.randn(F, B, 16), torch.randn(B * F, 16)
+
+    shim = types.ModuleType("torchdiffeq")
+    shim.odeint, shim.odeint_adjoint = tdq.odeint, tdq.odeint_adjoint
+    monkeypatch.setitem(sys.modules, "torchdiffeq", shim)
+    h0r, epsr = h0.clone().requires_grad_(True), eps.clone().requires_grad_(True)
+    ref = cpu_model.sample_z_m(B, h0=h0r, eps=epsr)
+    (ref * w).sum().backward()
+    monkeypatch.delitem(sys.modules, "torchdiffeq")
+
+    h0g, epsg = h0.to(DEV).requires_grad_(True), eps.to(DEV).requires_grad_(True)
+    codes = gode.odernn_codes(gpu_model.ode_fn, gpu_model.recurrent, h0g, epsg, options={"adjoint": mode})
+    out = codes.transpose(0, 1).reshape(-1, 16)     # models/mocogan_ode_rnn.py:51-52
+    (out * w.to(DEV)).sum().backward()
+    logs = gode.odernn.last_log().frames()
+    assert len(logs) == F and all(l["status"] == 0 for l in logs)
+    assert out.shape == (B * F, 16)
+    assert rel_err(out, ref) <= 2e-5, rel_err(out, ref)
+    assert rowwise_rel_err(out, ref) <= 1e-4, rowwise_rel_err(out, ref)
+    gtol = 1e-4 if mode == "continuous" else 1e-3
+    assert rel_err(h0g.grad, h0r.grad) <= gtol and rel_err(epsg.grad, epsr.grad) <= gtol, \
+        (rel_err(h0g.grad, h0r.grad), rel_err(epsg.grad, epsr.grad))
+    for (n, p), (_, q) in zip(gpu_model.named_parameters(), cpu_model.named_parameters()):
+        if p.grad is None and q.grad is None:   # the pre-MLP `linear` is constructed but unused by this sampler (:30-38)
+            continue
+        assert rel_err(p.grad, q.grad) <= gtol, (n, rel_err(p.grad, q.grad))
 
 
 @pytest.mark.parametrize("D,H", [(64, 256), (16, 16)])

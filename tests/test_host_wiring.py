@@ -231,3 +231,24 @@ def test_odernn_sampler_calls_one_entry_point_per_direction(wired):
         gode.odernn_codes(f, torch.nn.GRUCell(16, 16, bias=False), h0, eps)
     out = gode.gru_jump(eps[0], h0, cell)
     assert out.shape == (9, 16) and wired.calls[-1][0] == "gode_gru_jump_fwd"
+
+
+def test_device_gate_rejects_cpu_field_and_cpu_state():
+    """the gate covers the weights too.  Without a GPU in this container the CUDA-tensor half is emulated with
+    the `meta`-free check itself: a CPU y0 raises; a y0 that passes as CUDA with CPU weights must raise before any pointer
+    crosses the C ABI."""
+    f = make_field(seed=2)
+    with pytest.raises(gode.GodeError, match="no CPU fallback"):
+        gode.odeint(f, torch.randn(4, 16), torch.linspace(0, 1, 4), method="rk4")
+
+    class FakeCuda:
+        """Stands in for a CUDA tensor in the gate (is_cuda / device only)."""
+        is_cuda = True
+        device = torch.device("cuda", 0)
+
+    with pytest.raises(gode.GodeError, match="parameters are on cpu"):
+        api._require_cuda(FakeCuda(), weights=tuple(f.parameters()))
+    other = FakeCuda()
+    other.device = torch.device("cuda", 1)
+    with pytest.raises(gode.GodeError, match="different devices"):
+        api._require_cuda(FakeCuda(), other, what="h0 / eps")
