@@ -11,7 +11,8 @@ PER GPU (weak scaling), output grid t = linspace(0,1,16), dopri5 with rtol = ato
 the solver, upstream gradient supplied as a resident N(0,1) tensor.  One "step" = one forward + one
 backward of that batch.  trajectory-steps = B x ATTEMPTED dopri5 steps (accepted + rejected), read from the device log.
 
-value     inputs resident in HBM; the step (2 kernels + 2 memsets) replayed from a CUDA graph; per-step CUDA events,
+value     inputs resident in HBM; the step (2 kernels, the backward a programmatic dependent launch behind the forward; the
+          grid-sync workspace is persistent, so there are no memsets) replayed from a CUDA graph; per-step CUDA events,
           L2 flushed (256 MiB write) between steps outside the event pairs.
 e2e       the same metric through the public API the reference calls (gan_ode_b200.odeint), eager, with the
           batch's noise y0 in pinned HOST memory: H2D copy of y0 and D2H read of loss + parameter gradients are
@@ -310,6 +311,9 @@ def run_gpu(args):
     try:
         if args.no_graph:
             raise RuntimeError("--no-graph")
+        # Inside the captured step the kernel enqueued right before the backward is the matching forward, so the backward is
+        # captured as a programmatic dependent launch (gan_ode_b200.config.pdl; what GraphedSolveStep does by default).
+        gode.config.pdl = not args.no_pdl
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -320,6 +324,7 @@ def run_gpu(args):
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_grads = step()
+        gode.config.pdl = False
         graph.replay()
         torch.cuda.synchronize()
         ok = all(torch.allclose(a, b, rtol=1e-4, atol=1e-6) for a, b in zip(static_grads, grads))
@@ -329,6 +334,7 @@ def run_gpu(args):
     except Exception as e:  # noqa: BLE001
         sys.stderr.write("[bench] CUDA-graph capture unavailable ({}); timing eager launches\n".format(str(e)[:200]))
         graph = None
+        gode.config.pdl = False
         torch.cuda.synchronize()
 
     run_step = graph.replay if graph is not None else step
@@ -385,7 +391,7 @@ def run_gpu(args):
     try:
         if args.no_graph:
             raise RuntimeError("--no-graph")
-        gs = gode.GraphedSolveStep(f, B_PER_GPU, t, adjoint=False, read_back=("param_grads",), **kw)
+        gs = gode.GraphedSolveStep(f, B_PER_GPU, t, adjoint=False, read_back=("param_grads",), pdl=not args.no_pdl, **kw)
         gs.y0_host.copy_(y0_host)
         gs.grad_traj.copy_(grad)
 
@@ -448,6 +454,7 @@ def run_gpu(args):
             return gode.odeint(f, y0r, t, **kw)
 
         def graph_of(fn):
+            gode.config.pdl = not args.no_pdl
             s_ = torch.cuda.Stream()
             s_.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s_):
@@ -458,6 +465,7 @@ def run_gpu(args):
             g_ = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_):
                 keep_ = fn()
+            gode.config.pdl = False
             return g_, keep_
 
         def replay_us(g_):
@@ -575,6 +583,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_for(n_gpus),
         "run": {"cuda_graph": graphed, "attempted_steps": n_att, "accepted_steps": n_acc,
+                "pdl_backward": bool(graphed and not args.no_pdl),
                 "grad_allreduce": ("none (1 GPU)" if n_gpus == 1 else
                                    "fused into the backward kernel's reduction tail over NVLink peer memory "
                                    "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
@@ -606,6 +615,8 @@ def main():
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "
                     "of the fused peer-memory kernel")
+    ap.add_argument("--no-pdl", action="store_true", help="capture the backward as an ordinary launch (no programmatic "
+                    "dependent launch behind the forward)")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch / wide-field side measurements")
     args = ap.parse_args()
     if args.nccl_allreduce:

@@ -16,6 +16,8 @@ PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
 MAX_HOST_STEPS = 255
+SYNC_REGION_BYTES = 256 * 1024   # include/gode.h GODE_SYNC_REGION_BYTES
+LAUNCH_PDL_BWD = 1
 
 ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_CKPT_OVERFLOW, ST_PEER_TIMEOUT = 1, 2, 4, 8, 16
 
@@ -46,6 +48,9 @@ _I = C.c_int
 _SIGS = {
     "gode_strerror": (C.c_char_p, [_I]),
     "gode_version": (C.c_char_p, []),
+    "gode_workspace_init": (_I, [_P, C.c_size_t, _P]),
+    "gode_stream_capture_id": (_I, [_P, C.POINTER(C.c_ulonglong)]),
+    "gode_set_thread_launch_flags": (_I, [_I]),
     "gode_supported": (_I, [_I, _I, _I]),
     "gode_param_count": (_I, [_I, _I]),
     "gode_rk4_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -3,9 +3,38 @@
 
 using namespace gode;
 
+namespace gode {
+int& thread_launch_flags() {
+  static thread_local int flags = 0;
+  return flags;
+}
+}  // namespace gode
+
 extern "C" {
 
-const char* gode_version(void) { return "gode 0.1 (sm_100a)"; }
+const char* gode_version(void) { return "gode 0.2 (sm_100a)"; }
+
+int gode_workspace_init(void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (!workspace || ws_bytes < (size_t)GODE_SYNC_REGION_BYTES) return GODE_ERR_WORKSPACE;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, GODE_SYNC_REGION_BYTES, (cudaStream_t)stream);
+  return e == cudaSuccess ? GODE_OK : -(1000 + (int)e);
+}
+
+int gode_stream_capture_id(gode_stream_t stream, unsigned long long* id_out) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  cudaError_t e = cudaStreamGetCaptureInfo((cudaStream_t)stream, &st, &id);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return -(1000 + (int)e); }
+  if (id_out) *id_out = id;
+  return st == cudaStreamCaptureStatusActive ? 1 : 0;
+}
+
+int gode_set_thread_launch_flags(int flags) {
+  int& f = gode::thread_launch_flags();
+  const int prev = f;
+  f = flags;
+  return prev;
+}
 
 const char* gode_strerror(int code) {
   switch (code) {
@@ -55,13 +84,21 @@ size_t gode_bwd_workspace_bytes(int B, int D, int H) {
   return bwd_workspace_bytes(gode_param_count(D, H));
 }
 
+// Kernels that use their workspace as plain scratch (no grid synchronisation) get the part BEHIND the persistent sync
+// region, so that a workspace shared with the cooperative kernels never has its counters or tagged words overwritten.
+static inline void* scratch_of(void* workspace) { return ws_scratch(workspace); }
+static inline size_t scratch_bytes(size_t ws_bytes) {
+  return ws_bytes > (size_t)GODE_SYNC_REGION_BYTES ? ws_bytes - (size_t)GODE_SYNC_REGION_BYTES : 0;
+}
+
 size_t gode_rk4_bwd_workspace_bytes(int B, int D, int H, int T) {
   if (wide_shape(D, H)) {
     const size_t a = wide_bwd_workspace_bytes(B, D, H, T), b = tc_wide_shape(D, H) ? tc_rk4_adj_wide_workspace_bytes(B) : 0;
-    return a > b ? a : b;
+    return (size_t)GODE_SYNC_REGION_BYTES + (a > b ? a : b);
   }
   {
-    const size_t a = bwd_workspace_bytes(gode_param_count(D, H)), b = tc_shape(D, H) ? tc_rk4_adj_small_workspace_bytes(B) : 0;
+    const size_t a = bwd_workspace_bytes(gode_param_count(D, H)),
+                 b = tc_shape(D, H) ? (size_t)GODE_SYNC_REGION_BYTES + tc_rk4_adj_small_workspace_bytes(B) : 0;
     return a > b ? a : b;
   }
 }
@@ -74,15 +111,15 @@ static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_tra
     return GODE_ERR_ARG;
   if (precision == GODE_PREC_BF16 && tc_wide_shape(D, H) && adjoint)  // tensor-core continuous adjoint (wide field)
     return tc_rk4_adj_wide(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
-                           workspace, ws_bytes, (cudaStream_t)stream);
+                           scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
   if (precision == GODE_PREC_BF16 && tc_shape(D, H) && adjoint)       // tensor-core continuous adjoint (reference shape)
     return tc_rk4_adj_small(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
-                            workspace, ws_bytes, (cudaStream_t)stream);
+                            scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
   if (wide_shape(D, H)) {
     if (!adjoint) return GODE_ERR_SHAPE;  // wide backprop-through-solver: not built
     return wide_rk4_adjoint_bwd(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
-                                grad_params, workspace, ws_bytes, (cudaStream_t)stream);
+                                grad_params, scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
   }
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return rk4_small_bwd(adjoint, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,

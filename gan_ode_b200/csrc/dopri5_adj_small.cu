@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
   const float n_elem = (float)p.B * (float)D;
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
   const float asign = -p.o.fsign;  // the adjoint runs against the forward direction
-  unsigned int epoch = 0;
+  SyncState ss;
+  ss.begin(p.gs);
   float* my_acc = s_acc + (size_t)warp * P + lane * Q;  // + vec * WARPS * P
 
 #ifdef GODE_ADJ_TIMING
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
       for (int q = 1; q < WARPS; ++q) x += s_sc[q * kAdjNS + tid];
       __stcg(mine + kAdjNV * P + tid, x);
     }
-    grid_barrier(p.gs, epoch);
+    grid_barrier(p.gs, ss);
     const int nb = gridDim.x, gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
     // (with few CTAs a warp owns several columns: issue the loads of up to four of them before the first shuffle tree)
     for (int c0 = gw; c0 < VT / 4; c0 += 4 * nw) {
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
         if (lane == 0) __stcg(reinterpret_cast<float4*>(p.totals) + c4, s[k]);
       }
     }
-    grid_barrier(p.gs, epoch);
+    grid_barrier(p.gs, ss);
     for (int c4 = tid; c4 < VT / 4; c4 += NT) {
       if (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4)) continue;
       reinterpret_cast<float4*>(s_tot)[c4] = __ldcg(reinterpret_cast<const float4*>(p.totals) + c4);
@@ -598,6 +599,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
     p.log->nfe = nfe;
     p.log->dt0 = dt0;
     p.log->t_final = t0;
+    ss.finish(p.gs);
   }
 }
 
@@ -612,7 +614,7 @@ size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H) {
   (void)D; (void)H;
   using A = AdjLayout<16, 16, 8, kAdjWarps>;
   const int grid = adj_grid<16, 16, 8, kAdjWarps>(B);
-  return align256(grid_sync_bytes(grid)) + align256(sizeof(float) * (size_t)grid * A::VT) + align256(sizeof(float) * A::VT);
+  return (size_t)GODE_SYNC_REGION_BYTES + align256(sizeof(float) * (size_t)grid * A::VT) + align256(sizeof(float) * A::VT);
 }
 
 template <int L, int MINB>
@@ -626,13 +628,11 @@ static int launch_adj(Dp5AdjArgs& a, void* workspace, size_t ws_bytes, cudaStrea
   const int grid = adj_grid<16, 16, L, WARPS>(a.B);
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, smem, limit_cache);
-  if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
+  if (cap <= 0 || grid > cap || grid > kSyncMaxGrid) return GODE_ERR_COOP;
   char* base = reinterpret_cast<char*>(workspace);
   grid_sync_bind(a.gs, base);
-  a.partials = reinterpret_cast<float*>(base + align256(grid_sync_bytes(grid)));
-  a.totals = reinterpret_cast<float*>(base + align256(grid_sync_bytes(grid)) + align256(sizeof(float) * (size_t)grid * A::VT));
-  e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
+  a.partials = reinterpret_cast<float*>(ws_scratch(workspace));
+  a.totals = reinterpret_cast<float*>(ws_scratch(workspace) + align256(sizeof(float) * (size_t)grid * A::VT));
   void* args[] = {(void*)&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
   if (e != cudaSuccess) return -(1000 + (int)e);

@@ -24,7 +24,7 @@ struct Dp5Args {
   GodeStepLog* log;
   double* att_t0; double* att_dt; float* att_er; uint8_t* att_acc;
   float* ckpt; double* acc_t0; double* acc_dt;
-  GridSyncWs gs;              // grid all-reduce slots, zeroed by the host wrapper
+  GridSyncWs gs;              // persistent grid all-reduce region (grid_sync.cuh)
   GodeAdaptiveOpts o;
   int B, T, layout;
   // world-scope norm (gode_dopri5_fwd_world): off when w_world <= 1
@@ -119,6 +119,9 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   __shared__ float s_f[WARPS * kGsMaxVals];
   __shared__ double s_d[kGsMaxVals];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  griddep_launch_dependents();   // a backward launched with PDL may stage its weights under this kernel's tail
+  SyncState ss;
+  ss.begin(p.gs);                // persistent tags: continue where the previous launch on this workspace stopped
   FwdLines<D, H, L> ln;
   ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
   RowWeights<D, H, L> w;
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   const double n_elem = (double)(world ? p.w_total_B : (long long)p.B) * (double)D;
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
   // cumulative world epoch: read before the first grid-wide reduction; CTA 0 writes it back after the last one
-  unsigned int epoch = 0, wepoch = 0;
+  unsigned int wepoch = 0;
   if constexpr (WORLD) wepoch = *reinterpret_cast<volatile unsigned int*>(p.w_launch_ctr);
 
   float y0[S::DL], k[7][S::DL], hk[S::HL];
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         if (!isfinite(y0[c])) v[2] += 1.0;
       }
     }
-    grid_allreduce_sum<3, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
+    grid_allreduce_sum<3, WARPS>(v, s_f, s_d, p.gs, ss, lane, warp);
     if constexpr (WORLD) world_allreduce_sum<3>(v, p, wepoch, status, lane, warp);
     if (v[2] > 0.0) status |= GODE_ST_NONFINITE;
     if (p.o.first_step > 0.0) {
@@ -178,7 +181,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         const float r = (f1[c] - k[0][c]) / scale[c];
         if (valid) v2[0] += (double)r * (double)r;
       }
-      grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, epoch, lane, warp);
+      grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, ss, lane, warp);
       if constexpr (WORLD) world_allreduce_sum<1>(v2, p, wepoch, status, lane, warp);
       const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
       float h1;
@@ -220,7 +223,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       const float r = e / tol;
       if (valid) v[0] += (double)r * (double)r;
     }
-    grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, epoch, lane, warp);
+    grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, ss, lane, warp);
     if constexpr (WORLD) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
     const float er = (float)sqrt(v[0] / n_elem);
     bool accept = er <= 1.f;
@@ -289,6 +292,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     p.log->nfe = nfe;
     p.log->t_final = t0;
     if constexpr (WORLD) *p.w_launch_ctr = wepoch;
+    ss.finish(p.gs);   // every CTA has arrived at the last reduction, hence has read the bases
   }
 }
 
@@ -307,8 +311,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
   const bool staged = p.T <= kDp5StageT;
   float* my_gr = s_gr + (size_t)warp * p.T * (S::G * D);
-  // the step log is read first so that its latency overlaps the weight loads below (all are cold global reads)
-  const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
+  // Weights first: under a PDL launch (GODE_LAUNCH_PDL_BWD) this prologue runs while the forward kernel is still in its
+  // tail; everything the forward wrote (step log, checkpoints) and the persistent sync counters are read after the wait.
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
@@ -317,6 +321,10 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
+  griddep_wait();
+  const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
+  SyncState ss;
+  ss.begin(p.ws.gs);
   __syncthreads();
   const int n_acc = min(log_n_accepted, p.o.ckpt_capacity);
   // A forward that failed (dt underflow, non-finite state, step budget, checkpoint overflow) has no valid replay:
@@ -481,7 +489,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
     }
   }
-  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, ss, p.grad_params, lane, warp, tid);
+  if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -495,8 +504,8 @@ static int dp5_fwd_grid(int B) {
 
 size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   (void)D; (void)H;
-  // grid all-reduce slots, sized for the L=8 mapping (the densest we launch)
-  return align256(grid_sync_bytes(dp5_fwd_grid<16, 16, 8>(B)));
+  (void)B;
+  return (size_t)GODE_SYNC_REGION_BYTES;   // the persistent sync region only
 }
 
 template <int D, int H, int L, int WARPS, bool WORLD>
@@ -505,13 +514,11 @@ static int launch_dp5_fwd_k(Dp5Args& a, void* workspace, size_t ws_bytes, cudaSt
   auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD>;
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, 0, limit_cache);
-  if (cap <= 0 || grid > cap) return GODE_ERR_COOP;
+  if (cap <= 0 || grid > cap || grid > kSyncMaxGrid) return GODE_ERR_COOP;
   if (ws_bytes < grid_sync_bytes(grid)) return GODE_ERR_WORKSPACE;
   grid_sync_bind(a.gs, workspace);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, 0, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, 0, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }
@@ -541,13 +548,10 @@ static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStre
   int grid = (a.B + per_cta - 1) / per_cta;
   if (grid > cap) grid = cap;
   if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
-  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
   grid_sync_bind(a.ws.gs, workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
-  e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
+  a.ws.partials = reinterpret_cast<float*>(ws_scratch(workspace));
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  e = coop_launch(kern, grid, WARPS * 32, args, smem, st, (thread_launch_flags() & GODE_LAUNCH_PDL_BWD) != 0);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }

@@ -221,6 +221,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_traj_bwd_kernel(const __gri
   GradAcc<D, H, L> acc;
   const float poison = p.log->status != 0 ? __int_as_float(0x7fc00000) : 0.f;
   acc.fill(poison);
+  SyncState ss;
+  ss.begin(p.ws.gs);
   __syncthreads();
   const int stride = gridDim.x * WARPS * S::G;
   for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
@@ -340,7 +342,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_traj_bwd_kernel(const __gri
       store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
     }
   }
-  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, ss, p.grad_params, lane, warp, tid);
+  if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
 }
 
 // ---- host -----------------------------------------------------------------------------------------------------------------
@@ -392,13 +395,10 @@ int dopri5_traj_small_bwd(const float* grad_traj, const float* W1, const float* 
   int grid = (B + per_cta - 1) / per_cta;
   if (grid > cap) grid = cap;
   if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
-  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
   grid_sync_bind(a.ws.gs, workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
+  a.ws.partials = reinterpret_cast<float*>(ws_scratch(workspace));
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }

@@ -25,10 +25,18 @@
 // (CTA-index) order in fp64, so all threads of the grid get bit-identical totals and the accept/reject branch that
 // follows is uniform without any further broadcast.
 //
-// The host zeroes the workspace before the launch (epoch 0 = "nothing published") and launches cooperatively.
+// PERSISTENT workspace (round 2): no memset per launch.  The first kSyncRegionBytes of every workspace are the sync region
+// [counter | epoch base | counter base | tagged-word slots]; the caller zero-fills it ONCE after allocation and then hands the
+// same workspace to any number of launches that are ordered on one stream.  Tags keep counting ACROSS launches: every thread
+// reads (epoch base, counter base) when the kernel starts, and thread 0 of CTA 0 stores the final values after the kernel's
+// last grid-wide operation (by then every CTA has read them: it has arrived at that operation).  A stale word therefore always
+// carries an OLDER tag than any tag a later launch waits for, whatever grid sizes the launches had, and the two
+// cudaMemsetAsync nodes per step (forward + backward) are gone from the stream / the CUDA graph.  Tags and the counter are
+// compared modulo 2^32 (equality / signed difference), so wrap-around is harmless.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/gode.h"
 
 namespace gode {
 
@@ -36,17 +44,40 @@ constexpr int kGsMaxVals = 4;
 constexpr int kGsFlagMaxCtas = 16;  // measured inside dopri5_fwd_kernel (scripts/dp5_lane_sweep.py): beyond 16 CTAs the counter wins
 
 struct GridSyncWs {
-  unsigned int* counter;      // 256-byte slot
-  unsigned long long* slots;  // [2][kGsMaxVals][gridDim.x] tagged words (small grids) / floats (large grids)
+  unsigned int* counter;      // 256-byte header: [0] arrival counter, [1] epoch base, [2] counter base
+  unsigned long long* slots;  // [2][kGsMaxVals][gridDim.x] tagged words
 };
 
-__host__ __device__ inline size_t grid_sync_bytes(int grid) {
-  return 256 + sizeof(unsigned long long) * 2 * kGsMaxVals * (size_t)grid;
-}
+// Fixed size of the sync region at the front of every workspace (so that scratch data behind it can never be mistaken for
+// a tagged word by a later launch with a larger grid): header + slots for up to kSyncMaxGrid CTAs.
+constexpr size_t kSyncRegionBytes = GODE_SYNC_REGION_BYTES;
+constexpr int kSyncMaxGrid = (int)((kSyncRegionBytes - 256) / (sizeof(unsigned long long) * 2 * kGsMaxVals));
+
+__host__ __device__ inline size_t grid_sync_bytes(int /*grid*/) { return kSyncRegionBytes; }
 __host__ __device__ inline void grid_sync_bind(GridSyncWs& ws, void* base) {
   ws.counter = reinterpret_cast<unsigned int*>(base);
   ws.slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + 256);
 }
+
+// Programmatic dependent launch (PDL): a kernel launched with programmatic stream serialisation may start while the
+// previous kernel on the stream is still running; griddep_wait() blocks until that kernel has completed and its memory is
+// visible (a no-op for an ordinary launch).  griddep_launch_dependents() lets the NEXT kernel's CTAs be scheduled early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Per-thread view of the persistent counters: `epoch` is the running tag, `ctarget` the running counter target.
+struct SyncState {
+  unsigned int epoch, ctarget;
+  __device__ __forceinline__ void begin(const GridSyncWs& ws) {
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch) : "l"(ws.counter + 1) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ctarget) : "l"(ws.counter + 2) : "memory");
+  }
+  // thread 0 of CTA 0, after the kernel's LAST grid-wide operation
+  __device__ __forceinline__ void finish(const GridSyncWs& ws) const {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ws.counter + 1), "r"(epoch) : "memory");
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ws.counter + 2), "r"(ctarget) : "memory");
+  }
+};
 
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -70,10 +101,11 @@ __device__ __forceinline__ void wait_counter(const unsigned int* c, unsigned int
 // lanes) and leaves as the grid total, identical in every thread.  s_f: shared float[WARPS*NV]; s_d: shared double[NV].
 template <int NV, int WARPS>
 __device__ __forceinline__ void grid_allreduce_sum(double (&v)[NV], float* s_f, double* s_d, const GridSyncWs& ws,
-                                                   unsigned int& epoch, int lane, int warp) {
+                                                   SyncState& ss, int lane, int warp) {
   static_assert(NV <= kGsMaxVals, "raise kGsMaxVals");
-  ++epoch;
+  const unsigned int epoch = ++ss.epoch;
   const int grid = gridDim.x;
+  if (grid > kGsFlagMaxCtas) ss.ctarget += (unsigned int)grid;
   // warp partials (fp32 is ample: the result is rounded to fp32 anyway; CTA sums are combined in fp64)
   float w[NV];
 #pragma unroll
@@ -129,7 +161,7 @@ __device__ __forceinline__ void grid_allreduce_sum(double (&v)[NV], float* s_f, 
                        (unsigned long long)__float_as_uint(mine) | ((unsigned long long)epoch << 32));
       if (lane == 0) {
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ws.counter) : "memory");
-        const unsigned int target = epoch * (unsigned int)grid;
+        const unsigned int target = ss.ctarget;
         unsigned int seen;
         do {
           asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ws.counter) : "memory");
@@ -168,13 +200,13 @@ __device__ __forceinline__ void grid_allreduce_sum(double (&v)[NV], float* s_f, 
 // Plain grid barrier.  Orders prior global writes of every CTA before later global reads (L2 path: __ldcg) of any
 // CTA: bar.sync, then one thread does a gpu-scope release on the counter (cumulative over the CTA's writes ordered
 // before the bar.sync), polls it with acquire loads, and a second bar.sync releases the rest of the CTA.
-__device__ __forceinline__ void grid_barrier(const GridSyncWs& ws, unsigned int& epoch) {
-  ++epoch;
+__device__ __forceinline__ void grid_barrier(const GridSyncWs& ws, SyncState& ss) {
+  ss.ctarget += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     arrive_counter(ws.counter);
-    wait_counter(ws.counter, epoch * gridDim.x);
+    wait_counter(ws.counter, ss.ctarget);
     __threadfence();
   }
   __syncthreads();

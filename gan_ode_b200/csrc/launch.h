@@ -31,10 +31,35 @@ inline int bwd_grid_cap() { return sm_count() * 2; }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-// [grid-sync slots | per-CTA partial rows]
+// [persistent sync region (GODE_SYNC_REGION_BYTES, zero-filled once by the owner) | per-CTA partial rows]
 inline size_t bwd_workspace_bytes(int P) {
   const int cap = bwd_grid_cap();
-  return align256(256 + sizeof(unsigned long long) * 2 * 4 * (size_t)cap) + sizeof(float) * (size_t)P * (size_t)cap;
+  return (size_t)GODE_SYNC_REGION_BYTES + sizeof(float) * (size_t)P * (size_t)cap;
+}
+inline char* ws_scratch(void* workspace) { return reinterpret_cast<char*>(workspace) + GODE_SYNC_REGION_BYTES; }
+
+// launch flags of the calling thread (gode_set_thread_launch_flags)
+int& thread_launch_flags();
+
+// Cooperative launch; with `pdl` also programmatic stream serialisation (the kernel must call griddep_wait() before it
+// touches anything the previous kernel on the stream wrote).  If the driver refuses the attribute pair, the plain
+// cooperative launch is used (remembered per process).
+template <class K>
+inline cudaError_t coop_launch(K kern, int grid, int block, void** args, size_t smem, cudaStream_t st, bool pdl) {
+  static bool pdl_ok = true;
+  if (pdl && pdl_ok) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
+    if (e == cudaSuccess) return e;
+    (void)cudaGetLastError();
+    pdl_ok = false;
+  }
+  return cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(block), args, smem, st);
 }
 
 // co-resident CTA limit of a kernel (cached per instantiation; racing writers store the same value)

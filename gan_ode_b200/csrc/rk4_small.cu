@@ -31,6 +31,7 @@ __device__ __forceinline__ size_t traj_off(int layout, int s, int b, int B, int 
 // ------------------------------------------------------------------------------------------------------------
 template <int D, int H, int L, int WARPS, int METHOD>
 __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_constant__ Rk4Args p) {
+  griddep_launch_dependents();   // a backward launched with PDL may stage its weights under this kernel's tail
   using S = Shape<D, H, L>;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / L, l = lane % L;
@@ -110,6 +111,9 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
   acc.zero();
+  griddep_wait();        // PDL launch: the weight prologue above overlapped the forward's tail; its outputs are read below
+  SyncState ss;
+  ss.begin(p.ws.gs);
   __syncthreads();
   const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
   const int stride = gridDim.x * WARPS * S::G;
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
     }
     if (valid) store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, a);
   }
-  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, ss, p.grad_params, lane, warp, tid);
+  if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -208,6 +213,9 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
   acc.zero();
+  griddep_wait();        // PDL launch: the weight prologue above overlapped the forward's tail; its outputs are read below
+  SyncState ss;
+  ss.begin(p.ws.gs);
   __syncthreads();
   const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
   const int stride = gridDim.x * WARPS * S::G;
@@ -298,7 +306,8 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
     }
     if (valid) store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, yb);
   }
-  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, ss, p.grad_params, lane, warp, tid);
+  if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -347,13 +356,10 @@ static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStre
   int grid = (a.B + per_cta - 1) / per_cta;
   if (grid > cap) grid = cap;
   if (ws_bytes < bwd_workspace_bytes(S::P)) return GODE_ERR_WORKSPACE;
-  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
   grid_sync_bind(a.ws.gs, workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
-  e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
+  a.ws.partials = reinterpret_cast<float*>(ws_scratch(workspace));
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  e = coop_launch(kern, grid, WARPS * 32, args, smem, st, (thread_launch_flags() & GODE_LAUNCH_PDL_BWD) != 0);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }

@@ -175,6 +175,8 @@ __global__ void __launch_bounds__(WARPS * 32) sde_em_bwd_kernel(const __grid_con
   float* s_cwg = s_cwf + CW::kFloats;
   float* s_red = s_cwg + CW::kFloats;  // WARPS * P
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  SyncState ss;
+  ss.begin(p.ws.gs);
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   CW cwf, cwg;
@@ -237,19 +239,19 @@ __global__ void __launch_bounds__(WARPS * 32) sde_em_bwd_kernel(const __grid_con
       store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
     }
   }
-  // two parameter sets: reduce one after the other through the same workspace halves
+  // two parameter sets: reduce one after the other (same persistent counter, running target; separate partial rows)
   ReduceWs w1 = p.ws, w2 = p.ws;
-  w2.gs.counter = p.ws.gs.counter + 32;            // second 128-byte half of the counter slot
   w2.partials = p.ws.partials + (size_t)gridDim.x * S::P;
-  reduce_param_grads<D, H, L, WARPS>(af, s_red, w1, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(af, s_red, w1, ss, p.grad_params, lane, warp, tid);
   __syncthreads();
-  reduce_param_grads<D, H, L, WARPS>(ag, s_red, w2, p.grad_params + S::P, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS>(ag, s_red, w2, ss, p.grad_params + S::P, lane, warp, tid);
+  if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
 }
 
 // ---- host ----------------------------------------------------------------------------------------------------------------
 size_t sde_small_workspace_bytes(int D, int H) {
   const int P = H * D + H + D * H + D;
-  return align256(grid_sync_bytes(bwd_grid_cap())) + sizeof(float) * 2 * (size_t)P * (size_t)bwd_grid_cap();
+  return (size_t)GODE_SYNC_REGION_BYTES + sizeof(float) * 2 * (size_t)P * (size_t)bwd_grid_cap();
 }
 
 static int fill_grid(SdeArgs& a, const float* h_host, int n_steps, const int* out_step_host, const float* w0_host,
@@ -305,13 +307,10 @@ int sde_small_bwd(const float* states, const float* grad_out, const float* const
   int grid = (B + per_cta - 1) / per_cta;
   if (grid > cap) grid = cap;
   if (ws_bytes < sde_small_workspace_bytes(D, H)) return GODE_ERR_WORKSPACE;
-  const size_t slots = align256(grid_sync_bytes(bwd_grid_cap()));
   grid_sync_bind(a.ws.gs, workspace);
-  a.ws.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + slots);
-  cudaError_t e = cudaMemsetAsync(workspace, 0, grid_sync_bytes(grid), st);
-  if (e != cudaSuccess) return -(1000 + (int)e);
+  a.ws.partials = reinterpret_cast<float*>(ws_scratch(workspace));
   void* args[] = {(void*)&a};
-  e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
   if (e != cudaSuccess) return -(1000 + (int)e);
   return launch_status();
 }

@@ -281,7 +281,7 @@ __device__ __forceinline__ void regather(const BwdLines<D, H, L>& ln, int l, con
 //    the grid: each warp sums its columns over all rows with a fixed tree and writes them.  All warps work in
 //    parallel and the order of every floating-point addition is fixed by (grid, block) alone -> bit-reproducible.
 struct ReduceWs {
-  GridSyncWs gs;    // zeroed by the host wrapper before launch
+  GridSyncWs gs;    // persistent sync region (grid_sync.cuh); the calling kernel owns the SyncState and its finish()
   float* partials;  // [gridDim.x][P]
   // data-parallel exchange fused into the tail of the reduction (w_world > 1, see reduce_param_grads): every rank's
   // buffer [2 parities][w_world][P] of tagged 64-bit words, peer-mapped; w_ctr: cumulative launch count in device memory
@@ -306,8 +306,8 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 
 template <int D, int H, int L, int WARPS>
 __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float* smem_red /* [WARPS][P] */,
-                                                   const ReduceWs& ws, float* __restrict__ grad_params, int lane,
-                                                   int warp, int tid) {
+                                                   const ReduceWs& ws, SyncState& ss, float* __restrict__ grad_params,
+                                                   int lane, int warp, int tid) {
   using S = Shape<D, H, L>;
   constexpr int P = S::P;
   constexpr int NT = WARPS * 32;
@@ -352,8 +352,7 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
   }
   const bool xchg = ws.w_world > 1;
   const unsigned int wtag = xchg ? *reinterpret_cast<volatile unsigned int*>(ws.w_ctr) + 1u : 0u;  // read before the barrier
-  unsigned int epoch = 0;
-  grid_barrier(ws.gs, epoch);
+  grid_barrier(ws.gs, ss);
   if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;  // every thread of the grid has read it
   // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
   // in order, then a shuffle tree.  No block-level synchronisation.

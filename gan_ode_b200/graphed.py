@@ -26,10 +26,25 @@ _api = importlib.import_module(__package__ + ".odeint")  # the module, not the r
 __all__ = ["GraphedSolveStep"]
 
 
+def _flat_param_grads(gs):
+    """The flat [W1|b1|W2|b2] gradient.  The backward kernels write ONE flat buffer and hand autograd views of it; when the
+    views are still those (same base, back to back) the base is returned as it is — no concatenation kernel."""
+    base = getattr(gs[0], "_base", None)
+    if base is not None and base.dim() == 1 and all(getattr(g, "_base", None) is base for g in gs):
+        off = gs[0].storage_offset()
+        ok = True
+        for g in gs:
+            ok = ok and g.is_contiguous() and g.storage_offset() == off
+            off += g.numel()
+        if ok:
+            return base[gs[0].storage_offset() - base.storage_offset():off - base.storage_offset()]
+    return torch.cat([g.reshape(-1) for g in gs])
+
+
 class GraphedSolveStep:
     def __init__(self, func, batch: int, t: torch.Tensor, *, method: Optional[str] = None, rtol=1e-7, atol=1e-9,
                  adjoint: bool = True, options: Optional[dict] = None, device=None,
-                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3):
+                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = True):
         W1, _, _, _ = _api.recognise_field(func)
         D = W1.shape[1]
         dev = torch.device(device) if device is not None else W1.device
@@ -60,16 +75,23 @@ class GraphedSolveStep:
         self.grads = None
         self.log = None
 
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
+        # In this graph the kernel right before the backward IS the matching forward (nothing in between writes the weights
+        # or the upstream gradient), so the backward may be a programmatic dependent launch (config.pdl).
+        prev_pdl = _api.config.pdl
+        _api.config.pdl = bool(pdl)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
                 self._body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._body()
+        finally:
+            _api.config.pdl = prev_pdl
         self.stream = torch.cuda.current_stream(dev)
 
     def _body(self):
@@ -80,7 +102,7 @@ class GraphedSolveStep:
         grads = torch.autograd.grad(sol, [self.y0] + self.params, self.grad_traj)
         self.traj, self.grads = sol.detach(), grads
         if "param_grads" in self.host:
-            self.host["param_grads"].copy_(torch.cat([g.reshape(-1) for g in grads[1:]]), non_blocking=True)
+            self.host["param_grads"].copy_(_flat_param_grads(grads[1:]), non_blocking=True)
         if "grad_y0" in self.host:
             self.host["grad_y0"].copy_(grads[0], non_blocking=True)
         if "traj" in self.host:

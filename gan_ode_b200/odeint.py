@@ -56,6 +56,11 @@ class _Config:
     grad_exchange = None
     # NVTX ranges ("gode.<solver>.fwd" / ".bwd") around the boundary calls, for `ncu --nvtx` / timeline tools; off by default
     nvtx = False
+    # Programmatic dependent launch of the rk4 / dopri5 backward kernels (GODE_LAUNCH_PDL_BWD): the backward's weight-staging
+    # prologue overlaps the tail of the kernel enqueued just before it on the stream.  Opt-in, because the caller must
+    # guarantee that that kernel does not write the ODEFunc weights — true when it is the matching forward (GraphedSolveStep
+    # sets it for its own capture), not true in general (e.g. an optimiser step right before a backward).
+    pdl = False
 
 
 config = _Config()
@@ -145,6 +150,46 @@ def _stream() -> int:
     if _raw_stream is not None:
         return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+# ---- persistent workspaces (include/gode.h "WORKSPACES ARE PERSISTENT") -----------------------------------------------------
+# The front of every workspace is the kernels' grid-synchronisation region; it is zero-filled ONCE and then reused by every
+# launch ordered on the same stream, so no memset is enqueued per call.  One workspace per (device, stream) for eager calls; one
+# per (device, capture) while a CUDA graph is being captured, taken from a small pool of workspaces that were zero-filled
+# ahead of time (a capture cannot run an uncaptured memset; if the pool is empty the workspace is zero-filled INSIDE the capture,
+# which is correct and costs one memset node per replay).  Launches that may run concurrently never share a workspace.
+_WS_DEFAULT = 8 << 20
+_WS_SPARES = 4
+_ws_cache = {}    # key -> uint8 tensor
+_ws_spare = {}    # device index -> [zero-filled tensors of _WS_DEFAULT bytes]
+_cap_id = C.c_ulonglong(0)
+
+
+def _new_ws(device, nbytes):
+    return torch.zeros(max(int(nbytes), _WS_DEFAULT), dtype=torch.uint8, device=device)
+
+
+def _workspace(device, nbytes):
+    """(tensor, pointer) of the persistent workspace of the current stream / the current capture, at least `nbytes` long."""
+    L = _lib.lib()
+    st = _stream()
+    capturing = L.gode_stream_capture_id(st, C.byref(_cap_id)) == 1
+    key = (device.index, "cap", _cap_id.value) if capturing else (device.index, st)
+    ws = _ws_cache.get(key)
+    if ws is not None and ws.numel() >= nbytes:
+        return ws
+    spares = _ws_spare.setdefault(device.index, [])
+    if capturing:
+        ws = spares.pop() if (spares and nbytes <= _WS_DEFAULT) else _new_ws(device, nbytes)   # else: memset node in the graph
+    else:
+        ws = _new_ws(device, nbytes)
+        while len(spares) < _WS_SPARES:
+            spares.append(_new_ws(device, _WS_DEFAULT))
+        if len(_ws_cache) > 256:      # streams come and go: forget eager entries (captured graphs keep theirs alive below)
+            for k in [k for k in _ws_cache if len(k) == 2]:
+                del _ws_cache[k]
+    _ws_cache[key] = ws
+    return ws
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -361,7 +406,7 @@ class _Rk4(torch.autograd.Function):
         n_pad = (n_param + 3) & ~3
         gbuf = torch.empty(n_pad + B * D, dtype=torch.float32, device=buf.device)
         grad_p, grad_y0 = gbuf[:n_param], gbuf[n_pad:].view(B, D)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=buf.device)
+        ws = _workspace(buf.device, ws_bytes)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
         # Wide field (D=64, H=256) in bf16 mode: the continuous adjoint runs on tcgen05 too (csrc/tc_rk4_adj_wide.cu).
@@ -376,6 +421,9 @@ class _Rk4(torch.autograd.Function):
                 bwd_prec = _lib.PREC["bf16"]
         ex = config.grad_exchange
         fused = (ex is not None and not meta.get("method", 0) and bwd_prec == _lib.PREC["fp32"] and (D, H) == (16, 16))
+        pdl = config.pdl
+        if pdl:
+            L.gode_set_thread_launch_flags(_lib.LAUNCH_PDL_BWD)
         if fused:    # all-reduce over ranks inside the kernel's reduction tail (NVLink peer memory)
             xs = ex.struct(n_param)
             rc = L.gode_rk4_bwd_world(1 if meta["adjoint"] else 0, buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(),
@@ -390,6 +438,8 @@ class _Rk4(torch.autograd.Function):
             rc = fn(buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(), W2c.data_ptr(), b2c.data_ptr(), dt_ptr,
                     dt_dev, B, D, H, T, bwd_prec, meta["layout"], grad_y0.data_ptr(), grad_p.data_ptr(),
                     ws.data_ptr(), ws_bytes, _stream())
+        if pdl:
+            L.gode_set_thread_launch_flags(0)
         if rc:
             _lib.check(rc, "gode_rk4_bwd")
         needs = ctx.needs_input_grad
@@ -544,7 +594,7 @@ class _Dopri5(torch.autograd.Function):
         ckpt = torch.empty((max(kc, 1), B, D), dtype=torch.float32, device=dev) if keep else None
         acc = torch.empty(2 * max(kc, 1), dtype=torch.float64, device=dev) if keep else None
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(dev, ws_bytes)
         tarr = meta["t64"]
         args = (_ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
                 meta["layout"], _ptr(buf), base, base + 64, base + 64 + 8 * cap, base + 64 + 16 * cap, base + 64 + 20 * cap,
@@ -583,16 +633,23 @@ class _Dopri5(torch.autograd.Function):
         grad_y0 = torch.empty((B, D), dtype=torch.float32, device=ckpt.device)
         grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
+        ws = _workspace(ckpt.device, ws_bytes)
         args = (_ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
                 meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
                 C.c_float(meta["opts"].fsign), _ptr(grad_y0), _ptr(grad_p), _ptr(ws), ws_bytes)
         ex = config.grad_exchange
+        pdl = config.pdl
+        if pdl:
+            L.gode_set_thread_launch_flags(_lib.LAUNCH_PDL_BWD)
         if ex is not None:   # the all-reduce over ranks happens inside the kernel's reduction tail (NVLink peer memory)
             xs = ex.struct(grad_p.numel())
-            _lib.check(L.gode_dopri5_backprop_bwd_world(*args, C.byref(xs), _stream()), "gode_dopri5_backprop_bwd_world")
+            rc = L.gode_dopri5_backprop_bwd_world(*args, C.byref(xs), _stream())
         else:
-            _lib.check(L.gode_dopri5_backprop_bwd(*args, _stream()), "gode_dopri5_backprop_bwd")
+            rc = L.gode_dopri5_backprop_bwd(*args, _stream())
+        if pdl:
+            L.gode_set_thread_launch_flags(0)
+        if rc:
+            _lib.check(rc, "gode_dopri5_backprop_bwd")
         needs = ctx.needs_input_grad
         gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6], reduced=ex is not None)
         return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
@@ -629,7 +686,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
         opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
         opts.ckpt_capacity = 0
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(dev, ws_bytes)
         tarr = meta["t64"]
         _lib.check(L.gode_dopri5_fwd(
             _ptr(y0c), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), tarr.ctypes.data, B, D, H, T, C.byref(opts),
@@ -662,7 +719,7 @@ class _Dopri5Adjoint(torch.autograd.Function):
         raw = torch.zeros(_log_layout(cap), dtype=torch.uint8, device=dev)
         base = raw.data_ptr()
         ws_bytes = L.gode_dopri5_adjoint_workspace_bytes(B, D, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        ws = _workspace(dev, ws_bytes)
         rc = L.gode_dopri5_adjoint_bwd(
             _ptr(buf), _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
             meta["layout"], C.byref(ao), meta["param_mask"], _ptr(grad_y0), _ptr(grad_p), base, base + 64 + 8 * cap, base + 64 + 16 * cap,
@@ -771,7 +828,7 @@ class _Dopri5Traj(torch.autograd.Function):
         grad_y0 = torch.empty((B, D), dtype=torch.float32, device=ckpt.device)
         grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
         ws_bytes = L.gode_bwd_workspace_bytes(B, D, H)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=ckpt.device)
+        ws = _workspace(ckpt.device, ws_bytes)
         _lib.check(L.gode_dopri5_traj_backprop_bwd(
             _ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T, meta["layout"],
             hdr.data_ptr(), counts[0].data_ptr(), _ptr(ckpt), acc[0].data_ptr(), acc[1].data_ptr(), kc,

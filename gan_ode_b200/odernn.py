@@ -113,7 +113,7 @@ class _OdeRnn(torch.autograd.Function):
         acc = (torch.empty((F, 2, max(kc, 1)) + ((B,) if per_traj else ()), dtype=torch.float64, device=dev)) if keep else None
         n_acc = torch.empty((F + 1, B), dtype=torch.int32, device=dev) if per_traj else None
         wsb = L.gode_odernn_workspace_bytes(B, D, H)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ws = _api._workspace(dev, wsb)
         _lib.check(L.gode_odernn_fwd(*[v.data_ptr() for v in ts], B, D, H, F, C.byref(opts), codes.data_ptr(),
                                      seg.data_ptr(), logs.data_ptr(), _ptr(ckpt), _ptr(acc), _ptr(n_acc), ws.data_ptr(), wsb,
                                      _stream()),
@@ -142,7 +142,7 @@ class _OdeRnn(torch.autograd.Function):
         gode_, ggru = torch.empty(P1, dtype=torch.float32, device=dev), torch.empty(P2, dtype=torch.float32, device=dev)
         scratch = torch.empty(3 * B * D + F * P1, dtype=torch.float32, device=dev)
         wsb = L.gode_odernn_workspace_bytes(B, D, H)
-        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        ws = _api._workspace(dev, wsb)
         o = ctx.meta["opts"]
         _lib.check(L.gode_odernn_bwd(g.data_ptr(), eps.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                      w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), B, D, H, F,

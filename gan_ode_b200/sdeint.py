@@ -131,7 +131,7 @@ class _SdeEM(torch.autograd.Function):
         grad_y0 = torch.empty((B, D), dtype=torch.float32, device=states.device)
         grad_p = torch.empty(2 * P, dtype=torch.float32, device=states.device)
         ws_bytes = L.gode_sde_workspace_bytes(B, D, H)
-        wsp = torch.empty(ws_bytes, dtype=torch.uint8, device=states.device)
+        wsp = _api._workspace(states.device, ws_bytes)
         dW = meta["dW"]
         rc = L.gode_sde_em_bwd(states.data_ptr(), g.data_ptr(), _ptrs(ws[:4]), _ptrs(ws[4:]), h.ctypes.data, n_steps,
                                out_step.ctypes.data, w0.ctypes.data, w1.ctypes.data, B, D, H, T,

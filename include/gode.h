@@ -20,6 +20,12 @@
  *  - every call is asynchronous on `stream` (a cudaStream_t), holds no global mutable state,
  *    never synchronises the device, and allocates nothing: outputs and workspaces come from
  *    the caller (PyTorch's caching allocator on the Python side).
+ *  - WORKSPACES ARE PERSISTENT (v0.2): the first GODE_SYNC_REGION_BYTES of every `workspace`
+ *    argument are the grid-synchronisation region.  The owner zero-fills it ONCE after allocation
+ *    (gode_workspace_init) and may then pass the same workspace to any number of calls that are
+ *    ordered on one stream; kernels leave it ready for the next launch (tags keep counting across
+ *    launches), so no memset is enqueued per call.  Never share one workspace between launches
+ *    that can run concurrently (different streams, concurrently replayed graphs).
  *  - return value: 0 OK; <0 argument / capability error (gode_strerror); launch failures are
  *    returned as -(1000 + cudaError_t).  Solver conditions that are only known on the device
  *    (dt underflow, non-finite state, step budget exhausted, checkpoint overflow) are written
@@ -77,6 +83,15 @@ enum {
 };
 
 #define GODE_MAX_HOST_STEPS 255
+#define GODE_SYNC_REGION_BYTES (256 * 1024) /* persistent grid-sync region at the front of every workspace */
+
+/* per-thread launch flags (gode_set_thread_launch_flags) */
+enum {
+  GODE_LAUNCH_PDL_BWD = 1 /* backward kernels are launched with programmatic stream serialisation: their
+                             weight-staging prologue may overlap the tail of the kernel enqueued just before
+                             them on the stream.  The caller guarantees that that kernel does not write the
+                             weights (it normally is the matching forward).                               */
+};
 
 /* Step log of one adaptive solve, device resident, written by the forward kernel and read by the
  * backward kernel (no host round trip).  One entry per ATTEMPTED step in attempt order. */
@@ -110,6 +125,13 @@ typedef struct GodeAdaptiveOpts {
 /* ---- introspection ------------------------------------------------------------------------- */
 const char* gode_strerror(int code);
 const char* gode_version(void);
+/* zero-fill the sync region of a freshly allocated workspace (once; see "WORKSPACES ARE PERSISTENT") */
+int gode_workspace_init(void* workspace, size_t ws_bytes, gode_stream_t stream);
+/* capture state of `stream`: returns 1 and the capture's unique id while the stream is being captured into a CUDA
+ * graph, 0 otherwise (<0: error).  Hosts key persistent workspaces by it: one workspace per captured graph. */
+int gode_stream_capture_id(gode_stream_t stream, unsigned long long* id_out);
+/* launch flags of the CALLING THREAD (thread-local; default 0), OR of GODE_LAUNCH_*; returns the previous value */
+int gode_set_thread_launch_flags(int flags);
 /* 1 if a kernel exists for (D,H) at this precision, else 0 */
 int gode_supported(int D, int H, int precision);
 /* number of floats in the flat parameter vector [W1|b1|W2|b2] = H*D + H + D*H + D */
