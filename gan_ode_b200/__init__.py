@@ -5,10 +5,10 @@ Public surface = the solver signatures the reference imports:
 or, without touching the reference files, `gan_ode_b200.install_shims()` registers this package as
 `torchdiffeq` / `torchsde` in sys.modules so `from torchdiffeq import odeint_adjoint as odeint` resolves here.
 """
-from .odeint import config, last_adjoint_log, last_step_log, odeint, odeint_adjoint, recognise_field  # noqa: F401
+from .odeint import check_status, config, last_adjoint_log, last_step_log, odeint, odeint_adjoint, recognise_field  # noqa: F401
 from ._lib import GodeError  # noqa: F401
 from .graphed import GraphedSolveStep  # noqa: F401
-from .sdeint import PhiloxBrownian, TableBrownian, sdeint, sdeint_adjoint  # noqa: F401
+from .sdeint import GridBrownian, PhiloxBrownian, TableBrownian, adjoint_grid, sdeint, sdeint_adjoint  # noqa: F401
 from .odernn import gru_jump, odernn_codes  # noqa: F401
 
 __version__ = "0.1.0"

@@ -51,6 +51,7 @@ _SIGS = {
     "gode_workspace_init": (_I, [_P, C.c_size_t, _P]),
     "gode_stream_capture_id": (_I, [_P, C.POINTER(C.c_ulonglong)]),
     "gode_set_thread_launch_flags": (_I, [_I]),
+    "gode_set_status_mailbox": (_I, [_P]),
     "gode_supported": (_I, [_I, _I, _I]),
     "gode_param_count": (_I, [_I, _I]),
     "gode_rk4_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
@@ -84,6 +85,9 @@ _SIGS = {
     "gode_allreduce_p2p": (_I, [_P, _I, _P, _P, _I, _I, _I, _P, _P]),
     "gode_sde_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_sde_em_fwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P]),
+    "gode_sde_em_fwd_cells": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P]),
+    "gode_sde_adjoint_bwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I,
+                                  _P, _P, _P, C.c_size_t, _P]),
     "gode_sde_em_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, C.c_uint64, C.c_int64, _I, _P, _P, _P,
                              C.c_size_t, _P]),
 }

@@ -4,6 +4,8 @@
 using namespace gode;
 
 namespace gode {
+static int32_t* g_status_mailbox = nullptr;   // set once by the host before the first solve, read-only afterwards
+int32_t* status_mailbox() { return g_status_mailbox; }
 int& thread_launch_flags() {
   static thread_local int flags = 0;
   return flags;
@@ -27,6 +29,11 @@ int gode_stream_capture_id(gode_stream_t stream, unsigned long long* id_out) {
   if (e != cudaSuccess) { (void)cudaGetLastError(); return -(1000 + (int)e); }
   if (id_out) *id_out = id;
   return st == cudaStreamCaptureStatusActive ? 1 : 0;
+}
+
+int gode_set_status_mailbox(int32_t* host_mapped) {
+  gode::g_status_mailbox = host_mapped;
+  return GODE_OK;
 }
 
 int gode_set_thread_launch_flags(int flags) {
@@ -301,6 +308,36 @@ int gode_sde_em_fwd(const float* y0, const float* const* drift, const float* con
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return sde_small_fwd(y0, drift, diffusion, h_host, n_steps, out_step_host, w0_host, w1_host, B, D, H, T, dW, seed,
                        traj_offset, out_layout, frames, states, (cudaStream_t)stream);
+}
+
+int gode_sde_em_fwd_cells(const float* y0, const float* const* drift, const float* const* diffusion, const float* h_host,
+                          int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host,
+                          const int* fwd_lo_host, const float* cell_sqrt_host, int R, int B, int D, int H, int T,
+                          const float* dW_cells, uint64_t seed, int64_t traj_offset, int out_layout, float* frames,
+                          gode_stream_t stream) {
+  if (!y0 || bad_nets(drift, diffusion) || !h_host || !out_step_host || !w0_host || !w1_host || !fwd_lo_host ||
+      !cell_sqrt_host || !frames || B <= 0 || T < 2 || n_steps < 1 || R < 1 ||
+      (out_layout != GODE_LAYOUT_TBD && out_layout != GODE_LAYOUT_BTD))
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return sde_small_fwd(y0, drift, diffusion, h_host, n_steps, out_step_host, w0_host, w1_host, B, D, H, T, dW_cells, seed,
+                       traj_offset, out_layout, frames, nullptr, (cudaStream_t)stream, fwd_lo_host, cell_sqrt_host, R);
+}
+
+int gode_sde_adjoint_bwd(const float* frames, const float* grad_frames, const float* const* drift,
+                         const float* const* diffusion, int n_rev, const float* h_rev_host, const int* rev_lo_host,
+                         const int* rev_hi_host, const int* ibeg_host, const int* iend_host, const float* cell_sqrt_host,
+                         int R, int B, int D, int H, int T, const float* dW_cells, uint64_t seed, int64_t traj_offset,
+                         int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                         gode_stream_t stream) {
+  if (!frames || !grad_frames || bad_nets(drift, diffusion) || !h_rev_host || !rev_lo_host || !rev_hi_host || !ibeg_host ||
+      !iend_host || !cell_sqrt_host || !grad_y0 || !grad_params || !workspace || B <= 0 || T < 2 || n_rev < 1 || R < 1 ||
+      (layout != GODE_LAYOUT_TBD && layout != GODE_LAYOUT_BTD))
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return sde_small_adjoint_bwd(frames, grad_frames, drift, diffusion, n_rev, h_rev_host, rev_lo_host, rev_hi_host, ibeg_host,
+                               iend_host, cell_sqrt_host, R, B, D, H, T, dW_cells, seed, traj_offset, layout, grad_y0,
+                               grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
 int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* const* drift,

@@ -36,6 +36,7 @@ struct Dp5AdjArgs {
   const float *traj, *grad_traj, *W1, *b1, *W2, *b2;
   float *grad_y0, *grad_params;
   GodeStepLog* log;
+  int32_t* mailbox;  // mapped host int (gode_set_status_mailbox) or null
   double* att_dt; float* att_er; uint8_t* att_acc;  // optional per-attempt log, all intervals concatenated
   GridSyncWs gs;
   float* partials;  // [grid][VT]
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
 #ifdef GODE_ADJ_TIMING
   if (logger) printf("adj timing: attempts %d  stages(other) %lld  reduce %lld  rest %lld | fwd %lld vjp %lld theta %lld cycles/attempt\n", n_att, tc_stage / max(n_att, 1), tc_red / max(n_att, 1), tc_rest / max(n_att, 1), tc_f / max(n_att, 1), tc_v / max(n_att, 1), tc_t / max(n_att, 1));
 #endif
+  if (logger && status != 0 && p.mailbox) *reinterpret_cast<volatile int32_t*>(p.mailbox) = status;
   if (logger && p.log) {
     p.log->status = status;
     p.log->n_attempts = n_att;
@@ -649,7 +651,7 @@ int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const fl
   if (ws_bytes < dopri5_small_adjoint_workspace_bytes(B, D, H)) return GODE_ERR_WORKSPACE;
   Dp5AdjArgs a{};
   a.traj = traj; a.grad_traj = grad_traj; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2;
-  a.grad_y0 = grad_y0; a.grad_params = grad_params; a.log = log; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
+  a.grad_y0 = grad_y0; a.grad_params = grad_params; a.log = log; a.mailbox = status_mailbox(); a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
   a.o = *opts; a.B = B; a.T = T; a.layout = layout; a.param_mask = param_mask;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
   // 8 lanes per trajectory (32 per CTA) has the shortest stage chain and wins while its CTAs get an SM each; beyond that

@@ -22,6 +22,7 @@ struct Dp5Args {
   float* grad_params;
   ReduceWs ws;
   GodeStepLog* log;
+  int32_t* mailbox;           // mapped host int (gode_set_status_mailbox) or null: receives a non-zero status
   double* att_t0; double* att_dt; float* att_er; uint8_t* att_acc;
   float* ckpt; double* acc_t0; double* acc_dt;
   GridSyncWs gs;              // persistent grid all-reduce region (grid_sync.cuh)
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   }
   if (logger) {
     p.log->status = status;
+    if (status != 0 && p.mailbox) *reinterpret_cast<volatile int32_t*>(p.mailbox) = status;
     p.log->n_attempts = n_att;
     p.log->n_accepted = n_acc;
     p.log->nfe = nfe;
@@ -567,7 +569,7 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
     a.w_rank = world->rank; a.w_world = world->world; a.w_total_B = world->total_B;
     a.w_slots = reinterpret_cast<unsigned long long* const*>(world->slots_dev); a.w_launch_ctr = world->launch_ctr;
   }
-  a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.log = log;
+  a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.log = log; a.mailbox = status_mailbox();
   a.att_t0 = att_t0; a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc;
   a.ckpt = ckpt; a.acc_t0 = acc_t0; a.acc_dt = acc_dt;
   a.o = *opts; a.B = B; a.T = T; a.layout = out_layout;

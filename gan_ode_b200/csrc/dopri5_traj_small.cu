@@ -21,6 +21,7 @@ struct Dp5TrajArgs {
   float* grad_params;
   ReduceWs ws;
   GodeStepLog* log;       // status = OR over trajectories; counts = max over trajectories
+  int32_t* mailbox;       // mapped host int (gode_set_status_mailbox) or null
   int32_t* n_acc;         // (B)
   int32_t* n_att;         // (B)
   double* att_dt; float* att_er; uint8_t* att_acc;   // (log_capacity, B) or null
@@ -196,7 +197,10 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_traj_fwd_kernel(const __gri
     if (valid && l == 0) { p.n_acc[b] = n_acc; p.n_att[b] = n_att; }
     if (valid) { st_or |= status; max_att = max(max_att, n_att); max_acc = max(max_acc, n_acc); max_nfe = max(max_nfe, nfe); }
   }
-  if (st_or) atomicOr(&p.log->status, st_or);
+  if (st_or) {
+    atomicOr(&p.log->status, st_or);
+    if (p.mailbox && (threadIdx.x & 31) == 0) *reinterpret_cast<volatile int32_t*>(p.mailbox) = st_or;
+  }
   atomicMax(&p.log->n_attempts, max_att);
   atomicMax(&p.log->n_accepted, max_acc);
   atomicMax(&p.log->nfe, max_nfe);
@@ -355,6 +359,7 @@ int dopri5_traj_small_fwd(const float* y0, const float* W1, const float* b1, con
   if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
   Dp5TrajArgs a{};
   a.y0 = y0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = traj; a.log = log; a.n_acc = n_acc; a.n_att = n_att;
+  a.mailbox = status_mailbox();
   a.att_dt = att_dt; a.att_er = att_er; a.att_acc = att_acc; a.ckpt = ckpt; a.acc_t0 = acc_t0; a.acc_dt = acc_dt;
   a.o = *opts; a.B = B; a.T = T; a.layout = out_layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];

@@ -40,6 +40,8 @@ inline char* ws_scratch(void* workspace) { return reinterpret_cast<char*>(worksp
 
 // launch flags of the calling thread (gode_set_thread_launch_flags)
 int& thread_launch_flags();
+// process-wide status mailbox in mapped host memory (gode_set_status_mailbox); null = off
+int32_t* status_mailbox();
 
 // Cooperative launch; with `pdl` also programmatic stream serialisation (the kernel must call griddep_wait() before it
 // touches anything the previous kernel on the stream wrote).  If the driver refuses the attribute pair, the plain
@@ -108,7 +110,12 @@ size_t sde_small_workspace_bytes(int D, int H);
 int sde_small_fwd(const float* y0, const float* const* fw, const float* const* gw, const float* h_host, int n_steps,
                   const int* out_step_host, const float* w0_host, const float* w1_host, int B, int D, int H, int T,
                   const float* dW, unsigned long long seed, long long traj_offset, int layout, float* out, float* states,
-                  cudaStream_t st);
+                  cudaStream_t st, const int* fwd_lo_host = nullptr, const float* cell_sqrt_host = nullptr, int R = 0);
+int sde_small_adjoint_bwd(const float* frames, const float* grad_out, const float* const* fw, const float* const* gw,
+                          int n_rev, const float* h_rev_host, const int* rev_lo_host, const int* rev_hi_host,
+                          const int* ibeg_host, const int* iend_host, const float* cell_sqrt_host, int R, int B, int D, int H,
+                          int T, const float* dW, unsigned long long seed, long long traj_offset, int layout, float* grad_y0,
+                          float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
 int sde_small_bwd(const float* states, const float* grad_out, const float* const* fw, const float* const* gw,
                   const float* h_host, int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host,
                   int B, int D, int H, int T, const float* dW, unsigned long long seed, long long traj_offset, int layout,

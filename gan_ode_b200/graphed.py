@@ -116,5 +116,8 @@ class GraphedSolveStep:
         self.graph.replay()
 
     def sync(self):
+        """Wait for the replay and return the pinned host buffers.  Raises torchdiffeq's solver asserts if the solve failed
+        on the device (status mailbox; a plain host-memory read after the synchronisation)."""
         torch.cuda.current_stream(self.device).synchronize()
+        _api.check_status()
         return self.host

@@ -35,7 +35,7 @@ import torch.nn as nn
 from . import _lib
 from ._lib import GodeAdaptiveOpts, GodeError, GodeStepLog
 
-__all__ = ["odeint", "odeint_adjoint", "last_step_log", "StepLog", "recognise_field", "config"]
+__all__ = ["odeint", "odeint_adjoint", "last_step_log", "StepLog", "recognise_field", "config", "check_status"]
 
 
 class _Config:
@@ -550,6 +550,39 @@ def last_step_log() -> Optional[StepLog]:
     return _LAST_LOG[0]
 
 
+# ---- status mailbox: failed adaptive solves are loud without a synchronisation per call ----------------------------------------
+# One int in pinned (device-mapped) host memory, registered with the library once.  A solve that ends with a non-zero status
+# word also stores it there (nothing is written on the success path).  The host looks at it — a plain memory read — at every
+# entry into the solver API, in the backward of the adaptive solves, and at the natural synchronisation points
+# (StepLog reads, GraphedSolveStep.sync, gan_ode_b200.check_status()).  So a failed forward is reported at the latest by the
+# next call into this package, instead of only poisoning the gradients with NaN.
+_mailbox = [None, None]   # (pinned tensor, numpy view)
+
+
+def _mailbox_view():
+    mb = _mailbox[1]
+    if mb is None and _mailbox[0] is None and torch.cuda.is_available():
+        t = torch.zeros(16, dtype=torch.int32).pin_memory()
+        _lib.lib().gode_set_status_mailbox(t.data_ptr())   # UVA: pinned host memory is addressable from every device as is
+        _mailbox[0], _mailbox[1] = t, t.numpy()
+        mb = _mailbox[1]
+    return mb
+
+
+def check_status():
+    """Raise (torchdiffeq's assert texts) if any adaptive solve launched so far has ended with a solver failure that has not
+    been reported yet.  Never synchronises: call it after a synchronisation of your own to be sure nothing is in flight."""
+    mb = _mailbox[1]
+    if mb is not None and mb[0]:
+        st = int(mb[0])
+        mb[0] = 0
+        try:
+            raise_for_status(st)
+        except (AssertionError, GodeError) as e:
+            raise type(e)("{} (reported by the device for an earlier adaptive solve; gradients computed from it are NaN)"
+                          .format(e)) from None
+
+
 def raise_for_status(status: int):
     """torchdiffeq's solver asserts, raised from the device status word."""
     if status & _lib.ST_NONFINITE:
@@ -623,9 +656,11 @@ class _Dopri5(torch.autograd.Function):
         if ckpt is None:
             raise GodeError("dopri5 forward ran without checkpoints (inputs did not require grad)")
         # No host sync by default (keeps fwd+bwd CUDA-graph capturable): a failed forward (status != 0, including
-        # checkpoint overflow) makes the backward kernel return NaN gradients; options['check'] raises eagerly.
+        # checkpoint overflow) makes the backward kernel return NaN gradients; options['check'] raises eagerly, and the
+        # status mailbox raises here if the forward has already finished, else at the next call into the package.
         if meta["check"]:
             raise_for_status(ctx.log.status)
+        check_status()
         T = meta["T"]
         _, B, D = ckpt.shape
         H = W1c.shape[0]
@@ -869,6 +904,8 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
     W1, b1, W2, b2 = recognise_field(func)
     _check_common(y0, t)
     _require_cuda(y0, weights=(W1, b1, W2, b2))
+    if _mailbox_view() is not None:
+        check_status()
     with _on_device(y0.device):
         return _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, (W1, b1, W2, b2))
 

@@ -130,6 +130,11 @@ int gode_workspace_init(void* workspace, size_t ws_bytes, gode_stream_t stream);
 /* capture state of `stream`: returns 1 and the capture's unique id while the stream is being captured into a CUDA
  * graph, 0 otherwise (<0: error).  Hosts key persistent workspaces by it: one workspace per captured graph. */
 int gode_stream_capture_id(gode_stream_t stream, unsigned long long* id_out);
+/* Status mailbox: ONE int in pinned, device-mapped HOST memory (set once per process, before the first solve; NULL turns
+ * it off).  Every adaptive solve whose device status word is non-zero (GODE_ST_*) also stores it there, so a host that
+ * does not synchronise per call still learns of a failed solve at its next natural check point by reading plain host
+ * memory — nothing is written on the success path. */
+int gode_set_status_mailbox(int32_t* host_mapped);
 /* launch flags of the CALLING THREAD (thread-local; default 0), OR of GODE_LAUNCH_*; returns the previous value */
 int gode_set_thread_launch_flags(int flags);
 /* 1 if a kernel exists for (D,H) at this precision, else 0 */
@@ -292,6 +297,29 @@ int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* 
                     const float* w0_host, const float* w1_host, int B, int D, int H, int T, const float* dW,
                     uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
                     void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* ---- f3: sdeint_adjoint with torchsde's stochastic adjoint (models/mocogan_sde.py:57-59, adjoint_method='euler') -------
+ * torchsde/_core/adjoint.py re-solves every output interval backwards in time with its own dt grid, so the Brownian
+ * path must answer increments over intervals that are not forward steps.  The path is sampled on CELLS = the union of the
+ * forward and reverse step times (host-built, fp32 time accumulation as torchsde): cell r carries an N(0, len_r) increment,
+ * Philox counter (traj_offset + b, r, d/4, 1) * cell_sqrt_host[r], or row r of dW_cells (R,B,D); a step's increment is
+ * the left-to-right sum of its cells.  fwd_lo_host[k] .. fwd_lo_host[k+1] are the cells of forward step k (n_steps+1 ints).
+ * The forward keeps nothing but its output frames. */
+int gode_sde_em_fwd_cells(const float* y0, const float* const* drift, const float* const* diffusion, const float* h_host,
+                          int n_steps, const int* out_step_host, const float* w0_host, const float* w1_host,
+                          const int* fwd_lo_host, const float* cell_sqrt_host, int R, int B, int D, int H, int T,
+                          const float* dW_cells, uint64_t seed, int64_t traj_offset, int out_layout, float* frames,
+                          gode_stream_t stream);
+/* The adjoint solve: for output interval i = T-1 .. 1 the reverse Euler steps [ibeg_host[i], iend_host[i]) (sizes
+ * h_rev_host[n], increment = cells [rev_lo_host[n], rev_hi_host[n]) in forward time) of the augmented state
+ * (y, a, theta_bar) with the Ito-corrected adjoint drift for diagonal noise (adjoint_sde.py::f_corrected_diagonal), then
+ * y <- frames[i-1], a += grad_frames[i-1].  grad_params: flat [drift | diffusion], overwritten.  workspace as gode_sde_em_bwd. */
+int gode_sde_adjoint_bwd(const float* frames, const float* grad_frames, const float* const* drift,
+                         const float* const* diffusion, int n_rev, const float* h_rev_host, const int* rev_lo_host,
+                         const int* rev_hi_host, const int* ibeg_host, const int* iend_host, const float* cell_sqrt_host,
+                         int R, int B, int D, int H, int T, const float* dW_cells, uint64_t seed, int64_t traj_offset,
+                         int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                         gode_stream_t stream);
 
 /* ---- a6: ODE-RNN sampler (models/mocogan_ode_rnn.py:40-54) ---------------------------------------------------- */
 /* The GRU jump h_out = GRUCell(x, h) of models/mocogan_ode_rnn.py:49 (nn.GRUCell semantics, models/mocogan.py:198:

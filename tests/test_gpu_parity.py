@@ -326,6 +326,67 @@ def test_device_gate_cpu_field_with_cuda_state_raises_before_launch():
     assert torch.isfinite(out).all()
 
 
+def test_failed_solve_is_reported_without_check_option():
+    """no options['check'], no synchronisation per call — a forward that exhausts max_num_steps (or overflows
+    its checkpoints) must still surface as torchdiffeq's AssertionError: at the next call into the package, or at
+    gode.check_status() after a synchronisation; the gradients of the failed solve are NaN, never silently truncated."""
+    _need_gpu()
+    gode.check_status()
+    f = clone_to(make_field(seed=1, scale=8.0), DEV)
+    y0 = torch.randn(16, 16, device=DEV, requires_grad=True)
+    sol = gode.odeint(f, y0, torch.tensor([0.0, 1.0]), method="dopri5", rtol=1e-5, atol=1e-5, options={"max_num_steps": 3})
+    torch.cuda.synchronize()
+    with pytest.raises(AssertionError, match="max_num_steps"):
+        gode.check_status()
+    gode.check_status()    # reported once
+    # checkpoint overflow: reported at the next entry into the solver API, and the gradients are NaN
+    sol = gode.odeint(f, y0, torch.tensor([0.0, 1.0]), method="dopri5", rtol=1e-5, atol=1e-5, options={"ckpt_capacity": 2})
+    torch.cuda.synchronize()
+    with pytest.raises(gode.GodeError, match="ckpt_capacity"):
+        sol.sum().backward()
+    torch.cuda._sleep(100_000_000)                # keep the device busy (~50 ms) so that the host is surely ahead of it
+    sol = gode.odeint(f, y0, torch.tensor([0.0, 1.0]), method="dopri5", rtol=1e-5, atol=1e-5, options={"ckpt_capacity": 2})
+    g, = torch.autograd.grad(sol.sum(), [y0])     # host ahead of the device: nothing to report yet
+    torch.cuda.synchronize()
+    with pytest.raises(gode.GodeError, match="ckpt_capacity"):
+        gode.odeint(f, y0, _t16(), method="rk4")
+    assert torch.isnan(g).all()
+    out = gode.odeint(f, y0, _t16(), method="rk4")   # healthy again
+    assert torch.isfinite(out).all()
+
+
+def test_persistent_workspace_across_kernels_and_grid_sizes():
+    """The grid-sync workspace is zero-filled once and reused by every launch on the stream (no memset per call): mixed
+    kernels and grid sizes, back to back, must keep reproducing their first results bit for bit."""
+    _need_gpu()
+    f = clone_to(make_field(seed=9, scale=2.0), DEV)
+    params = list(f.parameters())
+    cases = []
+    for B in (16, 4096, 300, 8192, 1):
+        torch.manual_seed(B)
+        cases.append((torch.randn(B, 16, device=DEV, requires_grad=True), torch.randn(16, B, 16, device=DEV)))
+
+    def run(y, g, which):
+        if which == 0:
+            sol = gode.odeint(f, y, _t16(), method="dopri5", rtol=1e-5, atol=1e-5)
+        elif which == 1:
+            sol = gode.odeint_adjoint(f, y, _t16(), method="rk4")
+        else:
+            sol = gode.odeint_adjoint(f, y, _t16(), method="dopri5", rtol=1e-5, atol=1e-5)
+        return [sol.detach().clone()] + [x.clone() for x in torch.autograd.grad(sol, [y] + params, g)]
+
+    first = {}
+    for rep in range(6):
+        for ci, (y, g) in enumerate(cases):
+            for which in range(3):
+                out = run(y, g, which)
+                key = (ci, which)
+                if key not in first:
+                    first[key] = out
+                else:
+                    assert all(torch.equal(a, b) for a, b in zip(out, first[key])), (rep, key)
+
+
 def test_unrecognised_field_raises():
     _need_gpu()
 
@@ -690,7 +751,10 @@ def test_sde_given_increments_matches_oracle(B, layout):
     dW = torch.randn(41, B, 16) * torch.from_numpy(h).sqrt().view(-1, 1, 1)
     ref_sol, ref_g = _sde_run(tsde.sdeint, sde, y0, ts, g, bm=tsde.TableBrownian(dW))
     out_sol, out_g = _sde_run(gode.sdeint_adjoint, sde_g, y0.to(DEV), ts, g.to(DEV),
-                              bm=gode.TableBrownian(dW.to(DEV)), adjoint_method="euler", options={"layout": layout})
+                              bm=gode.TableBrownian(dW.to(DEV)), adjoint_method="euler",
+                              options={"layout": layout, "adjoint": "discrete"})
+    with pytest.raises(NotImplementedError, match="TableBrownian"):   # forward-step increments cannot serve the reverse grid
+        gode.sdeint_adjoint(sde_g, y0.to(DEV), ts, bm=gode.TableBrownian(dW.to(DEV)), method="euler", dt=2.5e-2)
     assert out_sol.shape == (16, B, 16) and torch.equal(out_sol[0].cpu(), y0)
     assert rel_err(out_sol, ref_sol) <= TOL
     for a, b in zip(out_g, ref_g):
@@ -722,6 +786,73 @@ def test_sde_given_increments_at_config4_batch():
     assert elem_close(out_sol, ref_sol)[0] and rowwise_rel_err(out_sol, ref_sol) <= 5 * TOL, \
         (elem_close(out_sol, ref_sol), rowwise_rel_err(out_sol, ref_sol))
     _assert_grads(out_g, ref_g, ref64_g, names=["y0"] + [n for n, _ in sde.named_parameters()])
+
+
+@pytest.mark.parametrize("B,layout", [(1, "tbd"), (37, "btd"), (1024, "tbd"), (16384, "tbd")])
+def test_sde_stochastic_adjoint_matches_torchsde_restatement(B, layout):
+    """SURVEY §8 f3 — sdeint_adjoint as the reference calls it (models/mocogan_sde.py:57-59): forward on the cell grid and
+    torchsde's stochastic adjoint (45 reverse Euler steps of the Ito-corrected adjoint SDE) GIVEN the Brownian path, against
+    oracle/torchsde_restatement.py::sdeint_adjoint.  B = 16384 is BASELINE.json configs[4]'s batch."""
+    _need_gpu()
+    from gan_ode_b200.sdeint import adjoint_grid
+    from oracle import torchsde_restatement as tsde
+    sde, sde_g = _sde_pair(seed=B + 1)
+    ts = torch.linspace(0, 1, 16).float()
+    ag = adjoint_grid(ts, 2.5e-2)
+    assert ag.n_rev == 45 and ag.R == 79
+    y0 = torch.randn(B, 16)
+    g = torch.randn(16, B, 16)
+    times = torch.from_numpy(ag.times)
+    inc = torch.randn(ag.R, B, 16) * torch.from_numpy(ag.cell_sqrt).view(-1, 1, 1)
+    ref_sol, ref_g = _sde_run(tsde.sdeint_adjoint, sde, y0, ts, g, bm=tsde.GridBrownian(times, inc), adjoint_method="euler")
+    sde64 = clone_to(sde, "cpu", torch.float64)
+    _, ref64_g = _sde_run(tsde.sdeint_adjoint, sde64, y0.double(), ts, g.double(),
+                          bm=tsde.GridBrownian(times, inc.double()), adjoint_method="euler")
+    out_sol, out_g = _sde_run(gode.sdeint_adjoint, sde_g, y0.to(DEV), ts, g.to(DEV),
+                              bm=gode.GridBrownian(ag.times, inc.to(DEV)), adjoint_method="euler", options={"layout": layout})
+    assert out_sol.shape == (16, B, 16) and torch.equal(out_sol[0].cpu(), y0)
+    assert rel_err(out_sol, ref_sol) <= TOL
+    _assert_grads(out_g, ref_g, ref64_g, names=["y0"] + [n for n, _ in sde.named_parameters()])
+    # deterministic: the same call again is bit-identical
+    _, again = _sde_run(gode.sdeint_adjoint, sde_g, y0.to(DEV), ts, g.to(DEV),
+                        bm=gode.GridBrownian(ag.times, inc.to(DEV)), adjoint_method="euler", options={"layout": layout})
+    assert all(torch.equal(a, b) for a, b in zip(again, out_g))
+
+
+def test_sde_stochastic_adjoint_philox_cells_contract_and_sharding():
+    """Philox cells: counter (global trajectory, cell, d_block, stream = 1) * sqrt(cell length); the backward regenerates
+    them, so the CUDA result with a seed equals the CUDA/oracle result with the same path given as a table, and shards with
+    global trajectory offsets reproduce the full batch bit for bit (forward and gradients)."""
+    _need_gpu()
+    import numpy as np
+    from gan_ode_b200.sdeint import adjoint_grid
+    from oracle import torchsde_restatement as tsde
+    from oracle.philox import normals
+    sde, sde_g = _sde_pair(seed=8)
+    ts = torch.linspace(0, 1, 16).float()
+    ag = adjoint_grid(ts, 2.5e-2)
+    B, seed = 96, 0x0F1E2D3C4B5A6978
+    y0, g = torch.randn(B, 16), torch.randn(16, B, 16)
+    inc = np.zeros((ag.R, B, 16), dtype=np.float32)
+    for r in range(ag.R):
+        for blk in range(4):
+            inc[r, :, 4 * blk:4 * blk + 4] = normals(seed, np.arange(B), step=r, d_block=blk, stream=1) * ag.cell_sqrt[r]
+    inc = torch.from_numpy(inc)
+    ref_sol, ref_g = _sde_run(tsde.sdeint_adjoint, sde, y0, ts, g, bm=tsde.GridBrownian(torch.from_numpy(ag.times), inc),
+                              adjoint_method="euler")
+    out_sol, out_g = _sde_run(gode.sdeint_adjoint, sde_g, y0.to(DEV), ts, g.to(DEV), bm=gode.PhiloxBrownian(seed),
+                              adjoint_method="euler")
+    assert rel_err(out_sol, ref_sol) <= 2e-5
+    for a, b in zip(out_g, ref_g):
+        assert rel_err(a, b) <= 1e-4, rel_err(a, b)
+    halves = []
+    for lo, hi in ((0, 48), (48, 96)):
+        halves.append(_sde_run(gode.sdeint_adjoint, sde_g, y0[lo:hi].to(DEV), ts, g[:, lo:hi].to(DEV),
+                               bm=gode.PhiloxBrownian(seed, lo), adjoint_method="euler"))
+    assert torch.equal(torch.cat([halves[0][0], halves[1][0]], dim=1), out_sol)
+    assert torch.equal(torch.cat([halves[0][1][0], halves[1][1][0]], dim=0), out_g[0])
+    for k in range(1, 9):   # parameter gradients: sums over trajectories, equal up to the order of the additions
+        assert rel_err(halves[0][1][k] + halves[1][1][k], out_g[k]) <= 1e-5
 
 
 def test_sde_philox_stream_matches_cpu_contract_and_is_shard_invariant():

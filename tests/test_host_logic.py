@@ -150,3 +150,26 @@ def test_nvtx_wrapper_is_transparent_to_autograd():
     assert torch.equal(x.grad, torch.full((5,), 3.0))
     for cls in (api._Rk4, api._Dopri5, api._Dopri5Adjoint, api._Dopri5Traj):
         assert cls.forward.__name__ == "forward" and cls.backward.__name__ == "backward"
+
+
+def test_sde_adjoint_grid_matches_the_oracle_grids():
+    """gan_ode_b200.sdeint.adjoint_grid (host tables of gode_sde_em_fwd_cells / gode_sde_adjoint_bwd) against the oracle's
+    independently written grids: same cell times, same reverse steps, cells tile every step exactly."""
+    import numpy as np
+    from gan_ode_b200.sdeint import adjoint_grid
+    from oracle import torchsde_restatement as tsde
+    for ts, dt in ((torch.linspace(0, 1, 16).float(), 2.5e-2), (torch.tensor([0.0, 0.3, 0.35, 1.1]), 0.07)):
+        ag = adjoint_grid(ts, dt)
+        og = tsde.adjoint_time_grid(ts, dt).numpy()
+        assert ag.R == len(og) - 1 and np.abs(ag.times - og).max() == 0.0
+        fwd = tsde.step_grid(ts, dt)
+        assert len(fwd) == len(ag.fwd[0]) == len(ag.fwd_lo) - 1
+        for k, (a, b) in enumerate(fwd):
+            assert ag.times[ag.fwd_lo[k]] == float(a) and ag.times[ag.fwd_lo[k + 1]] == float(b)
+        rev = [(i, s0, s1) for i, pairs in tsde.reverse_step_grid(ts, dt) for s0, s1 in pairs]
+        assert len(rev) == ag.n_rev
+        for n, (i, s0, s1) in enumerate(rev):
+            assert ag.ibeg[i] <= n < ag.iend[i]
+            assert ag.times[ag.rev_hi[n]] == float(-s0) and ag.times[ag.rev_lo[n]] == float(-s1)
+            assert ag.h_rev[n] == np.float32(float(s1 - s0))
+        assert np.allclose(ag.cell_sqrt ** 2, np.diff(og), rtol=1e-6, atol=0)

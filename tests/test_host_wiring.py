@@ -17,7 +17,8 @@ api = importlib.import_module("gan_ode_b200.odeint")
 
 COMPUTE = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_fixed_fwd", "gode_fixed_adjoint_bwd",
            "gode_fixed_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd", "gode_dopri5_adjoint_bwd",
-           "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd", "gode_sde_em_fwd", "gode_sde_em_bwd", "gode_odernn_fwd",
+           "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd", "gode_sde_em_fwd", "gode_sde_em_bwd", "gode_sde_em_fwd_cells",
+           "gode_sde_adjoint_bwd", "gode_odernn_fwd",
            "gode_odernn_bwd", "gode_gru_jump_fwd", "gode_gru_jump_bwd")
 
 
@@ -180,8 +181,20 @@ def test_sde_call_carries_the_torchsde_step_grid_and_the_philox_contract(wired):
     sde = SDEFunc(16, 16)
     y0 = torch.randn(7, 16, requires_grad=True)
     ts = torch.linspace(0, 1, 16)
+    # the reference's call (models/mocogan_sde.py:57-59): forward on the cell grid, backward = torchsde's stochastic adjoint
     sol = gode.sdeint_adjoint(sde, y0, ts, bm=PhiloxBrownian(1234, traj_offset=70), method="euler", adjoint_method="euler", dt=2.5e-2)
     assert sol.shape == (16, 7, 16)
+    name, a = wired.calls[0]
+    assert name == "gode_sde_em_fwd_cells" and a[0] == y0.data_ptr() and a[4] == 41
+    assert a[10] == 79 and list(a[11:15]) == [7, 16, 16, 16] and a[15] is None and (a[16], a[17]) == (1234, 70)   # R | B D H T | Philox
+    grads = torch.autograd.grad(sol.sum(), [y0] + list(sde.parameters()))
+    name, a = wired.calls[1]
+    assert len(grads) == 9 and name == "gode_sde_adjoint_bwd"
+    assert a[4] == 45 and a[11] == 79 and list(a[12:16]) == [7, 16, 16, 16] and (a[17], a[18]) == (1234, 70)       # 45 reverse steps
+    wired.calls.clear()
+    # options={'adjoint': 'discrete'}: one draw per forward step, exact gradient of the recorded steps
+    sol = gode.sdeint_adjoint(sde, y0, ts, bm=PhiloxBrownian(1234, traj_offset=70), method="euler", adjoint_method="euler", dt=2.5e-2,
+                              options={"adjoint": "discrete"})
     name, a = wired.calls[0]
     assert name == "gode_sde_em_fwd" and a[0] == y0.data_ptr()
     assert a[4] == 41                                              # torchsde's fp32 time accumulation: 41 steps, not 40

@@ -374,3 +374,105 @@ def test_sde_euler_given_increments_matches_hand_loop():
         y3 = y2 + sde.f(a, y2) * (b - a) + sde.g(a, y2) * dW[2]
         w = (ts[1] - a) / (b - a)
     assert torch.allclose(sol[1], (1 - w) * y2 + w * y3, atol=1e-6)
+
+
+# ---- torchsde's stochastic adjoint (f3) ---------------------------------------------------------------------------------
+def _adjoint_step_closed_form(params, y, a, v):
+    """One evaluation of the augmented adjoint field in closed form for the two tanh MLPs — the arithmetic
+    csrc/sde_small.cu::sde_adjoint_bwd_kernel performs (its header derives it)."""
+    fW1, fb1, fW2, fb2, gW1, gb1, gW2, gb2 = params
+    hf = torch.tanh(y @ fW1.T + fb1)
+    f = hf @ fW2.T + fb2
+    df = (a @ fW2) * (1 - hf * hf)
+    z = y @ gW1.T + gb1
+    h = torch.tanh(z)
+    s = 1 - h * h
+    g = h @ gW2.T + gb2
+    q, p = g @ gW2, a @ gW1.T
+    gdg = (s * q) @ gW1
+    a_dg = (s * (a @ gW2)) @ gW1
+    r = p * s
+    gbar = r @ gW2.T
+    hbar = gbar @ gW2 - 2 * h * p * q
+    zbar = s * hbar
+
+    def vjp_g(c):
+        d = (c @ gW2) * s
+        return d @ gW1, d.T @ y, d.sum(0), c.T @ h, c.sum(0)
+
+    ey, eW1, eb1, eW2, eb2 = vjp_g(a_dg)
+    wy, wW1, wb1, wW2, wb2 = vjp_g(a * v)
+    f_o = [-(f - gdg), df @ fW1 - zbar @ gW1 + ey, df.T @ y, df.sum(0), a.T @ hf, a.sum(0),
+           -(zbar.T @ y + (s * q).T @ a) + eW1, -zbar.sum(0) + eb1, -(g.T @ r + gbar.T @ h) + eW2, -gbar.sum(0) + eb2]
+    g_o = [-(g * v), wy, None, None, None, None, wW1, wb1, wW2, wb2]
+    return f_o, g_o
+
+
+def test_sde_adjoint_field_closed_form_equals_autograd_restatement():
+    from oracle import torchsde_restatement as tsde
+    from oracle.latent_motion import SDEFunc
+    torch.manual_seed(0)
+    sde = SDEFunc(16, 16).double()
+    params = list(sde.parameters())
+    y, a = torch.randn(5, 16, dtype=torch.float64), torch.randn(5, 16, dtype=torch.float64)
+    v = 0.15 * torch.randn(5, 16, dtype=torch.float64)
+    f_out, g_out = tsde.adjoint_f_and_g_prod(sde, params, torch.tensor(-0.5), y, a, v)
+    f_c, g_c = _adjoint_step_closed_form([p.detach() for p in params], y, a, v)
+    for x, ref in zip(f_c, f_out):
+        assert float((x - ref).abs().max()) <= 1e-13
+    for x, ref in zip(g_c, g_out):
+        assert float(((0 * ref if x is None else x) - ref).abs().max()) <= 1e-13
+
+
+def test_sde_adjoint_grids_of_the_reference_call():
+    """models/mocogan_sde.py:57-59: 41 forward steps, 45 reverse steps (3 per output interval: 0.025, 0.025, 0.01667), and
+    the union grid both sides are measured on."""
+    from oracle import torchsde_restatement as tsde
+    ts = torch.linspace(0, 1, 16).float()
+    rev = tsde.reverse_step_grid(ts, 2.5e-2)
+    assert [len(p) for _, p in rev] == [3] * 15
+    hs = [float(s1 - s0) for s0, s1 in rev[0][1]]
+    assert abs(hs[0] - 0.025) < 1e-6 and abs(hs[1] - 0.025) < 1e-6 and abs(hs[2] - (1 / 15 - 0.05)) < 1e-6
+    grid = tsde.adjoint_time_grid(ts, 2.5e-2)
+    assert len(grid) == 80 and float(grid[0]) == 0.0 and float(grid[-1]) == 1.0
+
+
+def test_sde_stochastic_adjoint_converges_to_discrete_gradient_for_diagonal_jacobian():
+    """Pin of the restatement's signs and correction terms: for a diffusion whose Jacobian is diagonal (what torchsde's
+    'diagonal' formulas assume) the stochastic adjoint converges to the pathwise (discrete) gradient as dt -> 0."""
+    from oracle import torchsde_restatement as tsde
+
+    class DiagSDE(torch.nn.Module):
+        noise_type, sde_type = "diagonal", "ito"
+
+        def __init__(self):
+            super().__init__()
+            self.drift = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 4))
+            self.w, self.b = torch.nn.Parameter(torch.randn(4)), torch.nn.Parameter(torch.randn(4))
+
+        def f(self, t, y):
+            return self.drift(y)
+
+        def g(self, t, y):
+            return 0.7 * torch.tanh(self.w * y + self.b) + 0.3
+
+    torch.manual_seed(0)
+    ts = torch.linspace(0, 1, 3).float()
+    B = 1500
+    sde = DiagSDE().double()
+    y0, up = torch.randn(B, 4, dtype=torch.float64), torch.randn(3, B, 4, dtype=torch.float64)
+    errs = []
+    for dt in (0.1, 0.00625):
+        grid = tsde.adjoint_time_grid(ts, dt)
+        gen = torch.Generator().manual_seed(1)
+        inc = torch.randn(len(grid) - 1, B, 4, dtype=torch.float64, generator=gen) * torch.diff(grid).sqrt().view(-1, 1, 1)
+        bm = tsde.GridBrownian(grid, inc)
+
+        def run(fn):
+            y = y0.clone().requires_grad_(True)
+            sol = fn(sde, y, ts, bm=bm, method="euler", dt=dt)
+            return torch.autograd.grad((sol * up).sum(), [y] + list(sde.parameters()))
+
+        g_disc, g_adj = run(tsde.sdeint), run(tsde.sdeint_adjoint)
+        errs.append(max(float((a - b).norm() / b.norm()) for a, b in zip(g_adj, g_disc)))
+    assert errs[1] < 0.06 and errs[1] < 0.5 * errs[0], errs   # O(sqrt(dt)) strong error of the Euler adjoint: 16x smaller dt
