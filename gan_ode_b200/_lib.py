@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libgode.so")
+LIB_PATH = os.environ.get("GODE_LIB") or os.path.join(HERE, "csrc", "libgode.so")   # GODE_LIB: developer trace build only
 
 METHODS = {"rk4": 0, "euler": 1, "midpoint": 2}
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}

@@ -601,8 +601,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
     p.log->nfe = nfe;
     p.log->dt0 = dt0;
     p.log->t_final = t0;
-    ss.finish(p.gs);
   }
+  if (logger) ss.finish(p.gs);   // unconditionally (the ODE-RNN frames pass no log): the next launch continues from these tags
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,24 @@
 #include <stdlib.h>
 #include "dopri5_common.cuh"
 
+#ifdef GODE_TRACE
+// Developer build only (python -m gan_ode_b200.build --trace -> libgode_trace.so): thread 0 of CTA 0 stamps
+// (%globaltimer ns, clock64) at fixed points of the two headline kernels; scripts/headline_trace.py reads them back.
+__device__ unsigned long long g_gode_trace[2 * 64 * 2];
+#define GODE_TP(kern, slot)                                                                   \
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                                                  \
+    unsigned long long gt_;                                                                   \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                   \
+    g_gode_trace[((kern) * 64 + (slot)) * 2] = gt_;                                           \
+    g_gode_trace[((kern) * 64 + (slot)) * 2 + 1] = (unsigned long long)clock64();             \
+  }
+extern "C" int gode_debug_trace_read(unsigned long long* host_out) {
+  return (int)cudaMemcpyFromSymbol(host_out, g_gode_trace, sizeof(g_gode_trace));
+}
+#else
+#define GODE_TP(kern, slot)
+#endif
+
 namespace gode {
 
 constexpr int kMaxT = 256;  // output times passed by value
@@ -120,6 +138,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   __shared__ float s_f[WARPS * kGsMaxVals];
   __shared__ double s_d[kGsMaxVals];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  GODE_TP(0, 0);
   griddep_launch_dependents();   // a backward launched with PDL may stage its weights under this kernel's tail
   SyncState ss;
   ss.begin(p.gs);                // persistent tags: continue where the previous launch on this workspace stopped
@@ -144,7 +163,9 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y0);
     store_frag<S::DL>(p.traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y0);
   }
+  GODE_TP(0, 1);
   field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], hk);  // f0
+  GODE_TP(0, 2);
   int nfe = 1, status = 0;
   double t0 = p.t[0];
   double dt;
@@ -192,6 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     }
   }
   if (logger) p.log->dt0 = dt;
+  GODE_TP(0, 3);
 
   // ---- solvers.py::AdaptiveStepsizeODESolver.integrate / rk_common.py::_adaptive_step ---------------------------
   int iout = 1, n_att = 0, n_acc = 0, n_steps = 0;
@@ -213,6 +235,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], hk);
     }
     nfe += 6;
+    GODE_TP(0, 4 + 3 * min(n_att, 8));
     // u is y1 (FSAL: c_sol == beta[5]), k[6] is f1
     double v[1] = {0.0};
 #pragma unroll
@@ -226,6 +249,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     }
     grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, ss, lane, warp);
     if constexpr (WORLD) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
+    GODE_TP(0, 5 + 3 * min(n_att, 8));
     const float er = (float)sqrt(v[0] / n_elem);
     bool accept = er <= 1.f;
     if (dt > p.o.max_step) accept = false;
@@ -283,6 +307,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     }
     dt = optimal_step(dt, er, p.o);
     dt = fmin(fmax(dt, p.o.min_step), p.o.max_step);
+    GODE_TP(0, 6 + 3 * min(n_att, 8));
     ++n_att;
     ++n_steps;
   }
@@ -296,6 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     if constexpr (WORLD) *p.w_launch_ctr = wepoch;
     ss.finish(p.gs);   // every CTA has arrived at the last reduction, hence has read the bases
   }
+  GODE_TP(0, 40);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -311,6 +337,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   // in flight (T <= kDp5StageT): inside the replay loop they used to be T dependent global loads, each a full L2/HBM latency
   float* s_gr = s_red + WARPS * S::P;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
+  GODE_TP(1, 0);
   const bool staged = p.T <= kDp5StageT;
   float* my_gr = s_gr + (size_t)warp * p.T * (S::G * D);
   // Weights first: under a PDL launch (GODE_LAUNCH_PDL_BWD) this prologue runs while the forward kernel is still in its
@@ -323,11 +350,14 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
+  GODE_TP(1, 1);
   griddep_wait();
+  GODE_TP(1, 2);
   const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
   SyncState ss;
   ss.begin(p.ws.gs);
   __syncthreads();
+  GODE_TP(1, 3);
   const int n_acc = min(log_n_accepted, p.o.ckpt_capacity);
   // A forward that failed (dt underflow, non-finite state, step budget, checkpoint overflow) has no valid replay:
   // return NaN gradients instead of silently truncated ones (the host does not sync to look at the status).
@@ -364,6 +394,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       }
       __syncwarp();
     }
+    GODE_TP(1, 4);
     // checkpoint and step table of the step about to be replayed are fetched one step ahead
     float y0n[S::DL];
     double t0n = 0.0, dtn = 0.0;
@@ -374,6 +405,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(n_acc - 1) * p.B + b) * D + l * S::DL, y0n);
     }
     for (int s = n_acc - 1; s >= 0; --s) {
+      GODE_TP(1, 5 + 2 * min(s, 8));
       const double t0 = t0n, dtd = dtn, t1 = t0 + dtd;
       const float dt32 = (float)dtd;
       float y0[S::DL], k[7][S::DL], h[7][S::HL], u[S::DL];
@@ -396,6 +428,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
         }
         field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], h[i + 1]);
       }
+      GODE_TP(1, 6 + 2 * min(s, 8));
       // cotangents of the interpolation inputs (y0, y1, ymid, f0, f1) from every output inside (t0, t1]
       float y0b[S::DL], ymb[S::DL], f0b[S::DL], kb[7][S::DL];
 #pragma unroll
@@ -491,8 +524,10 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, g0);
     }
   }
+  GODE_TP(1, 30);
   reduce_param_grads<D, H, L, WARPS>(acc, s_red, p.ws, ss, p.grad_params, lane, warp, tid);
   if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
+  GODE_TP(1, 31);
 }
 
 // ------------------------------------------------------------------------------------------------------------
