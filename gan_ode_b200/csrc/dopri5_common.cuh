@@ -32,15 +32,28 @@ __device__ constexpr float kCMid[7] = {F32(6025192743.0 / 30085553152.0 / 2),
 #undef F32
 
 // misc.py::_optimal_step_size in fp64
+// er^(-1/5) without fp64 exp/log (they were ~1.2 k cycles per attempted step on the solver's critical path, trace in
+// profiles/README.md): MUFU-based fp32 guess (relative error ~1e-6), then two Newton steps for F(y) = y^-5 - er,
+// y <- y (6 - er y^5) / 5 — division-free, quadratic: 1e-6 -> 3e-12 -> 3e-23, i.e. correctly rounded to within an ulp.
+__device__ __forceinline__ double inv_fifth_root(float er32) {
+  double y = (double)__powf(er32, -0.2f);
+  const double er = (double)er32;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double y2 = y * y, y5 = y2 * y2 * y;
+    y = y * ((6.0 - er * y5) * 0.2);
+  }
+  return y;
+}
+
 __device__ __forceinline__ double optimal_step(double dt, float er32, const GodeAdaptiveOpts& o) {
   if (er32 == 0.f) return dt * o.ifactor;
+  if (er32 != er32) return (double)er32;                       // torch.min/max propagate NaN; fmin/fmax do not
   const double dfactor = er32 < 1.f ? 1.0 : o.dfactor;
-  const double er = (double)er32;
-  // er^(1/5) as exp(log(er)/5): er is a positive finite fp32 value here (0 and NaN are handled around this line),
-  // so none of pow()'s special-case machinery is needed; relative error ~1e-15, far inside the 1e-5*dt budget.
-  const double factor = fmin(o.ifactor, fmax(o.safety / exp(0.2 * log(er)), dfactor));
-  // torch.min/max propagate NaN; fmin/fmax do not
-  return (er != er) ? er : dt * factor;
+  // below 1e-30 (and for +inf) the factor is pinned by ifactor / dfactor whatever the root is; keep the guess in range
+  const float erc = fminf(fmaxf(er32, 1e-30f), 1e30f);
+  const double factor = fmin(o.ifactor, fmax(o.safety * inv_fifth_root(erc), dfactor));
+  return dt * factor;
 }
 
 // the (possibly time-reversed) field: out = fsign * f(u)

@@ -340,13 +340,38 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   GODE_TP(1, 0);
   const bool staged = p.T <= kDp5StageT;
   float* my_gr = s_gr + (size_t)warp * p.T * (S::G * D);
-  // Weights first: under a PDL launch (GODE_LAUNCH_PDL_BWD) this prologue runs while the forward kernel is still in its
-  // tail; everything the forward wrote (step log, checkpoints) and the persistent sync counters are read after the wait.
+  // Prologue = independent cold global reads, all issued before the first one is needed (each is a full L2/HBM latency and
+  // at this batch the kernel is a latency chain): the first batch of upstream-gradient loads of this warp's trajectories,
+  // the lane's weight rows, then — after the dependency wait — the step log and the sync bases, and only then the staging
+  // of the column weights, which is the first thing that blocks on data.  Under a PDL launch (GODE_LAUNCH_PDL_BWD) the part
+  // above griddep_wait() overlaps the tail of the previous kernel: the caller guarantees that kernel writes neither the
+  // weights nor the upstream gradient (it is the matching forward).
+  const int n4 = p.T * (S::G * D / 4);   // float4 elements of one trajectory group's upstream gradients
+  const int first_base = (blockIdx.x * WARPS + warp) * S::G;
+  auto issue_grads = [&](int base, int e0, float4 (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = e0 + 32 * q;
+      const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (e < n4 && base + gg < p.B)
+        v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
+    }
+  };
+  auto commit_grads = [&](int e0, const float4 (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int e = e0 + 32 * q;
+      const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+      if (e < n4) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
+    }
+  };
+  float4 pre[8];
+  if (staged && first_base < p.B) issue_grads(first_base, lane, pre);
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
   cw.bind(s_cw);
-  cw.stage(p.W1, p.W2, tid, WARPS * 32);
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
@@ -356,6 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
   SyncState ss;
   ss.begin(p.ws.gs);
+  cw.stage(p.W1, p.W2, tid, WARPS * 32);
   __syncthreads();
   GODE_TP(1, 3);
   const int n_acc = min(log_n_accepted, p.o.ckpt_capacity);
@@ -374,22 +400,15 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
     int iout = p.T - 1;
     if (staged) {
       __syncwarp();
-      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store
-      for (int e0 = lane; e0 < p.T * (S::G * D / 4); e0 += 8 * 32) {
-        float4 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = e0 + 32 * q;
-          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < p.T * (S::G * D / 4) && base + gg < p.B)
-            v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = e0 + 32 * q;
-          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-          if (e < p.T * (S::G * D / 4)) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
+      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store (the
+      // first batch of the first group was issued at the top of the kernel)
+      for (int e0 = lane; e0 < n4; e0 += 8 * 32) {
+        if (base == first_base && e0 == lane) {
+          commit_grads(e0, pre);
+        } else {
+          float4 v[8];
+          issue_grads(base, e0, v);
+          commit_grads(e0, v);
         }
       }
       __syncwarp();

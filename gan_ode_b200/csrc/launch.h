@@ -43,19 +43,23 @@ int& thread_launch_flags();
 // process-wide status mailbox in mapped host memory (gode_set_status_mailbox); null = off
 int32_t* status_mailbox();
 
-// Cooperative launch; with `pdl` also programmatic stream serialisation (the kernel must call griddep_wait() before it
-// touches anything the previous kernel on the stream wrote).  If the driver refuses the attribute pair, the plain
-// cooperative launch is used (remembered per process).
+// Cooperative launch — or, with `pdl`, an ORDINARY launch with programmatic stream serialisation (the kernel must call
+// griddep_wait() before it touches anything the previous kernel on the stream wrote).  Measured on B200: a launch that is
+// both cooperative and programmatic is accepted but never starts early (the backward's CTA 0 entered 0.25 us after the
+// forward's exit) and the graph edge costs ~4 us more than a plain one, so the PDL variant gives the cooperative attribute
+// up.  That is sound for these kernels: their grid is capped at the co-resident capacity of an EMPTY device
+// (coop_limit), their grid barrier only waits for CTAs of the same grid, and the kernel they overlap (the forward) never
+// waits for them — so every CTA gets an SM at the latest when the forward's CTAs retire.  If the driver refuses the
+// attribute, the cooperative launch is used (remembered per kernel).
 template <class K>
 inline cudaError_t coop_launch(K kern, int grid, int block, void** args, size_t smem, cudaStream_t st, bool pdl) {
   static bool pdl_ok = true;
   if (pdl && pdl_ok) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[2];
-    at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelExC(&cfg, (const void*)kern, args);
     if (e == cudaSuccess) return e;
     (void)cudaGetLastError();

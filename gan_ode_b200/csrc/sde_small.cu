@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(WARPS * 32) sde_em_bwd_kernel(const __grid_con
   // two parameter sets: reduce one after the other (same persistent counter, running target; separate partial rows)
   ReduceWs w1 = p.ws, w2 = p.ws;
   w2.partials = p.ws.partials + (size_t)gridDim.x * S::P;
-  reduce_param_grads<D, H, L, WARPS>(af, s_red, w1, ss, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS, false>(af, s_red, w1, ss, p.grad_params, lane, warp, tid);
   __syncthreads();
   reduce_param_grads<D, H, L, WARPS>(ag, s_red, w2, ss, p.grad_params + S::P, lane, warp, tid);
   if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(WARPS * 32) sde_adjoint_bwd_kernel(const __gri
   }
   ReduceWs w1 = p.ws, w2 = p.ws;
   w2.partials = p.ws.partials + (size_t)gridDim.x * S::P;
-  reduce_param_grads<D, H, L, WARPS>(af, s_red, w1, ss, p.grad_params, lane, warp, tid);
+  reduce_param_grads<D, H, L, WARPS, false>(af, s_red, w1, ss, p.grad_params, lane, warp, tid);
   __syncthreads();
   reduce_param_grads<D, H, L, WARPS>(ag, s_red, w2, ss, p.grad_params + S::P, lane, warp, tid);
   if (blockIdx.x == 0 && tid == 0) ss.finish(p.ws.gs);

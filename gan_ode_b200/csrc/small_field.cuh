@@ -304,7 +304,11 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
-template <int D, int H, int L, int WARPS>
+// LAST: this is the kernel's last grid-wide operation.  Then only the CTAs that own columns (and CTA 0, which stores the sync
+// bases) wait at the barrier; the others arrive and are done — 222 of 256 CTAs stop polling the counter the 34 consumers
+// are waiting on.  Not allowed for an earlier reduction of the same kernel: a CTA that does not wait could arrive for the
+// NEXT barrier before a slow CTA has arrived for this one, and the counter cannot tell the two arrivals apart.
+template <int D, int H, int L, int WARPS, bool LAST = true>
 __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float* smem_red /* [WARPS][P] */,
                                                    const ReduceWs& ws, SyncState& ss, float* __restrict__ grad_params,
                                                    int lane, int warp, int tid) {
@@ -352,7 +356,23 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
   }
   const bool xchg = ws.w_world > 1;
   const unsigned int wtag = xchg ? *reinterpret_cast<volatile unsigned int*>(ws.w_ctr) + 1u : 0u;  // read before the barrier
-  grid_barrier(ws.gs, ss);
+  if constexpr (LAST) {
+    const bool waits = blockIdx.x == 0 || (int)blockIdx.x * WARPS < P / 4;
+    ss.ctarget += gridDim.x;
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      arrive_counter(ws.gs.counter);
+      if (waits) {
+        wait_counter(ws.gs.counter, ss.ctarget);
+        __threadfence();
+      }
+    }
+    if (!waits) return;
+    __syncthreads();
+  } else {
+    grid_barrier(ws.gs, ss);
+  }
   if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;  // every thread of the grid has read it
   // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
   // in order, then a shuffle tree.  No block-level synchronisation.

@@ -117,6 +117,28 @@ def case_sde(B=8, seed=41):
     return out
 
 
+def case_sde_stochastic_adjoint(B=8, seed=43):
+    """models/mocogan_sde.py:57-59 with the Brownian path given on the cell grid: forward + torchsde's stochastic adjoint."""
+    torch.manual_seed(seed)
+    sde = SDEFunc(16, 16)
+    ts = torch.linspace(0, 1, 16).float()
+    times = tsde.adjoint_time_grid(ts, 2.5e-2)
+    torch.manual_seed(seed + 1)
+    y0 = torch.randn(B, 16)
+    g = torch.randn(16, B, 16)
+    dW = torch.randn(len(times) - 1, B, 16) * torch.diff(times).float().sqrt().view(-1, 1, 1)
+    y = y0.clone().requires_grad_(True)
+    sol = tsde.sdeint_adjoint(sde, y, ts, bm=tsde.GridBrownian(times, dW), method="euler", adjoint_method="euler", dt=2.5e-2)
+    names = [n for n, _ in sde.named_parameters()]
+    grads = torch.autograd.grad((sol * g).sum(), [y] + list(sde.parameters()))
+    out = dict(y0=_np(y0), t=_np(ts), grad_traj=_np(g), times=times.numpy(), dW=_np(dW), sol=_np(sol), grad_y0=_np(grads[0]),
+               param_names=np.array(names))
+    for n, p, gp in zip(names, sde.parameters(), grads[1:]):
+        out["p:" + n] = _np(p)
+        out["g:" + n] = _np(gp)
+    return out
+
+
 def _reference_modules():
     """Import the unmodified reference model files with the oracle as `torchdiffeq` (and `on_dev` aliased to `models`,
     SURVEY Appendix C)."""
@@ -187,6 +209,7 @@ def main():
         "dopri5_backprop_tol1e-5_B8": case_dopri5_backprop(),
         "dopri5_adjoint_default_tol_B4": case_dopri5_adjoint_default_tol(),
         "sde_euler_given_dW_B8": case_sde(),
+        "sde_stochastic_adjoint_B8": case_sde_stochastic_adjoint(),
     }
     if os.path.isdir(os.path.join(REF, "models")):
         ode_mod, rnn_mod = _reference_modules()
@@ -194,7 +217,10 @@ def main():
         cases["reference_sample_z_m_odernn"] = case_reference_odernn(rnn_mod)
     else:
         print("WARNING: /root/reference absent - caller cases not regenerated")
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
     for name, arrays in cases.items():
+        if only and name not in only:
+            continue
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **arrays)
         print("{:45s} {:8.1f} KB".format(name, os.path.getsize(path) / 1024))

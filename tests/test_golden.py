@@ -63,7 +63,7 @@ def run_ode(mod, z, adjoint, kw, dev="cpu", extra_options=None):
 
 def test_every_fixture_is_present_and_small():
     names = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz"))
-    assert len(names) == 9, names
+    assert len(names) == 10, names
     assert sum(os.path.getsize(os.path.join(GOLD, f)) for f in names) < 1 << 20
 
 
@@ -101,6 +101,36 @@ def test_oracle_reproduces_golden_sde():
     assert rel_err(grads[0], T(z["grad_y0"])) <= 1e-5
     for (n, _), g in zip(sde.named_parameters(), grads[1:]):
         assert rel_err(g, T(z["g:" + n])) <= 1e-5, n
+
+
+def test_oracle_reproduces_golden_sde_stochastic_adjoint():
+    z = load("sde_stochastic_adjoint_B8")
+    sde = _sde_from(z)
+    y = T(z["y0"]).requires_grad_(True)
+    bm = tsde.GridBrownian(torch.from_numpy(z["times"]), T(z["dW"]))
+    sol = tsde.sdeint_adjoint(sde, y, T(z["t"]), bm=bm, method="euler", adjoint_method="euler", dt=2.5e-2)
+    grads = torch.autograd.grad((sol * T(z["grad_traj"])).sum(), [y] + list(sde.parameters()))
+    assert z["dW"].shape[0] == 79
+    assert rel_err(sol, T(z["sol"])) <= 1e-6
+    assert rel_err(grads[0], T(z["grad_y0"])) <= 1e-5
+    for (n, _), g in zip(sde.named_parameters(), grads[1:]):
+        assert rel_err(g, T(z["g:" + n])) <= 1e-5, n
+
+
+@pytest.mark.gpu
+def test_cuda_sde_stochastic_adjoint_matches_golden():
+    _need_gpu()
+    import gan_ode_b200 as gode
+    z = load("sde_stochastic_adjoint_B8")
+    sde = _sde_from(z, DEV)
+    y = T(z["y0"], DEV).requires_grad_(True)
+    sol = gode.sdeint_adjoint(sde, y, T(z["t"]), bm=gode.GridBrownian(z["times"], T(z["dW"], DEV)), method="euler",
+                              adjoint_method="euler", dt=2.5e-2)
+    grads = torch.autograd.grad((sol * T(z["grad_traj"], DEV)).sum(), [y] + list(sde.parameters()))
+    assert rel_err(sol, T(z["sol"])) <= 1e-5
+    assert rel_err(grads[0], T(z["grad_y0"])) <= 2e-5
+    for (n, _), g in zip(sde.named_parameters(), grads[1:]):
+        assert rel_err(g, T(z["g:" + n])) <= 2e-5, n
 
 
 def _caller_ode(z, dev="cpu"):
@@ -205,7 +235,7 @@ def test_cuda_sde_matches_golden():
     sde = _sde_from(z, DEV)
     y = T(z["y0"], DEV).requires_grad_(True)
     sol = gode.sdeint_adjoint(sde, y, T(z["t"]), bm=gode.TableBrownian(T(z["dW"], DEV)), method="euler",
-                              adjoint_method="euler", dt=2.5e-2)
+                              adjoint_method="euler", dt=2.5e-2, options={"adjoint": "discrete"})
     grads = torch.autograd.grad((sol * T(z["grad_traj"], DEV)).sum(), [y] + list(sde.parameters()))
     assert rel_err(sol, T(z["sol"])) <= 1e-5
     assert rel_err(grads[0], T(z["grad_y0"])) <= 2e-5
