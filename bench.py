@@ -11,8 +11,8 @@ PER GPU (weak scaling), output grid t = linspace(0,1,16), dopri5 with rtol = ato
 the solver, upstream gradient supplied as a resident N(0,1) tensor.  One "step" = one forward + one
 backward of that batch.  trajectory-steps = B x ATTEMPTED dopri5 steps (accepted + rejected), read from the device log.
 
-value     inputs resident in HBM; the step (2 kernels, the backward a programmatic dependent launch behind the forward; the
-          grid-sync workspace is persistent, so there are no memsets) replayed from a CUDA graph; per-step CUDA events,
+value     inputs resident in HBM; the step (2 kernels; the grid-sync workspace is persistent, so there are no memsets)
+          replayed from a CUDA graph; per-step CUDA events,
           L2 flushed (256 MiB write) between steps outside the event pairs.
 e2e       the same metric through the public API the reference calls (gan_ode_b200.odeint), eager, with the
           batch's noise y0 in pinned HOST memory: H2D copy of y0 and D2H read of loss + parameter gradients are
@@ -311,9 +311,8 @@ def run_gpu(args):
     try:
         if args.no_graph:
             raise RuntimeError("--no-graph")
-        # Inside the captured step the kernel enqueued right before the backward is the matching forward, so the backward is
-        # captured as a programmatic dependent launch (gan_ode_b200.config.pdl; what GraphedSolveStep does by default).
-        gode.config.pdl = not args.no_pdl
+        # (--pdl: the backward captured as a programmatic dependent launch behind the forward, gan_ode_b200.config.pdl)
+        gode.config.pdl = args.pdl
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -391,7 +390,7 @@ def run_gpu(args):
     try:
         if args.no_graph:
             raise RuntimeError("--no-graph")
-        gs = gode.GraphedSolveStep(f, B_PER_GPU, t, adjoint=False, read_back=("param_grads",), pdl=not args.no_pdl, **kw)
+        gs = gode.GraphedSolveStep(f, B_PER_GPU, t, adjoint=False, read_back=("param_grads",), pdl=args.pdl, **kw)
         gs.y0_host.copy_(y0_host)
         gs.grad_traj.copy_(grad)
 
@@ -454,7 +453,7 @@ def run_gpu(args):
             return gode.odeint(f, y0r, t, **kw)
 
         def graph_of(fn):
-            gode.config.pdl = not args.no_pdl
+            gode.config.pdl = args.pdl
             s_ = torch.cuda.Stream()
             s_.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s_):
@@ -583,7 +582,7 @@ def run_gpu(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_for(n_gpus),
         "run": {"cuda_graph": graphed, "attempted_steps": n_att, "accepted_steps": n_acc,
-                "pdl_backward": bool(graphed and not args.no_pdl),
+                "pdl_backward": bool(graphed and args.pdl),
                 "grad_allreduce": ("none (1 GPU)" if n_gpus == 1 else
                                    "fused into the backward kernel's reduction tail over NVLink peer memory "
                                    "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
@@ -615,8 +614,8 @@ def main():
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "
                     "of the fused peer-memory kernel")
-    ap.add_argument("--no-pdl", action="store_true", help="capture the backward as an ordinary launch (no programmatic "
-                    "dependent launch behind the forward)")
+    ap.add_argument("--pdl", action="store_true", help="capture the backward as a programmatic dependent launch behind the "
+                    "forward (measured slower for this pair of kernels; off by default)")
     ap.add_argument("--no-extras", action="store_true", help="skip the large-batch / wide-field side measurements")
     args = ap.parse_args()
     if args.nccl_allreduce:

@@ -76,5 +76,37 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
     return lib
 
 
+TORCH_EXT = os.path.join(HERE, "_gode_torch.so")
+TORCH_SRC = os.path.join(HERE, "csrc_torch", "gode_torch.cpp")
+
+
+def build_torch_ext(force: bool = False) -> str:
+    """Compile the thin PyTorch C++ host (csrc_torch/gode_torch.cpp) in-tree as gan_ode_b200/_gode_torch.so with g++ against
+    this interpreter's torch (same image on the GPU box, so the prebuilt module travels).  It holds no kernels and links
+    nothing from libgode.so (the entry points are bound by address at import), so it needs no nvcc."""
+    deps = [TORCH_SRC, os.path.join(ROOT, "include", "gode.h"), __file__]
+    if not force and os.path.exists(TORCH_EXT) and os.path.getmtime(TORCH_EXT) >= max(os.path.getmtime(d) for d in deps):
+        return TORCH_EXT
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = os.environ.get("CUDA_HOME") or "/usr/local/cuda"
+    inc = ce.include_paths() + [sysconfig.get_paths()["include"], os.path.join(cuda_home, "include"),
+                                os.path.join(ROOT, "include")]
+    libdir = ce.library_paths()[0]
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_gode_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI={}".format(int(torch._C._GLIBCXX_USE_CXX11_ABI)),
+           *["-I" + i for i in inc], TORCH_SRC, "-o", TORCH_EXT, "-L" + libdir, "-Wl,-rpath," + libdir,
+           "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building _gode_torch.so failed:\n{}\n{}".format(r.stdout[-4000:], r.stderr[-4000:]))
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    if "--trace" not in sys.argv:
+        print(build_torch_ext(force="--force" in sys.argv))

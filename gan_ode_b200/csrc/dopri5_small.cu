@@ -151,6 +151,8 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   const bool logger = (blockIdx.x == 0 && tid == 0);
   constexpr bool world = WORLD;
   const double n_elem = (double)(world ? p.w_total_B : (long long)p.B) * (double)D;
+  const double inv_n = 1.0 / n_elem;   // the norms below are rms values rounded to fp32 (torch computes them in fp32): one
+                                       // fp64 multiply + fp32 sqrt instead of an fp64 divide + fp64 sqrt on the critical path
   const float rtol32 = (float)p.o.rtol, atol32 = (float)p.o.atol;
   // cumulative world epoch: read before the first grid-wide reduction; CTA 0 writes it back after the last one
   unsigned int wepoch = 0;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     if (p.o.first_step > 0.0) {
       dt = p.o.first_step;
     } else {
-      const float d0 = (float)sqrt(v[0] / n_elem), d1 = (float)sqrt(v[1] / n_elem);
+      const float d0 = sqrtf((float)(v[0] * inv_n)), d1 = sqrtf((float)(v[1] * inv_n));
       const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
       float u[S::DL], f1[S::DL];
 #pragma unroll
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       }
       grid_allreduce_sum<1, WARPS>(v2, s_f, s_d, p.gs, ss, lane, warp);
       if constexpr (WORLD) world_allreduce_sum<1>(v2, p, wepoch, status, lane, warp);
-      const float d2 = (float)sqrt(v2[0] / n_elem) / h0;
+      const float d2 = sqrtf((float)(v2[0] * inv_n)) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
       else h1 = powf(0.01f / fmaxf(d1, d2), 0.2f);
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     grid_allreduce_sum<1, WARPS>(v, s_f, s_d, p.gs, ss, lane, warp);
     if constexpr (WORLD) world_allreduce_sum<1>(v, p, wepoch, status, lane, warp);
     GODE_TP(0, 5 + 3 * min(n_att, 8));
-    const float er = (float)sqrt(v[0] / n_elem);
+    const float er = sqrtf((float)(v[0] * inv_n));
     bool accept = er <= 1.f;
     if (dt > p.o.max_step) accept = false;
     if (dt <= p.o.min_step) accept = true;
@@ -280,7 +282,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
           cc[c] = dt32 * (f1 - 4.f * f0) - 11.f * y0[c] - 5.f * y1 + 16.f * ymid;
           cd[c] = dt32 * f0;
         }
-        const double inv_span = 1.0 / (t1 - t0);  // one fp64 division per step instead of one per output time
+        // 1 / (t1 - t0) to fp64 accuracy without an fp64 division: fp32 reciprocal + two Newton steps (6e-8 -> 4e-15 -> 0)
+        const double span = t1 - t0;
+        double inv_span = (double)__frcp_rn((float)span);
+        inv_span = inv_span * (2.0 - span * inv_span);
+        inv_span = inv_span * (2.0 - span * inv_span);
         while (iout < p.T && p.t[iout] <= t1) {
           const float x = (float)((p.t[iout] - t0) * inv_span);
           float o[S::DL];
@@ -340,48 +346,23 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   GODE_TP(1, 0);
   const bool staged = p.T <= kDp5StageT;
   float* my_gr = s_gr + (size_t)warp * p.T * (S::G * D);
-  // Prologue = independent cold global reads, all issued before the first one is needed (each is a full L2/HBM latency and
-  // at this batch the kernel is a latency chain): the first batch of upstream-gradient loads of this warp's trajectories,
-  // the lane's weight rows, then — after the dependency wait — the step log and the sync bases, and only then the staging
-  // of the column weights, which is the first thing that blocks on data.  Under a PDL launch (GODE_LAUNCH_PDL_BWD) the part
-  // above griddep_wait() overlaps the tail of the previous kernel: the caller guarantees that kernel writes neither the
-  // weights nor the upstream gradient (it is the matching forward).
+  // (griddep_wait first: a no-op for an ordinary launch.  Overlapping this prologue with the forward's tail by a programmatic
+  // dependent launch was built and measured, profiles/README.md round 2: it does not pay for this pair of kernels.)
+  griddep_wait();
+  // the step log and the sync bases are read first so that their latency overlaps the weight loads below (all cold reads)
+  const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
+  SyncState ss;
+  ss.begin(p.ws.gs);
   const int n4 = p.T * (S::G * D / 4);   // float4 elements of one trajectory group's upstream gradients
-  const int first_base = (blockIdx.x * WARPS + warp) * S::G;
-  auto issue_grads = [&](int base, int e0, float4 (&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int e = e0 + 32 * q;
-      const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-      v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (e < n4 && base + gg < p.B)
-        v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
-    }
-  };
-  auto commit_grads = [&](int e0, const float4 (&v)[8]) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int e = e0 + 32 * q;
-      const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-      if (e < n4) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
-    }
-  };
-  float4 pre[8];
-  if (staged && first_base < p.B) issue_grads(first_base, lane, pre);
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
   cw.bind(s_cw);
+  cw.stage(p.W1, p.W2, tid, WARPS * 32);
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
   GODE_TP(1, 1);
-  griddep_wait();
-  GODE_TP(1, 2);
-  const int log_n_accepted = p.log->n_accepted, log_status = p.log->status;
-  SyncState ss;
-  ss.begin(p.ws.gs);
-  cw.stage(p.W1, p.W2, tid, WARPS * 32);
   __syncthreads();
   GODE_TP(1, 3);
   const int n_acc = min(log_n_accepted, p.o.ckpt_capacity);
@@ -400,15 +381,22 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
     int iout = p.T - 1;
     if (staged) {
       __syncwarp();
-      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store (the
-      // first batch of the first group was issued at the top of the kernel)
+      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store
       for (int e0 = lane; e0 < n4; e0 += 8 * 32) {
-        if (base == first_base && e0 == lane) {
-          commit_grads(e0, pre);
-        } else {
-          float4 v[8];
-          issue_grads(base, e0, v);
-          commit_grads(e0, v);
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = e0 + 32 * q;
+          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e < n4 && base + gg < p.B)
+            v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int e = e0 + 32 * q;
+          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+          if (e < n4) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
         }
       }
       __syncwarp();
@@ -666,7 +654,17 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
   a.o.ckpt_capacity = ckpt_capacity; a.o.fsign = fsign; a.grad_y0 = grad_y0; a.grad_params = grad_params;
   a.B = B; a.T = T; a.layout = layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
-  if (D == 16 && H == 16) return launch_dp5_bwd<16, 16, 8>(a, workspace, ws_bytes, st);  // (8-warp CTAs measured: slower)
+  if (D == 16 && H == 16) {
+    // 4 trajectories per warp.  With 4-warp CTAs, 148 < CTAs <= 296 means 108 SMs carry two CTAs and 40 carry one: the kernel
+    // is bound by shared-memory bandwidth, so the doubled SMs finish last and everyone waits for them in the final reduction
+    // (trace in profiles/README.md).  In that range 7-warp CTAs put ONE CTA on every SM (B = 4096: 147 CTAs x 28 trajectories).
+    const int sms = sm_count();
+    const int grid4 = (B + 15) / 16, grid7 = (B + 27) / 28;
+    const char* force = getenv("GODE_DP5_BWD_WARPS");
+    const bool seven = force ? force[0] == '7' : (grid4 > sms && grid7 <= sms);
+    if (seven) return launch_dp5_bwd<16, 16, 8, 7>(a, workspace, ws_bytes, st);
+    return launch_dp5_bwd<16, 16, 8>(a, workspace, ws_bytes, st);  // (8-warp CTAs measured: slower)
+  }
   return GODE_ERR_SHAPE;
 }
 

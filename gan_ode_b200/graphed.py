@@ -44,7 +44,7 @@ def _flat_param_grads(gs):
 class GraphedSolveStep:
     def __init__(self, func, batch: int, t: torch.Tensor, *, method: Optional[str] = None, rtol=1e-7, atol=1e-9,
                  adjoint: bool = True, options: Optional[dict] = None, device=None,
-                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = True):
+                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = False):
         W1, _, _, _ = _api.recognise_field(func)
         D = W1.shape[1]
         dev = torch.device(device) if device is not None else W1.device
@@ -76,7 +76,9 @@ class GraphedSolveStep:
         self.log = None
 
         # In this graph the kernel right before the backward IS the matching forward (nothing in between writes the weights
-        # or the upstream gradient), so the backward may be a programmatic dependent launch (config.pdl).
+        # or the upstream gradient), so the backward MAY be a programmatic dependent launch (config.pdl, `pdl=True`).  Off by
+        # default: measured slower for the dopri5 pair (the 256-CTA backward does not fit beside the forward, the CTAs that
+        # start late arrive late at its final reduction; profiles/README.md).
         prev_pdl = _api.config.pdl
         _api.config.pdl = bool(pdl)
         try:

@@ -584,7 +584,10 @@ def check_status():
 
 
 def raise_for_status(status: int):
-    """torchdiffeq's solver asserts, raised from the device status word."""
+    """torchdiffeq's solver asserts, raised from the device status word.  (Callers read `status` from a step log, i.e. after a
+    synchronisation: whatever the mailbox holds by then has been reported here, so it is cleared.)"""
+    if status and _mailbox[1] is not None:
+        _mailbox[1][0] = 0
     if status & _lib.ST_NONFINITE:
         raise AssertionError("non-finite values in state `y`")
     if status & _lib.ST_DT_UNDERFLOW:

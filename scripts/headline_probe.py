@@ -66,12 +66,15 @@ for name, kw, solve in (("dopri5_backprop", dict(method="dopri5", rtol=1e-5, ato
     r = {}
     gf, _ = graph_of(fwd, False)
     r["fwd_graph_us(median,min)"] = replay_us(gf)
-    for pdl in (False, True):
-        gs, keep = graph_of(step, pdl)
-        r["step_graph_pdl=%d_us" % pdl] = replay_us(gs)
-        gs.replay()
-        torch.cuda.synchronize()
-        r["pdl=%d_matches_eager" % pdl] = bool(all(torch.equal(a, b) for a, b in zip(keep, ref)))
+    for warps in ("4", "7"):
+        os.environ["GODE_DP5_BWD_WARPS"] = warps
+        for pdl in (False, True):
+            gs, keep = graph_of(step, pdl)
+            r["step_graph_bwdwarps=%s_pdl=%d_us" % (warps, pdl)] = replay_us(gs)
+            gs.replay()
+            torch.cuda.synchronize()
+            r["bwdwarps=%s_pdl=%d_maxrel_vs_eager" % (warps, pdl)] = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(keep, ref))
+    os.environ.pop("GODE_DP5_BWD_WARPS")
     # eager issue rate (host-bound)
     for _ in range(5):
         step()
