@@ -61,6 +61,8 @@ class _Config:
     # guarantee that that kernel does not write the ODEFunc weights — true when it is the matching forward (GraphedSolveStep
     # sets it for its own capture), not true in general (e.g. an optimiser step right before a backward).
     pdl = False
+    # The thin C++ host (gan_ode_b200._gode_torch) for rk4 / dopri5 calls; False forces the Python autograd.Functions
+    use_cpp_host = True
 
 
 config = _Config()
@@ -409,16 +411,7 @@ class _Rk4(torch.autograd.Function):
         ws = _workspace(buf.device, ws_bytes)
         fn = L.gode_rk4_adjoint_bwd if meta["adjoint"] else L.gode_rk4_backprop_bwd
         dt_ptr, dt_dev = _dt_arg(dt)
-        # Wide field (D=64, H=256) in bf16 mode: the continuous adjoint runs on tcgen05 too (csrc/tc_rk4_adj_wide.cu).
-        # Everything else backpropagates with the FP32 kernels, re-solving from the stored (tensor-core) trajectory,
-        # which keeps the gradient inside the 2e-3 budget of the tf32/bf16 modes.
-        bwd_prec = _lib.PREC["fp32"]
-        want = meta.get("bwd_precision")
-        if meta["adjoint"] and meta["precision"] == _lib.PREC["bf16"]:
-            if (D, H) == (64, 256) and want in (None, "bf16"):     # default for the wide field
-                bwd_prec = _lib.PREC["bf16"]
-            elif (D, H) == (16, 16) and want == "bf16":            # opt-in for the reference shape (tc_rk4_adj_small.cu)
-                bwd_prec = _lib.PREC["bf16"]
+        bwd_prec = _bwd_precision(meta, D, H)
         ex = config.grad_exchange
         fused = (ex is not None and not meta.get("method", 0) and bwd_prec == _lib.PREC["fp32"] and (D, H) == (16, 16))
         pdl = config.pdl
@@ -445,6 +438,19 @@ class _Rk4(torch.autograd.Function):
         needs = ctx.needs_input_grad
         gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[3:7], reduced=fused)
         return (grad_y0 if needs[0] else None), None, None, gW1, gb1, gW2, gb2
+
+
+def _bwd_precision(meta, D, H):
+    """Which adjoint kernel backs a tensor-core forward: wide field (D=64, H=256) in bf16 mode -> the tcgen05 adjoint
+    (csrc/tc_rk4_adj_wide.cu) by default; reference shape -> opt-in (options['bwd_precision']='bf16', tc_rk4_adj_small.cu).
+    Everything else backpropagates with the FP32 kernels from the stored trajectory (inside the 2e-3 budget of tf32/bf16)."""
+    want = meta.get("bwd_precision")
+    if meta["adjoint"] and meta["precision"] == _lib.PREC["bf16"]:
+        if (D, H) == (64, 256) and want in (None, "bf16"):
+            return _lib.PREC["bf16"]
+        if (D, H) == (16, 16) and want == "bf16":
+            return _lib.PREC["bf16"]
+    return _lib.PREC["fp32"]
 
 
 def _dt_arg(dt):
@@ -699,7 +705,11 @@ _LAST_ADJ_LOG = [None]
 def last_adjoint_log() -> Optional[StepLog]:
     """Step log of the most recent continuous dopri5 adjoint solve (attempts of all intervals back to back; `t0` is not
     recorded).  Reading synchronises."""
-    return _LAST_ADJ_LOG[0]
+    v = _LAST_ADJ_LOG[0]
+    if isinstance(v, tuple):    # the C++ host ran the backward: fetch the log it kept
+        raw = _ext[0].last_adjoint_log()
+        return StepLog(raw, v[1]) if raw.numel() else None
+    return v
 
 
 class _Dopri5Adjoint(torch.autograd.Function):
@@ -903,6 +913,98 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
 
 
 # ------------------------------------------------------------------------------------------------------------
+# The thin C++ host (csrc_torch/gode_torch.cpp -> _gode_torch.so): autograd node, allocations, workspace and the two C-ABI
+# launches of an rk4 / dopri5 call in C++, no Python in the backward.  The Python above turns a call into a PLAN once and
+# caches it by everything the plan depends on; per call what is left here is the argument checks, one dict lookup and one
+# extension call.  Calls that need something the C++ host does not do (data-parallel exchanges, NVTX ranges, eager status
+# checks, euler / midpoint, per-trajectory or world-scope step control, step_size) run on the Python autograd.Functions —
+# same C ABI, same kernels.
+_ext = [None, False]   # (module, load attempted)
+_FRONT = {}            # call key -> (kind, plan id, log capacity) | False (not eligible)
+
+
+def _load_ext():
+    if not _ext[1]:
+        _ext[1] = True
+        try:
+            from . import _gode_torch as m
+        except ImportError as e:   # not built: the Python host is complete on its own; say so once
+            warnings.warn("gan_ode_b200._gode_torch is not built ({}); using the Python autograd host. "
+                          "`python -m gan_ode_b200.build` builds it.".format(e))
+            return None
+        L = _lib.lib()
+        names = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd",
+                 "gode_dopri5_adjoint_bwd", "gode_rk4_bwd_workspace_bytes", "gode_dopri5_workspace_bytes",
+                 "gode_dopri5_adjoint_workspace_bytes", "gode_param_count", "gode_stream_capture_id",
+                 "gode_set_thread_launch_flags", "gode_strerror")
+        m.bind({n: C.cast(getattr(L, n), C.c_void_p).value for n in names})
+        _ext[0] = m
+    return _ext[0]
+
+
+def _ext_enabled():
+    return (config.use_cpp_host and config.grad_allreduce in (None, False) and config.grad_exchange is None
+            and not config.nvtx)
+
+
+def _plan_for(tag, meta, dt, D, H):
+    """Turn a prepared call into a C++ plan, or return False if the C++ host does not cover it."""
+    m = _load_ext()
+    if m is None or meta.get("check") or meta.get("method", 0) or meta.get("world") is not None:
+        return False
+    if tag == "rk4":
+        host = isinstance(dt, np.ndarray)
+        pid = m.make_plan(0, meta["T"], meta["layout"], meta["precision"], _bwd_precision(meta, D, H), bool(meta["adjoint"]),
+                          dt.tobytes() if host else b"", None if host else dt, b"", b"", b"", 15, False)
+        return (0, pid, 0)
+    o = meta["opts"]
+    if tag == "dopri5":
+        pid = m.make_plan(1, meta["T"], meta["layout"], meta["precision"], 0, False, b"", None, meta["t64"].tobytes(), bytes(o),
+                          b"", 15, bool(meta["keep_ckpt"]))
+        return (1, pid, o.log_capacity)
+    if tag == "dopri5_adjoint":
+        pid = m.make_plan(2, meta["T"], meta["layout"], meta["precision"], 0, True, b"", None, meta["t64"].tobytes(), bytes(o),
+                          bytes(meta["adj_opts"]), meta["param_mask"], False)
+        return (2, pid, o.log_capacity, meta["adj_opts"].log_capacity)
+    return False
+
+
+def _run_plan(plan, y0, W1, b1, W2, b2):
+    m = _ext[0]
+    if plan[0] == 0:
+        return m.rk4(y0, W1, b1, W2, b2, plan[1], config.pdl)
+    if plan[0] == 1:
+        sol, raw = m.dopri5(y0, W1, b1, W2, b2, plan[1], config.pdl)
+        _LAST_LOG[0] = StepLog(raw, plan[2])
+        return sol
+    sol, raw = m.dopri5_adjoint(y0, W1, b1, W2, b2, plan[1])
+    _LAST_LOG[0] = StepLog(raw, plan[2])
+    _LAST_ADJ_LOG[0] = ("ext", plan[3])
+    return sol
+
+
+def _front_key(y0, t, rtol, atol, method, options, adjoint, adj, weights):
+    """Everything a plan depends on, hashable — or None if this call cannot be keyed (device-resident t, tensor tolerances,
+    unhashable option values): such calls take the general path."""
+    if t.is_cuda or isinstance(rtol, torch.Tensor) or isinstance(atol, torch.Tensor):
+        return None
+    try:
+        okey = tuple(sorted(options.items())) if options else ()
+        akey = None
+        if adj is not None:
+            akey = (adj[0], adj[1], tuple(sorted(adj[2].items())) if adj[2] else adj[2])
+        W1 = weights[0]
+        grad = torch.is_grad_enabled()
+        pmask = sum(1 << k for k, q in enumerate(weights) if q.requires_grad)
+        key = (method, adjoint, rtol, atol, okey, akey, t.dtype, t.detach().numpy().tobytes(), W1.shape[1], W1.shape[0],
+               grad and (y0.requires_grad or pmask != 0), pmask if grad else 0,
+               config.layout, config.precision, config.dopri5_adjoint, config.ckpt_capacity, config.log_capacity)
+        hash(key)
+        return key
+    except TypeError:
+        return None
+
+
 def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
     W1, b1, W2, b2 = recognise_field(func)
     _check_common(y0, t)
@@ -915,6 +1017,29 @@ def _solve(func, y0, t, rtol, atol, method, options, adjoint: bool, adj=None):
 
 def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, weights):
     W1, b1, W2, b2 = weights
+    fkey = None
+    if _ext_enabled():
+        fkey = _front_key(y0, t, rtol, atol, method, options, adjoint, adj, weights)
+        plan = _FRONT.get(fkey) if fkey is not None else None
+        if plan:
+            if y0.shape[1] != W1.shape[1]:
+                raise ValueError("y0 has {} features but func expects {}".format(y0.shape[1], W1.shape[1]))
+            return _run_plan(plan, y0, W1, b1, W2, b2)
+        if plan is False:
+            fkey = None     # known not to be coverable: skip the plan attempt below
+
+    def dispatch(tag, fn, meta, dt=None):
+        """The one place a prepared call is launched: through the C++ host if it covers the call, else the Python Function."""
+        if fkey is not None:
+            plan = _plan_for(tag, meta, dt, D, H)
+            if len(_FRONT) < 512:
+                _FRONT[fkey] = plan
+            if plan:
+                return _run_plan(plan, y0, W1, b1, W2, b2)
+        if tag == "rk4":
+            return fn.apply(y0, dt, meta, W1, b1, W2, b2)
+        return fn.apply(y0, meta, W1, b1, W2, b2)
+
     options = {} if options is None else dict(options)
     if method is None:
         method = "dopri5"
@@ -955,7 +1080,7 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
 
             return _substepped(apply_fixed, y0, t, step_size, options.get("layout", config.layout))
         dt = _rk4_dt(t, options, y0.device)
-        return _Rk4.apply(y0, dt, meta, W1, b1, W2, b2)
+        return dispatch("rk4", _Rk4, meta, dt)
 
     if method == "dopri5":
         if not (D == 16 and H == 16):
@@ -973,7 +1098,7 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         meta["traj_log_capacity"] = int(options.get("traj_log_capacity", 0))  # per-attempt logs per trajectory (tests)
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
         if meta["opts"].norm_scope == _lib.NORM_TRAJ:
-            return _Dopri5Traj.apply(y0, meta, W1, b1, W2, b2)
+            return dispatch("dopri5_traj", _Dopri5Traj, meta)
         mode = options.get("adjoint", config.dopri5_adjoint)
         if mode not in ("continuous", "discrete"):
             raise ValueError("options['adjoint'] must be 'continuous' or 'discrete'")
@@ -995,8 +1120,8 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
             meta["param_mask"] = sum(1 << k for k, q in enumerate((W1, b1, W2, b2)) if q.requires_grad)
             meta["adj_opts"] = _adaptive_opts(rtol if a_rtol is None else a_rtol, atol if a_atol is None else a_atol,
                                               dict(a_options), fsign)
-            return _Dopri5Adjoint.apply(y0, meta, W1, b1, W2, b2)
-        return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
+            return dispatch("dopri5_adjoint", _Dopri5Adjoint, meta)
+        return dispatch("dopri5", _Dopri5, meta)
 
     raise NotImplementedError('method "{}" is not built (rk4, euler, midpoint and dopri5 are; SURVEY §8f-4)'.format(method))
 

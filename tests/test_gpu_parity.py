@@ -387,6 +387,53 @@ def test_persistent_workspace_across_kernels_and_grid_sizes():
                     assert all(torch.equal(a, b) for a, b in zip(out, first[key])), (rep, key)
 
 
+def test_cpp_host_and_python_host_launch_the_same_thing():
+    """The thin C++ host (gan_ode_b200._gode_torch: autograd node, allocations, workspace and launches in C++) is the default
+    for rk4 / dopri5 calls; the Python autograd.Functions are the general path.  Same C ABI, same kernels: bit-identical."""
+    _need_gpu()
+    import importlib
+    api = importlib.import_module("gan_ode_b200.odeint")
+    assert api._load_ext() is not None, "gan_ode_b200/_gode_torch.so is not built"
+    f = clone_to(make_field(seed=21, scale=2.0), DEV)
+    params = list(f.parameters())
+    torch.manual_seed(3)
+    y0 = torch.randn(300, 16, device=DEV, requires_grad=True)
+    cases = [(gode.odeint_adjoint, dict(method="rk4"), _t16()),
+             (gode.odeint, dict(method="rk4", options={"layout": "btd"}), torch.linspace(1, 0, 9)),
+             (gode.odeint_adjoint, dict(method="rk4", options={"precision": "bf16", "bwd_precision": "bf16"}), _t16()),
+             (gode.odeint, dict(method="dopri5", rtol=1e-5, atol=1e-5), _t16()),
+             (gode.odeint_adjoint, dict(rtol=1e-6, atol=1e-7, adjoint_rtol=1e-5, adjoint_atol=1e-6), torch.tensor([0.0, 1.0])),
+             (gode.odeint_adjoint, dict(method="dopri5", rtol=1e-5, atol=1e-5, options={"adjoint": "discrete"}), _t16())]
+    for solve, kw, t in cases:
+        g = torch.randn(len(t), 300, 16, device=DEV)
+        outs = []
+        for cpp in (True, False, True):
+            gode.config.use_cpp_host = cpp
+            try:
+                sol = solve(f, y0, t, **kw)
+                grads = torch.autograd.grad(sol, [y0] + params, g)
+            finally:
+                gode.config.use_cpp_host = True
+            outs.append([sol.detach()] + list(grads))
+        for a, b, c in zip(*outs):
+            assert torch.equal(a, b) and torch.equal(a, c), (solve.__name__, kw)
+    assert len(api._FRONT) >= len(cases) and all(api._FRONT.values())   # every one of them went through a C++ plan
+    # no-grad calls and frozen parameters
+    with torch.no_grad():
+        a = gode.odeint(f, y0, _t16(), method="dopri5", rtol=1e-5, atol=1e-5)
+    gode.config.use_cpp_host = False
+    try:
+        with torch.no_grad():
+            b = gode.odeint(f, y0, _t16(), method="dopri5", rtol=1e-5, atol=1e-5)
+    finally:
+        gode.config.use_cpp_host = True
+    assert torch.equal(a, b) and gode.last_step_log().status == 0
+    f.fn[0].weight.requires_grad_(False)
+    sol = gode.odeint_adjoint(f, y0.detach(), _t16(), method="rk4")
+    sol.sum().backward()
+    assert f.fn[0].weight.grad is None and f.fn[2].weight.grad is not None
+
+
 def test_unrecognised_field_raises():
     _need_gpu()
 

@@ -46,6 +46,9 @@ def wired(monkeypatch):
     monkeypatch.setattr(importlib.import_module("gan_ode_b200.odernn"), "_stream", lambda: 0)   # (imported by name there)
 
     monkeypatch.setattr(api, "_require_cuda", lambda *a, **k: None)   # the device gate is the one thing switched off here
+    # these tests watch the PYTHON host cross the C ABI; the C++ host (gan_ode_b200._gode_torch) binds the real entry points
+    # by address and needs CUDA tensors — it is what the -m gpu suite runs by default
+    monkeypatch.setattr(api.config, "use_cpp_host", False)
     return r
 
 
