@@ -95,8 +95,11 @@ def build_torch_ext(force: bool = False) -> str:
     inc = ce.include_paths() + [sysconfig.get_paths()["include"], os.path.join(cuda_home, "include"),
                                 os.path.join(ROOT, "include")]
     libdir = ce.library_paths()[0]
-    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-DTORCH_EXTENSION_NAME=_gode_torch",
+    # The SYSTEM g++ (dynamic libstdc++, the one torch's libraries were linked against).  $CXX is deliberately not honoured:
+    # in this image it points at /opt/gcc, which links libstdc++ statically into the module — two C++ runtimes in one
+    # process, and the first exception thrown across the boundary (any TORCH_CHECK) segfaults.
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_gode_torch",
            "-DTORCH_API_INCLUDE_EXTENSION_H", "-D_GLIBCXX_USE_CXX11_ABI={}".format(int(torch._C._GLIBCXX_USE_CXX11_ABI)),
            *["-I" + i for i in inc], TORCH_SRC, "-o", TORCH_EXT, "-L" + libdir, "-Wl,-rpath," + libdir,
            "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch", "-ltorch_python"]

@@ -69,8 +69,40 @@ void bind(const std::unordered_map<std::string, uint64_t>& a) {
   api.strerror_ = reinterpret_cast<decltype(api.strerror_)>(get("gode_strerror"));
 }
 
+// ---- errors: the same Python exception types the Python host raises ------------------------------------------------------
+// GodeError for C-ABI failures; for a failed adaptive solve (status mailbox != 0) the Python check_status() is called under
+// the GIL so that torchdiffeq's AssertionError texts come out identically.  A backward runs on autograd's device thread:
+// the Python error travels to the caller as a pybind11 error_already_set, which torch's boundary restores.
+PyObject* g_error_type = nullptr;       // gan_ode_b200.GodeError
+PyObject* g_check_status = nullptr;     // gan_ode_b200.odeint.check_status
+const volatile int32_t* g_mailbox = nullptr;
+
+void set_hooks(py::object error_type, py::object check_status, uint64_t mailbox_addr) {
+  g_error_type = error_type.release().ptr();
+  g_check_status = check_status.release().ptr();
+  g_mailbox = reinterpret_cast<const volatile int32_t*>(mailbox_addr);
+}
+
+[[noreturn]] void fail(const std::string& msg) {
+  if (g_error_type) {
+    py::gil_scoped_acquire gil;
+    PyErr_SetString(g_error_type, msg.c_str());
+    throw py::error_already_set();
+  }
+  TORCH_CHECK(false, msg);
+}
+
 void check(int rc, const char* what) {
-  TORCH_CHECK(rc == 0, what, " failed: ", api.strerror_ ? api.strerror_(rc) : "?", " (code ", rc, ")");
+  if (rc != 0) fail(c10::str(what, " failed: ", api.strerror_ ? api.strerror_(rc) : "?", " (code ", rc, ")"));
+}
+
+inline void poll_mailbox() {   // a plain host-memory read on the success path
+  if (g_mailbox && *g_mailbox != 0 && g_check_status) {
+    py::gil_scoped_acquire gil;
+    PyObject* r = PyObject_CallNoArgs(g_check_status);
+    if (!r) throw py::error_already_set();
+    Py_DECREF(r);
+  }
 }
 
 // ---- plans ---------------------------------------------------------------------------------------------------------------
@@ -158,6 +190,19 @@ at::Tensor workspace(const at::Device& dev, size_t nbytes, cudaStream_t st) {
 }
 
 // ---- helpers ---------------------------------------------------------------------------------------------------------------
+// Device guard + current stream of the tensor's device.  (CPU tensors only occur in the host-wiring tests, which bind
+// recording stubs instead of libgode.so's entry points: no guard, null stream.)
+struct OnDevice {
+  c10::cuda::OptionalCUDAGuard guard;
+  cudaStream_t stream = nullptr;
+  explicit OnDevice(const at::Tensor& t) {
+    if (t.is_cuda()) {
+      guard.set_device(t.device());
+      stream = c10::cuda::getCurrentCUDAStream(t.device().index()).stream();
+    }
+  }
+};
+
 inline at::Tensor f32c(const at::Tensor& t) {   // fp32, contiguous, 16-byte aligned; the common case returns t itself
   if (t.scalar_type() == at::kFloat && t.is_contiguous() && !(reinterpret_cast<uintptr_t>(t.data_ptr()) & 15)) return t;
   at::Tensor u = t.detach().to(at::kFloat).contiguous();
@@ -198,8 +243,8 @@ struct Rk4Function : public torch::autograd::Function<Rk4Function> {
   static at::Tensor forward(AutogradContext* ctx, const at::Tensor& y0, const at::Tensor& W1, const at::Tensor& b1,
                             const at::Tensor& W2, const at::Tensor& b2, int64_t plan_id, bool pdl) {
     const Plan& p = plan_of(plan_id);
-    c10::cuda::CUDAGuard guard(y0.device());
-    cudaStream_t st = c10::cuda::getCurrentCUDAStream().stream();
+    OnDevice on(y0);
+    cudaStream_t st = on.stream;
     const at::Tensor y = f32c(y0), w1 = f32c(W1), c1 = f32c(b1), w2 = f32c(W2), c2 = f32c(b2);
     const int64_t B = y.size(0), D = y.size(1), H = w1.size(0), T = p.T;
     at::Tensor buf = p.layout == GODE_LAYOUT_TBD ? at::empty({T, B, D}, y.options()) : at::empty({B, T, D}, y.options());
@@ -218,8 +263,8 @@ struct Rk4Function : public torch::autograd::Function<Rk4Function> {
     const at::Tensor &buf = saved[0], &w1 = saved[1], &c1 = saved[2], &w2 = saved[3], &c2 = saved[4];
     const Plan& p = plan_of(ctx->saved_data["plan"].toInt());
     const bool pdl = ctx->saved_data["pdl"].toBool();
-    c10::cuda::CUDAGuard guard(buf.device());
-    cudaStream_t st = c10::cuda::getCurrentCUDAStream().stream();
+    OnDevice on(buf);
+    cudaStream_t st = on.stream;
     const int64_t T = p.T, H = w1.size(0);
     const int64_t B = p.layout == GODE_LAYOUT_TBD ? buf.size(1) : buf.size(0), D = buf.size(2);
     const at::Tensor g = grad_in_layout(grads[0], p.layout);
@@ -254,9 +299,8 @@ struct Dp5Fwd {
   int kc = 0;
 };
 Dp5Fwd dopri5_forward(const Plan& p, const at::Tensor& y0, const at::Tensor& W1, const at::Tensor& b1, const at::Tensor& W2,
-                      const at::Tensor& b2, bool keep) {
+                      const at::Tensor& b2, bool keep, cudaStream_t st) {
   Dp5Fwd r;
-  cudaStream_t st = c10::cuda::getCurrentCUDAStream().stream();
   const at::Tensor y = f32c(y0);
   r.w1 = f32c(W1); r.c1 = f32c(b1); r.w2 = f32c(W2); r.c2 = f32c(b2);
   const int64_t B = y.size(0), D = y.size(1), H = r.w1.size(0), T = p.T;
@@ -288,8 +332,8 @@ struct Dopri5Function : public torch::autograd::Function<Dopri5Function> {
   static variable_list forward(AutogradContext* ctx, const at::Tensor& y0, const at::Tensor& W1, const at::Tensor& b1,
                                const at::Tensor& W2, const at::Tensor& b2, int64_t plan_id, bool pdl) {
     const Plan& p = plan_of(plan_id);
-    c10::cuda::CUDAGuard guard(y0.device());
-    Dp5Fwd r = dopri5_forward(p, y0, W1, b1, W2, b2, p.keep_ckpt);
+    OnDevice on(y0);
+    Dp5Fwd r = dopri5_forward(p, y0, W1, b1, W2, b2, p.keep_ckpt, on.stream);
     if (p.keep_ckpt) ctx->save_for_backward({r.raw, r.ckpt, r.acc, r.w1, r.c1, r.w2, r.c2});
     ctx->saved_data["plan"] = plan_id;
     ctx->saved_data["pdl"] = pdl;
@@ -300,14 +344,15 @@ struct Dopri5Function : public torch::autograd::Function<Dopri5Function> {
 
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     const auto saved = ctx->get_saved_variables();
-    TORCH_CHECK(saved.size() == 7, "dopri5 forward ran without checkpoints (inputs did not require grad)");
+    if (saved.size() != 7) fail("dopri5 forward ran without checkpoints (inputs did not require grad)");
+    poll_mailbox();   // a forward that has already failed on the device is reported here, before the replay is launched
     const at::Tensor &raw = saved[0], &ckpt = saved[1], &acc = saved[2], &w1 = saved[3], &c1 = saved[4], &w2 = saved[5],
                      &c2 = saved[6];
     const Plan& p = plan_of(ctx->saved_data["plan"].toInt());
     const bool pdl = ctx->saved_data["pdl"].toBool();
     const int kc = (int)ctx->saved_data["kc"].toInt();
-    c10::cuda::CUDAGuard guard(ckpt.device());
-    cudaStream_t st = c10::cuda::getCurrentCUDAStream().stream();
+    OnDevice on(ckpt);
+    cudaStream_t st = on.stream;
     const int64_t T = p.T, B = ckpt.size(1), D = ckpt.size(2), H = w1.size(0);
     const at::Tensor g = grad_in_layout(grads[0], p.layout);
     at::Tensor gy = at::empty({B, D}, ckpt.options());
@@ -334,8 +379,8 @@ struct Dopri5AdjointFunction : public torch::autograd::Function<Dopri5AdjointFun
   static variable_list forward(AutogradContext* ctx, const at::Tensor& y0, const at::Tensor& W1, const at::Tensor& b1,
                                const at::Tensor& W2, const at::Tensor& b2, int64_t plan_id) {
     const Plan& p = plan_of(plan_id);
-    c10::cuda::CUDAGuard guard(y0.device());
-    Dp5Fwd r = dopri5_forward(p, y0, W1, b1, W2, b2, false);
+    OnDevice on(y0);
+    Dp5Fwd r = dopri5_forward(p, y0, W1, b1, W2, b2, false, on.stream);
     ctx->save_for_backward({r.buf, r.w1, r.c1, r.w2, r.c2});
     ctx->saved_data["plan"] = plan_id;
     ctx->mark_non_differentiable({r.raw});
@@ -346,8 +391,8 @@ struct Dopri5AdjointFunction : public torch::autograd::Function<Dopri5AdjointFun
     const auto saved = ctx->get_saved_variables();
     const at::Tensor &buf = saved[0], &w1 = saved[1], &c1 = saved[2], &w2 = saved[3], &c2 = saved[4];
     const Plan& p = plan_of(ctx->saved_data["plan"].toInt());
-    c10::cuda::CUDAGuard guard(buf.device());
-    cudaStream_t st = c10::cuda::getCurrentCUDAStream().stream();
+    OnDevice on(buf);
+    cudaStream_t st = on.stream;
     const int64_t T = p.T, H = w1.size(0);
     const int64_t B = p.layout == GODE_LAYOUT_TBD ? buf.size(1) : buf.size(0), D = buf.size(2);
     const at::Tensor g = grad_in_layout(grads[0], p.layout);
@@ -364,9 +409,9 @@ struct Dopri5AdjointFunction : public torch::autograd::Function<Dopri5AdjointFun
                                           reinterpret_cast<double*>(base + 64 + 8 * cap),
                                           reinterpret_cast<float*>(base + 64 + 16 * cap), base + 64 + 20 * cap, ws.data_ptr(),
                                           ws_bytes, st);
-    TORCH_CHECK(rc != GODE_ERR_COOP,
-                "the continuous dopri5 adjoint keeps the whole batch co-resident (at most 18944 trajectories per GPU); shard "
-                "the batch, or pass options={'adjoint': 'discrete'} for the gradient of the recorded steps");
+    if (rc == GODE_ERR_COOP)
+      fail("the continuous dopri5 adjoint keeps the whole batch co-resident (at most 18944 trajectories per GPU); shard the "
+           "batch, or pass options={'adjoint': 'discrete'} for the gradient of the recorded steps (gode_dopri5_backprop_bwd)");
     check(rc, "gode_dopri5_adjoint_bwd");
     {
       std::lock_guard<std::mutex> lk(g_mu);
@@ -407,6 +452,7 @@ at::Tensor last_adjoint_log() {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "thin PyTorch C++ host of gan_ode_b200 over the C ABI of libgode.so (include/gode.h)";
   m.def("bind", &bind, "hand over the addresses of the libgode.so entry points (name -> address)");
+  m.def("set_hooks", &set_hooks, "GodeError type, check_status callable, address of the status mailbox (0: none)");
   m.def("make_plan", &make_plan);
   m.def("drop_plan", &drop_plan);
   m.def("rk4", &rk4);

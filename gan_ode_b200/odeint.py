@@ -938,6 +938,8 @@ def _load_ext():
                  "gode_dopri5_adjoint_workspace_bytes", "gode_param_count", "gode_stream_capture_id",
                  "gode_set_thread_launch_flags", "gode_strerror")
         m.bind({n: C.cast(getattr(L, n), C.c_void_p).value for n in names})
+        mb = _mailbox_view()
+        m.set_hooks(GodeError, check_status, _mailbox[0].data_ptr() if mb is not None else 0)
         _ext[0] = m
     return _ext[0]
 

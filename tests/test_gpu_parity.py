@@ -417,7 +417,12 @@ def test_cpp_host_and_python_host_launch_the_same_thing():
             outs.append([sol.detach()] + list(grads))
         for a, b, c in zip(*outs):
             assert torch.equal(a, b) and torch.equal(a, c), (solve.__name__, kw)
-    assert len(api._FRONT) >= len(cases) and all(api._FRONT.values())   # every one of them went through a C++ plan
+    W = gode.recognise_field(f)
+    for solve, kw, t in cases:     # every one of them went through a C++ plan
+        adj = (kw.get("adjoint_rtol"), kw.get("adjoint_atol"), None) if solve is gode.odeint_adjoint and kw.get("method", "dopri5") == "dopri5" else None
+        key = api._front_key(y0, t, kw.get("rtol", 1e-7), kw.get("atol", 1e-9), kw.get("method"), kw.get("options"),
+                             solve is gode.odeint_adjoint, adj, W)
+        assert api._FRONT.get(key), (solve.__name__, kw)
     # no-grad calls and frozen parameters
     with torch.no_grad():
         a = gode.odeint(f, y0, _t16(), method="dopri5", rtol=1e-5, atol=1e-5)
