@@ -258,6 +258,25 @@ def measure_extras(gode, dev):
         att = sum(fr["n_attempts"] for fr in gode.odernn.last_log().frames())
         out["odernn_fwd_bwd_B8192_F16_%s_adjoint" % mode] = {"ms": sec * 1e3, "attempted_steps_fwd": att,
                                                              "trajectory_steps_per_s": Br * att / sec}
+    # configs[3] end to end: the reference's training loop (ucf_moco_ode.py:113-163) on synthetic clips, 32
+    # videos, D=64 / H=256 motion ODE through the shim (scripts/train_dp_harness.py; reference nets when mounted)
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("train_dp_harness", os.path.join(ROOT, "scripts", "train_dp_harness.py"))
+        hmod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(hmod)
+        prev = (gode.config.layout, gode.config.precision)
+        try:
+            res = hmod.run_harness(iters=5, batch=32, precision="bf16", warmup=2)
+        finally:
+            gode.config.layout, gode.config.precision = prev
+            sys.modules.pop("torchdiffeq", None)
+            sys.modules.pop("torchsde", None)
+        out["train_dp_harness_configs3"] = {k: res[k] for k in ("nets", "videos_per_gpu", "iters_per_s", "ms_per_iter",
+                                                                "ode_forward_ms_per_iter", "ode_forward_share",
+                                                                "ode_trajectories_per_iter")}
+    except Exception as e:  # noqa: BLE001
+        out["train_dp_harness_configs3"] = {"error": str(e)[:200]}
     return out
 
 
