@@ -10,6 +10,7 @@ from ._lib import GodeError  # noqa: F401
 from .graphed import GraphedSolveStep  # noqa: F401
 from .sdeint import GridBrownian, PhiloxBrownian, TableBrownian, adjoint_grid, sdeint, sdeint_adjoint  # noqa: F401
 from .odernn import gru_jump, odernn_codes  # noqa: F401
+from .fused import FusedLatentSampler, fused_sample_z  # noqa: F401
 
 __version__ = "0.1.0"
 

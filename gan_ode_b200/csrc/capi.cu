@@ -149,6 +149,34 @@ int gode_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float
                         grad_y0, grad_params, workspace, ws_bytes, stream);
 }
 
+int gode_rk4_sampler_fwd(const float* pre_Wa, const float* pre_ba, const float* pre_Wb, const float* pre_bb, float pre_slope,
+                         int pre_hidden, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+                         int dt_on_device, int B, int D, int H, int T, uint64_t seed, int64_t traj_offset,
+                         const int64_t* traj_ids, int out_layout, float* out, int ld_out, float* noise_out,
+                         gode_stream_t stream) {
+  if (!W1 || !b1 || !W2 || !b2 || !dt || !out || B <= 0 || T < 2 ||
+      (out_layout != GODE_LAYOUT_TBD && out_layout != GODE_LAYOUT_BTD) || (pre_Wa && (!pre_ba || !pre_Wb || !pre_bb)) ||
+      (ld_out != 0 && (out_layout != GODE_LAYOUT_BTD || ld_out < D || (ld_out & 1))) || (reinterpret_cast<uintptr_t>(out) & 7))
+    return GODE_ERR_ARG;   // (rows are read / written as float2: even strides, 8-byte aligned base)
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_fused_sampler_fwd(pre_Wa, pre_ba, pre_Wb, pre_bb, pre_slope, pre_hidden, W1, b1, W2, b2, dt, dt_on_device, B,
+                                     D, H, T, seed, traj_offset, reinterpret_cast<const long long*>(traj_ids), out_layout, out,
+                                     ld_out, noise_out, (cudaStream_t)stream);
+}
+
+int gode_rk4_adjoint_bwd_strided(const float* traj, int ld_traj, const float* grad_traj, int ld_grad, const float* W1,
+                                 const float* b1, const float* W2, const float* b2, const float* dt, int dt_on_device, int B,
+                                 int D, int H, int T, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                                 gode_stream_t stream) {
+  if (bad_common(traj, W1, b1, W2, b2, B, T, GODE_LAYOUT_BTD) || !grad_traj || !dt || !grad_y0 || !grad_params || !workspace ||
+      ld_traj < D || ld_grad < D || (ld_traj & 1) || (ld_grad & 1) || (reinterpret_cast<uintptr_t>(traj) & 7) ||
+      (reinterpret_cast<uintptr_t>(grad_traj) & 7))
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return rk4_small_bwd(true, traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, GODE_LAYOUT_BTD, grad_y0,
+                       grad_params, workspace, ws_bytes, (cudaStream_t)stream, GODE_METHOD_RK4, nullptr, ld_traj, ld_grad);
+}
+
 int gode_rk4_bwd_world(int adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                        const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                        int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,

@@ -85,7 +85,12 @@ int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method = GODE_METHOD_RK4, const GodeWorld* xchg = nullptr);
+                  int method = GODE_METHOD_RK4, const GodeWorld* xchg = nullptr, int ld_traj = 0, int ld_grad = 0);
+int rk4_small_fused_sampler_fwd(const float* pre_Wa, const float* pre_ba, const float* pre_Wb, const float* pre_bb,
+                                float pre_slope, int pre_hidden, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                                unsigned long long seed, long long traj_offset, const long long* traj_ids, int out_layout,
+                                float* out, int ld_out, float* noise_out, cudaStream_t st);
 
 size_t dopri5_small_workspace_bytes(int B, int D, int H);
 int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,

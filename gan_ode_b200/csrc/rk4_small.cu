@@ -4,6 +4,7 @@
 //   rk4_backprop_bwd_kernel autograd through the same forward (discretise-then-optimise)        
 // One launch per call: every trajectory's whole time loop runs inside the kernel.
 #include "small_field.cuh"
+#include "philox.cuh"
 #include "launch.h"
 
 namespace gode {
@@ -21,36 +22,103 @@ struct Rk4Args {
   ReduceWs ws;
   const float* dt_dev;      // device dt table, or nullptr -> dt_val
   int B, T, layout;
+  // (B,T,D) layout only: row stride of traj / traj_in and of grad_traj in floats (0 = D).  Lets the codes live inside a wider
+  // buffer — the motion columns of the generator's z = cat([z_content, z_motion], 1) (models/mocogan.py:264-267).
+  int ld_traj, ld_grad;
+  // fused sampler prologue (models/mocogan_ode.py:136-140): y0 = linear(x), x ~ N(0, I) from Philox stream 2,
+  // linear = LeakyReLU(Wb LeakyReLU(Wa x + ba) + bb) (pre_Wa null: linear is nn.Identity, y0 = x)
+  const float *pre_Wa, *pre_ba, *pre_Wb, *pre_bb;
+  float pre_slope;
+  int pre_hidden;           // 64 in the reference
+  unsigned long long seed;
+  long long traj_offset;    // global index of local trajectory 0
+  const long long* traj_ids;  // optional (B): global trajectory index of every row (subset solves), else traj_offset + b
+  float* noise_out;         // (B,D): the drawn x, kept for the pre-MLP's backward
   float dt_val[GODE_MAX_HOST_STEPS];
 };
 
-__device__ __forceinline__ size_t traj_off(int layout, int s, int b, int B, int T, int D) {
-  return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
+__device__ __forceinline__ size_t traj_off(int layout, int s, int b, int B, int T, int D, int ld = 0) {
+  return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * (size_t)(ld ? ld : D);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int D, int H, int L, int WARPS, int METHOD>
+constexpr int kPreHidden = 64;   // width of the reference's pre-MLP (models/mocogan_ode.py:123-131)
+
+// FUSED: the sampler's prologue runs in the kernel — x from Philox, y0 = linear(x) — instead of reading y0.
+template <int D, int H, int L, int WARPS, int METHOD, bool FUSED = false>
 __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_constant__ Rk4Args p) {
   griddep_launch_dependents();   // a backward launched with PDL may stage its weights under this kernel's tail
   using S = Shape<D, H, L>;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
+  // fused prologue: pre-MLP weights (row-padded) and one hidden line per trajectory of the CTA
+  constexpr int PS = D + kPad, QS = kPreHidden + kPad;
+  __shared__ __align__(16) float s_pre[FUSED ? kPreHidden * PS + D * QS + kPreHidden + D + WARPS * S::G * QS : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane / L, l = lane % L;
   FwdLines<D, H, L> ln;
   ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
+  float* s_wa = s_pre;                          // [64][PS]
+  float* s_wb = s_wa + kPreHidden * PS;         // [D][QS]
+  float* s_ba = s_wb + D * QS;                  // [64]
+  float* s_bb = s_ba + kPreHidden;              // [D]
+  float* s_hid = s_bb + D + (warp * S::G + g) * QS;   // this trajectory's hidden line
+  if constexpr (FUSED) {
+    if (p.pre_Wa) {
+      for (int e = threadIdx.x; e < kPreHidden * D; e += WARPS * 32) {
+        s_wa[(e / D) * PS + e % D] = p.pre_Wa[e];                         // Wa[j][i]
+        s_wb[(e / kPreHidden) * QS + e % kPreHidden] = p.pre_Wb[e];       // Wb[d][j]
+      }
+      for (int e = threadIdx.x; e < kPreHidden; e += WARPS * 32) s_ba[e] = p.pre_ba[e];
+      for (int e = threadIdx.x; e < D; e += WARPS * 32) s_bb[e] = p.pre_bb[e];
+    }
+    __syncthreads();
+  }
   const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
   const int stride = gridDim.x * WARPS * S::G;
   for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
     const int b = base + g;
     const bool valid = b < p.B;
     float y[S::DL];
-    if (valid) load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y);
-    else {
+    if constexpr (FUSED) {
+      // models/mocogan_ode.py:136-140: x = randn(B, D); x = self.linear(x)
+      const unsigned long long gid = (unsigned long long)(p.traj_ids ? (valid ? p.traj_ids[b] : 0) : p.traj_offset + b);
+      float x[S::DL];
+      philox_normals<S::DL>(p.seed, gid, 0, l, x, 2u);
+      if (valid && p.noise_out) store_frag<S::DL>(p.noise_out + (size_t)b * D + l * S::DL, x);
+      if (p.pre_Wa) {
+        __syncwarp();
+        store_frag<S::DL>(ln.y + l * S::DL, x);
+        __syncwarp();
+        constexpr int JL = kPreHidden / L;   // hidden units of the pre-MLP per lane
+        float hid[JL];
 #pragma unroll
-      for (int i = 0; i < S::DL; ++i) y[i] = 0.f;
+        for (int jl = 0; jl < JL; ++jl) {
+          const int j = l * JL + jl;
+          const float z = dot_smem<D>(s_wa + j * PS, ln.y) + s_ba[j];
+          hid[jl] = z > 0.f ? z : p.pre_slope * z;
+        }
+        store_frag<JL>(s_hid + l * JL, hid);
+        __syncwarp();
+#pragma unroll
+        for (int dl = 0; dl < S::DL; ++dl) {
+          const int d = l * S::DL + dl;
+          const float z = dot_smem<kPreHidden>(s_wb + d * QS, s_hid) + s_bb[d];
+          y[dl] = z > 0.f ? z : p.pre_slope * z;
+        }
+        __syncwarp();
+      } else {
+#pragma unroll
+        for (int i = 0; i < S::DL; ++i) y[i] = x[i];
+      }
+    } else {
+      if (valid) load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y);
+      else {
+#pragma unroll
+        for (int i = 0; i < S::DL; ++i) y[i] = 0.f;
+      }
     }
-    if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y);
+    if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, 0, b, p.B, p.T, D, p.ld_traj) + l * S::DL, y);
     for (int s = 0; s + 1 < p.T; ++s) {
       const float dt = dtp[s];
       float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u[S::DL], hk[S::HL];
@@ -58,7 +126,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
       if constexpr (METHOD == kEuler) {          // fixed_grid.py::Euler: dy = dt * f(t0, y0)
 #pragma unroll
         for (int i = 0; i < S::DL; ++i) y[i] = y[i] + dt * k1[i];
-        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, y);
         continue;
       }
       if constexpr (METHOD == kMidpoint) {       // fixed_grid.py::Midpoint: y_mid = y0 + f(y0) * (dt/2); dy = dt * f(y_mid)
@@ -68,7 +136,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
         mlp_forward<D, H, L>(w, ln, l, u, k2, hk);
 #pragma unroll
         for (int i = 0; i < S::DL; ++i) y[i] = y[i] + dt * k2[i];
-        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+        if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, y);
         continue;
       }
 #pragma unroll
@@ -82,7 +150,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
       mlp_forward<D, H, L>(w, ln, l, u, k4, hk);
 #pragma unroll
       for (int i = 0; i < S::DL; ++i) y[i] = y[i] + (k1[i] + 3.f * (k2[i] + k3[i]) + k4[i]) * dt * 0.125f;
-      if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D) + l * S::DL, y);
+      if (valid) store_frag<S::DL>(p.traj + traj_off(p.layout, s + 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, y);
     }
   }
 }
@@ -129,9 +197,9 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < S::DL; ++i) { yn[i] = 0.f; gn[i] = 0.f; }
     if (valid) {
-      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, a);
-      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yn);
-      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, gn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D, p.ld_grad) + l * S::DL, a);
+      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
     }
     for (int i = p.T - 1; i >= 1; --i) {
       const float dt = dtp[i - 1];
@@ -139,8 +207,8 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gprev[c] = gn[c]; }
       if (valid && i > 1) {
-        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i - 1, b, p.B, p.T, D) + l * S::DL, yn);
-        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 2, b, p.B, p.T, D) + l * S::DL, gn);
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
       }
       const float c18 = dt * 0.125f, c38 = 3.f * c18;
       const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
@@ -230,9 +298,9 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
 #pragma unroll
     for (int c = 0; c < S::DL; ++c) { yn[c] = 0.f; gn[c] = 0.f; }
     if (valid) {
-      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D) + l * S::DL, yb);
-      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, yn);
-      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D) + l * S::DL, gn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 1, b, p.B, p.T, D, p.ld_grad) + l * S::DL, yb);
+      load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 2, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
+      load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
     }
     for (int s = p.T - 2; s >= 0; --s) {
       const float dt = dtp[s];
@@ -240,8 +308,8 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_backprop_bwd_kernel(const __gr
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gs[c] = gn[c]; }
       if (valid && s > 0) {
-        load_frag<S::DL>(p.traj_in + traj_off(p.layout, s - 1, b, p.B, p.T, D) + l * S::DL, yn);
-        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, s - 1, b, p.B, p.T, D) + l * S::DL, gn);
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, s - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, s - 1, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
       }
       // recompute (same expressions as the forward kernel)
       float k1[S::DL], k2[S::DL], k3[S::DL], k4[S::DL], u2[S::DL], u3[S::DL], u4[S::DL];
@@ -377,11 +445,35 @@ int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float
   return GODE_ERR_SHAPE;
 }
 
+// SURVEY §8 f2 — the sampler fused around the solve (opt-in: it changes which random numbers are consumed).
+int rk4_small_fused_sampler_fwd(const float* pre_Wa, const float* pre_ba, const float* pre_Wb, const float* pre_bb,
+                                float pre_slope, int pre_hidden, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
+                                unsigned long long seed, long long traj_offset, const long long* traj_ids, int out_layout,
+                                float* out, int ld_out, float* noise_out, cudaStream_t st) {
+  if (pre_Wa && pre_hidden != kPreHidden) return GODE_ERR_SHAPE;
+  Rk4Args a{};
+  a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = out; a.B = B; a.T = T; a.layout = out_layout; a.ld_traj = ld_out;
+  a.pre_Wa = pre_Wa; a.pre_ba = pre_ba; a.pre_Wb = pre_Wb; a.pre_bb = pre_bb; a.pre_slope = pre_slope; a.pre_hidden = pre_hidden;
+  a.seed = seed; a.traj_offset = traj_offset; a.traj_ids = traj_ids; a.noise_out = noise_out;
+  if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
+  if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
+  constexpr int WARPS = 4;
+  using S = Shape<16, 16, 8>;
+  const int per_cta = WARPS * S::G;
+  int grid = (B + per_cta - 1) / per_cta;
+  const int cap = sm_count() * 8;
+  if (grid > cap) grid = cap;
+  rk4_fwd_kernel<16, 16, 8, WARPS, kRk4, true><<<grid, WARPS * 32, 0, st>>>(a);
+  return launch_status();
+}
+
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method, const GodeWorld* xchg) {
+                  int method, const GodeWorld* xchg, int ld_traj, int ld_grad) {
   Rk4Args a{};
+  a.ld_traj = ld_traj; a.ld_grad = ld_grad;
   if (xchg) {  // all-reduce over ranks fused into the reduction tail (small_field.cuh::reduce_param_grads)
     a.ws.w_rank = xchg->rank; a.ws.w_world = xchg->world; a.ws.w_ctr = xchg->launch_ctr;
     a.ws.w_slots = reinterpret_cast<unsigned long long* const*>(xchg->slots_dev);

@@ -12,6 +12,7 @@
 // backward kernel regenerates them from the same counters, so no noise is ever stored and results do not depend on how
 // the batch is sharded over GPUs.
 #include "small_field.cuh"
+#include "philox.cuh"
 #include "launch.h"
 
 namespace gode {
@@ -39,50 +40,6 @@ struct SdeArgs {
 
 __device__ __forceinline__ size_t sde_off(int layout, int s, int b, int B, int T, int D) {
   return layout == GODE_LAYOUT_TBD ? ((size_t)s * B + b) * D : ((size_t)b * T + s) * D;
-}
-
-// ---- Philox4x32-10 ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned int hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
-  }
-  return c;
-}
-__device__ __forceinline__ float u01(unsigned int x) { return (float)x * 2.3283064e-10f + 1.1641532e-10f; }
-
-// the lane's DL standard normals for (trajectory, step): components l*DL .. l*DL+DL-1
-template <int DL>
-__device__ __forceinline__ void philox_normals(unsigned long long seed, unsigned long long traj, int step, int l, float (&z)[DL]) {
-  static_assert(DL == 1 || DL == 2 || DL == 4, "lane slice must tile a 4-wide Philox block");
-  const int d0 = l * DL;
-  const uint4 r = philox4x32_10(make_uint4((unsigned int)traj, (unsigned int)step, (unsigned int)(d0 >> 2), 0u),
-                                make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
-  // Box–Muller on the pair(s) this lane needs only (a lane owning 1 or 2 components needs one of the block's two pairs),
-  // with the hardware transcendental units: log2 (MUFU.LG2), rsqrt/sqrt, sin/cos of 2*pi*u via sinpi/cospi-style exact
-  // range (u in (0,1) -> the argument of MUFU.SIN/COS stays in (0, 2*pi)).  Differences from the CPU contract
-  // (oracle/philox.py, numpy float32) are ~1e-6 relative, far inside the 2e-5 the stream test allows.
-  auto pair = [](unsigned int a, unsigned int b, float& n0, float& n1) {
-    const float rad = sqrtf(-1.3862944f * __log2f(u01(a)));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
-    float sn, cs;
-    __sincosf(6.2831855f * u01(b), &sn, &cs);
-    n0 = rad * sn;
-    n1 = rad * cs;
-  };
-  if constexpr (DL == 4) {
-    pair(r.x, r.y, z[0], z[1]);
-    pair(r.z, r.w, z[2], z[3]);
-  } else {
-    const bool second = (d0 & 2) != 0;
-    float n0, n1;
-    pair(second ? r.z : r.x, second ? r.w : r.y, n0, n1);
-    if constexpr (DL == 2) { z[0] = n0; z[1] = n1; }
-    else z[0] = (d0 & 1) ? n1 : n0;
-  }
 }
 
 template <int D, int H, int L>

@@ -298,6 +298,29 @@ int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* 
                     uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
                     void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- f2: the latent-motion sampler fused around the solve (models/mocogan_ode.py:133-148, models/mocogan.py:259-269) ----
+ * OPT-IN (it changes which random numbers are consumed).  One launch does what sample_z_m does in five:
+ *   x = randn(B, D)              Philox4x32-10, counter (global trajectory, 0, d/4, 2), oracle/philox.py::normals
+ *   y0 = linear(x)               LeakyReLU(Wb LeakyReLU(Wa x + ba) + bb), Wa (pre_hidden, D), Wb (D, pre_hidden); pre_Wa NULL:
+ *                                linear is nn.Identity (models/mocogan_ode.py:36-37)
+ *   odeint(..., method='rk4')    3/8 rule on the grid dt, as gode_rk4_fwd
+ *   .transpose(0,1).reshape(-1,D) and the torch.cat into z: out_layout GODE_LAYOUT_BTD with row stride ld_out floats (0 = D)
+ *                                writes row b*T + j of a (B*T, ld_out) buffer at `out` (= &z[0][dim_z_content]).
+ * traj_ids (device, B int64, or NULL): global trajectory index of every row — sample_images keeps num_samples rows of
+ * num_samples*T*2 trajectories (models/mocogan.py:287-291); solving only those gives bit-identical codes.
+ * noise_out (B,D) or NULL: the drawn x, for the pre-MLP's backward. */
+int gode_rk4_sampler_fwd(const float* pre_Wa, const float* pre_ba, const float* pre_Wb, const float* pre_bb, float pre_slope,
+                         int pre_hidden, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
+                         int dt_on_device, int B, int D, int H, int T, uint64_t seed, int64_t traj_offset,
+                         const int64_t* traj_ids, int out_layout, float* out, int ld_out, float* noise_out,
+                         gode_stream_t stream);
+/* gode_rk4_adjoint_bwd for (B,T,D) codes that live inside wider buffers: traj rows are ld_traj floats apart, upstream-gradient
+ * rows ld_grad floats apart (the gradient of z arrives as one (B*T, dim_z) tensor; its motion columns are read in place). */
+int gode_rk4_adjoint_bwd_strided(const float* traj, int ld_traj, const float* grad_traj, int ld_grad, const float* W1,
+                                 const float* b1, const float* W2, const float* b2, const float* dt, int dt_on_device, int B,
+                                 int D, int H, int T, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,
+                                 gode_stream_t stream);
+
 /* ---- f3: sdeint_adjoint with torchsde's stochastic adjoint (models/mocogan_sde.py:57-59, adjoint_method='euler') -------
  * torchsde/_core/adjoint.py re-solves every output interval backwards in time with its own dt grid, so the Brownian
  * path must answer increments over intervals that are not forward steps.  The path is sampled on CELLS = the union of the

@@ -1440,3 +1440,84 @@ def test_world_norm_needs_its_exchange_buffers():
             gode.odeint(f, y0, _t16(), method="dopri5", options={"norm": "world"})
     with pytest.raises(NotImplementedError):
         gode.odeint(f, y0, _t16(), method="dopri5", options={"norm": "max"})
+
+
+# ---- f2: the sampler fused around the solve ----------------------------------------------------------------------------------
+def _fused_reference(model, content, B, T, seed, traj_ids=None, offset=0, dtype=torch.float32):
+    """What the fused launch must equal, computed the reference's way on the CPU: x from the Philox contract
+    (oracle/philox.py::normals, stream 2), x = linear(x), oracle odeint_adjoint rk4, frame-major, cat with the content."""
+    import numpy as np
+    from oracle.philox import normals
+    ids = np.arange(B) + offset if traj_ids is None else np.asarray(traj_ids)
+    x = np.concatenate([normals(seed, ids, step=0, d_block=k, stream=2) for k in range(4)], axis=1)
+    x = torch.from_numpy(x).to(dtype)
+    y0 = model.linear(x)
+    zt = tdq.odeint_adjoint(model.ode_fn, y0, torch.linspace(0, 1, T).float().to(dtype), method="rk4")
+    zm = zt.transpose(0, 1).reshape(-1, 16)
+    if content is None:
+        return zm
+    return torch.cat([content.to(dtype).repeat_interleave(T, 0), zm], dim=1)
+
+
+@pytest.mark.parametrize("B,identity", [(1, False), (37, False), (1024, False), (64, True)])
+def test_fused_sampler_matches_the_reference_call_chain(B, identity):
+    """randn (Philox) + pre-MLP + rk4 solve + transpose/reshape + cat in ONE launch against the same chain on the CPU oracle:
+    codes <= 1e-5, gradients to the pre-MLP and to the ODEFunc <= 1e-5 (fp64 oracle as arbiter), content columns exact."""
+    _need_gpu()
+    import copy
+    from tests.caller_model import LatentMotionODE
+    torch.manual_seed(B)
+    cpu = LatentMotionODE(16, 16)
+    if identity:
+        cpu.linear = torch.nn.Identity()
+    gpu = copy.deepcopy(cpu).to(DEV)
+    T, seed = 16, 0xABCDEF0123 + B
+    content = torch.randn(B, 50)
+    w = torch.randn(B * T, 66)
+    z = gode.fused_sample_z(gpu.linear, gpu.ode_fn, B, T, content=content.to(DEV), seed=seed, traj_offset=5)
+    params_g = list(gpu.linear.parameters()) + list(gpu.ode_fn.parameters())
+    out_g = torch.autograd.grad((z * w.to(DEV)).sum(), params_g)
+    ref = _fused_reference(cpu, content, B, T, seed, offset=5)
+    params_c = list(cpu.linear.parameters()) + list(cpu.ode_fn.parameters())
+    ref_g = torch.autograd.grad((ref * w).sum(), params_c)
+    cpu64 = copy.deepcopy(cpu).double()
+    ref64 = _fused_reference(cpu64, content, B, T, seed, offset=5, dtype=torch.float64)
+    ref64_g = torch.autograd.grad((ref64 * w.double()).sum(), list(cpu64.linear.parameters()) + list(cpu64.ode_fn.parameters()))
+    assert z.shape == (B * T, 66) and torch.equal(z[:, :50].cpu(), content.repeat_interleave(T, 0))
+    assert rel_err(z[:, 50:], ref[:, 50:]) <= 2e-5, rel_err(z[:, 50:], ref[:, 50:])   # Box-Muller: MUFU sin/cos/log vs numpy
+    assert rel_err(z[:, 50:], ref64[:, 50:]) <= 2e-5
+    names = [n for n, _ in cpu.linear.named_parameters()] + [n for n, _ in cpu.ode_fn.named_parameters()]
+    for n, a, r32, r64 in zip(names, out_g, ref_g, ref64_g):
+        e, e_ref = rel_err(a, r64), rel_err(r32, r64)
+        assert e <= max(5e-5, 2 * e_ref), (n, e, e_ref)
+
+
+def test_fused_sample_images_solves_only_the_kept_rows_and_generator_wrapper():
+    """models/mocogan.py:287-291 keeps num_samples of num_samples*T*2*T rows: solving only their trajectories is bit-identical
+    to solving all of them (noise is a function of (seed, trajectory)); the wrapper's samplers have the reference's shapes."""
+    _need_gpu()
+    import numpy as np
+    from tests.scripts_harness import harness
+    torch.manual_seed(4)
+    np.random.seed(4)
+    gen = harness.StandInGenerator(n_channels=1, dim_z_content=50, dim_z_motion=16, video_length=16, dim_hidden=16).to(DEV)
+    fs = gode.FusedLatentSampler(gen)
+    n, T = 8, 16
+    n_all = n * T * 2
+    seed = 99
+    st = np.random.get_state()
+    z_rows, j = fs.sample_image_codes(n, seed=seed)
+    np.random.set_state(st)
+    content_all = fs._content(n_all)
+    full = gode.fused_sample_z(gen.linear, gen.ode_fn, n_all, T, content=content_all, seed=seed)
+    assert z_rows.shape == (n, 66) and torch.equal(z_rows, full[torch.from_numpy(j).to(DEV)])
+    fs.install()
+    try:
+        v, _ = gen.sample_videos(3)
+        i, _ = gen.sample_images(3)
+        assert v.shape == (3, 1, 16, 64, 64) and i.shape == (3, 1, 64, 64)
+        (v.sum() + i.sum()).backward()
+        assert gen.ode_fn.fn[0].weight.grad is not None and gen.linear[0].weight.grad is not None
+    finally:
+        fs.uninstall()
+    assert "sample_videos" not in gen.__dict__

@@ -18,7 +18,7 @@ api = importlib.import_module("gan_ode_b200.odeint")
 COMPUTE = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_fixed_fwd", "gode_fixed_adjoint_bwd",
            "gode_fixed_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd", "gode_dopri5_adjoint_bwd",
            "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd", "gode_sde_em_fwd", "gode_sde_em_bwd", "gode_sde_em_fwd_cells",
-           "gode_sde_adjoint_bwd", "gode_odernn_fwd",
+           "gode_sde_adjoint_bwd", "gode_rk4_sampler_fwd", "gode_rk4_adjoint_bwd_strided", "gode_odernn_fwd",
            "gode_odernn_bwd", "gode_gru_jump_fwd", "gode_gru_jump_bwd")
 
 
@@ -268,3 +268,32 @@ def test_device_gate_rejects_cpu_field_and_cpu_state():
     other.device = torch.device("cuda", 1)
     with pytest.raises(gode.GodeError, match="different devices"):
         api._require_cuda(FakeCuda(), other, what="h0 / eps")
+
+
+def test_fused_sampler_writes_into_the_cat_buffer_and_reads_gradients_in_place(wired):
+    """one forward launch for randn + pre-MLP + solve + transpose + cat; the adjoint reads the codes and the
+    upstream gradient inside z / grad_z through their row stride."""
+    from tests.caller_model import LatentMotionODE
+    torch.manual_seed(0)
+    m = LatentMotionODE(16, 16)
+    content = torch.randn(5, 50)
+    z = gode.fused_sample_z(m.linear, m.ode_fn, 5, 16, content=content, seed=77, traj_offset=1000)
+    assert z.shape == (5 * 16, 66) and torch.equal(z.view(5, 16, 66)[:, 3, :50], content)
+    name, a = wired.calls[-1]
+    assert name == "gode_rk4_sampler_fwd"
+    assert a[0] == m.linear[0].weight.data_ptr() and a[2] == m.linear[2].weight.data_ptr() and abs(a[4] - 0.2) < 1e-7 and a[5] == 64
+    assert a[6] == m.ode_fn.fn[0].weight.data_ptr() and list(a[12:16]) == [5, 16, 16, 16]
+    assert (a[16], a[17], a[18]) == (77, 1000, None) and a[19] == _lib.LAYOUT_BTD
+    assert a[20] == z.data_ptr() + 4 * 50 and a[21] == 66                     # motion columns of z, row stride 66 floats
+    w = torch.randn_like(z)
+    grads = torch.autograd.grad((z * w).sum(), list(m.linear.parameters()) + list(m.ode_fn.parameters()))
+    assert [g.shape for g in grads] == [(64, 16), (64,), (16, 64), (16,), (16, 16), (16,), (16, 16), (16,)]
+    name, a = wired.calls[-1]
+    assert name == "gode_rk4_adjoint_bwd_strided" and a[0] == z.data_ptr() + 200 and a[1] == 66 and a[3] == 66
+    # subset of a larger batch: global trajectory ids ride along; nn.Identity pre-MLP -> no prologue weights
+    ids = torch.tensor([3, 900, 17])
+    codes = gode.fused_sample_z(torch.nn.Identity(), m.ode_fn, 3, 16, seed=5, traj_ids=ids)
+    name, a = wired.calls[-1]
+    assert codes.shape == (48, 16) and a[0] is None and a[5] == 0 and a[18] is not None and a[21] == 16
+    with pytest.raises(NotImplementedError):
+        gode.fused_sample_z(torch.nn.Linear(16, 16), m.ode_fn, 3, 16)
