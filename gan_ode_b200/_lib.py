@@ -56,6 +56,7 @@ _SIGS = {
     "gode_param_count": (_I, [_I, _I]),
     "gode_rk4_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "gode_bwd_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "gode_fixed_adjoint_bwd_substep": (_I, [_I] + [_P] * 6 + [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_rk4_sampler_fwd": (_I, [_P, _P, _P, _P, C.c_float, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_uint64, C.c_int64, _P, _I,
                                   _P, _I, _P, _P]),
     "gode_rk4_adjoint_bwd_strided": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),

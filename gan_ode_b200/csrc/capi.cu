@@ -177,6 +177,20 @@ int gode_rk4_adjoint_bwd_strided(const float* traj, int ld_traj, const float* gr
                        grad_params, workspace, ws_bytes, (cudaStream_t)stream, GODE_METHOD_RK4, nullptr, ld_traj, ld_grad);
 }
 
+int gode_fixed_adjoint_bwd_substep(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                                   const float* W2, const float* b2, const float* sub_dt, const int32_t* sub_beg,
+                                   const int32_t* sub_end, int B, int D, int H, int T, int layout, float* grad_y0,
+                                   float* grad_params, void* workspace, size_t ws_bytes, gode_stream_t stream) {
+  if (bad_common(traj, W1, b1, W2, b2, B, T, layout) || !grad_traj || !sub_dt || !sub_beg || !sub_end || !grad_y0 ||
+      !grad_params || !workspace)
+    return GODE_ERR_ARG;
+  if (method != GODE_METHOD_RK4 && method != GODE_METHOD_EULER && method != GODE_METHOD_MIDPOINT) return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  SubSteps sub{sub_dt, sub_beg, sub_end};
+  return rk4_small_bwd(true, traj, grad_traj, W1, b1, W2, b2, nullptr, 1, B, D, H, T, layout, grad_y0, grad_params, workspace,
+                       ws_bytes, (cudaStream_t)stream, method, nullptr, 0, 0, &sub);
+}
+
 int gode_rk4_bwd_world(int adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                        const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                        int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes,

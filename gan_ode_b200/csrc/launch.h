@@ -78,6 +78,12 @@ inline int coop_limit(K kern, int threads, size_t smem, int& cache) {
   return cache;
 }
 
+// sub-step tables of a sub-stepped adjoint (options['step_size']), device resident
+struct SubSteps {
+  const float* dt;
+  const int *beg, *end;
+};
+
 // entry points of the per-family translation units
 int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
                   int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st,
@@ -85,7 +91,8 @@ int rk4_small_fwd(const float* y0, const float* W1, const float* b1, const float
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method = GODE_METHOD_RK4, const GodeWorld* xchg = nullptr, int ld_traj = 0, int ld_grad = 0);
+                  int method = GODE_METHOD_RK4, const GodeWorld* xchg = nullptr, int ld_traj = 0, int ld_grad = 0,
+                  const struct SubSteps* sub = nullptr);
 int rk4_small_fused_sampler_fwd(const float* pre_Wa, const float* pre_ba, const float* pre_Wb, const float* pre_bb,
                                 float pre_slope, int pre_hidden, const float* W1, const float* b1, const float* W2,
                                 const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,

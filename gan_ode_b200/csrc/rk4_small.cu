@@ -34,6 +34,10 @@ struct Rk4Args {
   long long traj_offset;    // global index of local trajectory 0
   const long long* traj_ids;  // optional (B): global trajectory index of every row (subset solves), else traj_offset + b
   float* noise_out;         // (B,D): the drawn x, kept for the pre-MLP's backward
+  // options['step_size'] under odeint_adjoint: interval i (i = T-1 .. 1) is integrated with the sub-steps
+  // sub_dt[sub_beg[i] .. sub_end[i]) (device arrays; signed like dt), carrying y along inside the interval
+  const float* sub_dt;
+  const int *sub_beg, *sub_end;
   float dt_val[GODE_MAX_HOST_STEPS];
 };
 
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_fwd_kernel(const __grid_consta
 // value at the start of every interval and grad_traj[i-1] is added to a at its end, exactly as adjoint.py does.
 // theta_bar is linear in the stage contributions, so each lane keeps its rows of theta_bar in registers across ALL
 // intervals and ALL its trajectories and the grid reduces once at the end.
-template <int D, int H, int L, int WARPS, int METHOD>
+template <int D, int H, int L, int WARPS, int METHOD, bool SUB = false>
 __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __grid_constant__ Rk4Args p) {
   using S = Shape<D, H, L>;
   using BL = BwdLines<D, H, L>;
@@ -201,25 +205,22 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
       load_frag<S::DL>(p.traj_in + traj_off(p.layout, p.T - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
       load_frag<S::DL>(p.grad_traj + traj_off(p.layout, p.T - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
     }
-    for (int i = p.T - 1; i >= 1; --i) {
-      const float dt = dtp[i - 1];
-      float y[S::DL], gprev[S::DL];
-#pragma unroll
-      for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gprev[c] = gn[c]; }
-      if (valid && i > 1) {
-        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
-        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
-      }
+    const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
+    // one step of size dt of the augmented system (y, a, theta_bar) in reversed time; y is advanced only when the interval
+    // is sub-stepped (SUB: options['step_size'] under odeint_adjoint) — with one step per interval it is reloaded anyway
+    auto aug_step = [&](const float dt, float (&y)[S::DL]) {
       const float c18 = dt * 0.125f, c38 = 3.f * c18;
-      const float sc = valid ? 1.f : 0.f;  // padded lanes must not pollute theta_bar
       float f[S::DL], v[S::DL], hk[S::HL], uy[S::DL], ua[S::DL];
       float k1y[S::DL], k1a[S::DL], k2y[S::DL], k2a[S::DL], k3y[S::DL], k3a[S::DL];
       if constexpr (METHOD == kEuler) {          // one Euler step of the augmented system from (y_i, a_i)
         mlp_forward<D, H, L>(w, ln, l, y, f, hk);
         mlp_vjp<D, H, L>(cw, ln, l, hk, a, sc * dt, v, acc);
 #pragma unroll
-        for (int c = 0; c < S::DL; ++c) a[c] = a[c] + dt * v[c] + gprev[c];
-        continue;
+        for (int c = 0; c < S::DL; ++c) {
+          a[c] = a[c] + dt * v[c];
+          if constexpr (SUB) y[c] = y[c] - dt * f[c];
+        }
+        return;
       }
       if constexpr (METHOD == kMidpoint) {       // X1 = X0 + dt F(X0 + dt/2 F(X0)): only the second stage feeds theta_bar
         const float half_dt = 0.5f * dt;
@@ -230,8 +231,11 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
         mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
         mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * dt, v, acc);
 #pragma unroll
-        for (int c = 0; c < S::DL; ++c) a[c] = a[c] + dt * v[c] + gprev[c];
-        continue;
+        for (int c = 0; c < S::DL; ++c) {
+          a[c] = a[c] + dt * v[c];
+          if constexpr (SUB) y[c] = y[c] - dt * f[c];
+        }
+        return;
       }
       // stage 1
       mlp_forward<D, H, L>(w, ln, l, y, f, hk);
@@ -252,7 +256,26 @@ __global__ void __launch_bounds__(WARPS * 32) rk4_adjoint_bwd_kernel(const __gri
       mlp_forward<D, H, L>(w, ln, l, uy, f, hk);
       mlp_vjp<D, H, L>(cw, ln, l, hk, ua, sc * c18, v, acc);
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) a[c] = a[c] + (k1a[c] + 3.f * (k2a[c] + k3a[c]) + v[c]) * dt * 0.125f + gprev[c];
+      for (int c = 0; c < S::DL; ++c) {
+        a[c] = a[c] + (k1a[c] + 3.f * (k2a[c] + k3a[c]) + v[c]) * dt * 0.125f;
+        if constexpr (SUB) y[c] = y[c] + (k1y[c] + 3.f * (k2y[c] + k3y[c]) - f[c]) * dt * 0.125f;
+      }
+    };
+    for (int i = p.T - 1; i >= 1; --i) {
+      float y[S::DL], gprev[S::DL];
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) { y[c] = yn[c]; gprev[c] = gn[c]; }
+      if (valid && i > 1) {
+        load_frag<S::DL>(p.traj_in + traj_off(p.layout, i - 1, b, p.B, p.T, D, p.ld_traj) + l * S::DL, yn);
+        load_frag<S::DL>(p.grad_traj + traj_off(p.layout, i - 2, b, p.B, p.T, D, p.ld_grad) + l * S::DL, gn);
+      }
+      if constexpr (SUB) {
+        for (int q = p.sub_beg[i]; q < p.sub_end[i]; ++q) aug_step(p.sub_dt[q], y);
+      } else {
+        aug_step(dtp[i - 1], y);
+      }
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) a[c] += gprev[c];
     }
     if (valid) store_frag<S::DL>(p.grad_y0 + (size_t)b * D + l * S::DL, a);
   }
@@ -405,11 +428,11 @@ static int launch_rk4_fwd(Rk4Args& a, cudaStream_t st) {
   return launch_status();
 }
 
-template <int D, int H, int L, bool ADJOINT, int METHOD>
+template <int D, int H, int L, bool ADJOINT, int METHOD, bool SUB = false>
 static int launch_rk4_bwd(Rk4Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   constexpr int WARPS = 4;
   using S = Shape<D, H, L>;
-  auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS, METHOD> : rk4_backprop_bwd_kernel<D, H, L, WARPS, METHOD>;
+  auto kern = ADJOINT ? rk4_adjoint_bwd_kernel<D, H, L, WARPS, METHOD, SUB> : rk4_backprop_bwd_kernel<D, H, L, WARPS, METHOD>;
   const size_t smem = bwd_smem_bytes<D, H, L, WARPS>();
   cudaError_t e;
   if (smem > 48 * 1024) {
@@ -471,7 +494,7 @@ int rk4_small_fused_sampler_fwd(const float* pre_Wa, const float* pre_ba, const 
 int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const float* W1, const float* b1,
                   const float* W2, const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T,
                   int layout, float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st,
-                  int method, const GodeWorld* xchg, int ld_traj, int ld_grad) {
+                  int method, const GodeWorld* xchg, int ld_traj, int ld_grad, const SubSteps* sub) {
   Rk4Args a{};
   a.ld_traj = ld_traj; a.ld_grad = ld_grad;
   if (xchg) {  // all-reduce over ranks fused into the reduction tail (small_field.cuh::reduce_param_grads)
@@ -480,6 +503,14 @@ int rk4_small_bwd(bool adjoint, const float* traj, const float* grad_traj, const
   }
   a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj_in = traj; a.grad_traj = grad_traj; a.grad_y0 = grad_y0;
   a.grad_params = grad_params; a.B = B; a.T = T; a.layout = layout;
+  if (sub) {   // sub-stepped adjoint: the step sizes come from the device tables
+    if (!adjoint || !sub->dt || !sub->beg || !sub->end) return GODE_ERR_ARG;
+    if (!(D == 16 && H == 16)) return GODE_ERR_SHAPE;
+    a.sub_dt = sub->dt; a.sub_beg = sub->beg; a.sub_end = sub->end;
+    if (method == kEuler) return launch_rk4_bwd<16, 16, 8, true, kEuler, true>(a, workspace, ws_bytes, st);
+    if (method == kMidpoint) return launch_rk4_bwd<16, 16, 8, true, kMidpoint, true>(a, workspace, ws_bytes, st);
+    return launch_rk4_bwd<16, 16, 8, true, kRk4, true>(a, workspace, ws_bytes, st);
+  }
   if (int rc = fill_dt(a, dt, dt_on_device, T)) return rc;
   if (D == 16 && H == 16) {
     if (method == kEuler)

@@ -494,6 +494,89 @@ def _substepped(apply_fixed, y0, t, step_size, layout_name):
     return sol
 
 
+_SUBSTEP_CACHE = {}
+
+
+def _adjoint_substeps(t: torch.Tensor, step_size, device):
+    """Sub-step tables of torchdiffeq's adjoint when options['step_size'] is set: adjoint.py solves every output interval with
+    odeint(aug, state, [t_i, t_{i-1}], method, options) and FixedGridODESolver lays ITS grid from the interval's own start:
+    t_i, t_i -+ h, ... with the last point clamped to t_{i-1} (a decreasing pair is integrated as increasing negated time).
+    Returns device tensors (sub_dt float32, signed like the kernel's dt; sub_beg, sub_end int32 indexed by i)."""
+    tc = t.detach().cpu()
+    key = (tc.dtype, tc.numpy().tobytes(), float(step_size), str(device))
+    hit = _SUBSTEP_CACHE.get(key)
+    if hit is not None:
+        return hit
+    T = len(tc)
+    h = torch.as_tensor(step_size, dtype=tc.dtype)
+    dts, beg, end = [], [0] * T, [0] * T
+    for i in range(T - 1, 0, -1):
+        a, b = tc[i], tc[i - 1]
+        rev = bool(a > b)                       # forward grid increasing: the reversed solve runs in negated time
+        s0, s1 = (-a, -b) if rev else (a, b)
+        niters = int(torch.ceil((s1 - s0) / h + 1).item())
+        g = torch.arange(0, niters, dtype=tc.dtype) * h + s0
+        g[-1] = s1
+        d = (g[1:] - g[:-1]).to(torch.float32) * (1.0 if rev else -1.0)
+        beg[i] = len(dts)
+        dts.extend(d.tolist())
+        end[i] = len(dts)
+    out = (torch.tensor(dts, dtype=torch.float32).to(device), torch.tensor(beg, dtype=torch.int32).to(device),
+           torch.tensor(end, dtype=torch.int32).to(device))
+    if len(_SUBSTEP_CACHE) < 64:
+        _SUBSTEP_CACHE[key] = out
+    return out
+
+
+class _FixedSubstepAdjoint(torch.autograd.Function):
+    """odeint_adjoint with options['step_size'] on a fixed-grid method: forward = fine-grid kernel solve + linear
+    interpolation of the requested times (no graph), backward = gode_fixed_adjoint_bwd_substep."""
+
+    @staticmethod
+    def forward(ctx, y0, meta, W1, b1, W2, b2):
+        inner = dict(meta, adjoint=False)
+
+        def apply_fixed(grid):
+            m = dict(inner, T=len(grid), layout=_lib.LAYOUT_TBD)
+            return _Rk4.apply(y0.detach(), _rk4_dt(grid, {}, y0.device), m, W1.detach(), b1.detach(), W2.detach(), b2.detach())
+
+        with torch.no_grad():
+            sol = _substepped(apply_fixed, y0, meta["t"], meta["step_size"], "tbd")      # (T, B, D)
+        if meta["layout"] == _lib.LAYOUT_TBD:
+            buf = sol.contiguous()
+            view = buf
+        else:
+            buf = sol.transpose(0, 1).contiguous()
+            view = buf.transpose(0, 1)
+        ctx.meta = meta
+        ctx.save_for_backward(buf, *(_f32c(x) for x in (W1, b1, W2, b2)))
+        return view
+
+    @staticmethod
+    @_bwd_on_device
+    def backward(ctx, grad_traj):
+        L = _lib.lib()
+        buf, W1c, b1c, W2c, b2c = ctx.saved_tensors
+        meta = ctx.meta
+        T = meta["T"]
+        B, D = (buf.shape[1], buf.shape[2]) if meta["layout"] == _lib.LAYOUT_TBD else (buf.shape[0], buf.shape[2])
+        H = W1c.shape[0]
+        g = _grad_in_layout(grad_traj, meta["layout"])
+        n_param, ws_bytes = _rk4_sizes(L, B, D, H, T)
+        grad_p = torch.empty(n_param, dtype=torch.float32, device=buf.device)
+        grad_y0 = torch.empty((B, D), dtype=torch.float32, device=buf.device)
+        ws = _workspace(buf.device, ws_bytes)
+        sub_dt, sub_beg, sub_end = _adjoint_substeps(meta["t"], meta["step_size"], buf.device)
+        rc = L.gode_fixed_adjoint_bwd_substep(meta.get("method", 0), buf.data_ptr(), g.data_ptr(), W1c.data_ptr(), b1c.data_ptr(),
+                                              W2c.data_ptr(), b2c.data_ptr(), sub_dt.data_ptr(), sub_beg.data_ptr(),
+                                              sub_end.data_ptr(), B, D, H, T, meta["layout"], grad_y0.data_ptr(),
+                                              grad_p.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        _lib.check(rc, "gode_fixed_adjoint_bwd_substep")
+        needs = ctx.needs_input_grad
+        gW1, gb1, gW2, gb2 = _split_params(grad_p, D, H, needs[2:6])
+        return (grad_y0 if needs[0] else None), None, gW1, gb1, gW2, gb2
+
+
 def _rk4_dt(t: torch.Tensor, options, device):
     """Step table of torchdiffeq's fixed-grid driver: grid == t when no step_size is given, dt_j = t[j+1]-t[j] in t's
     dtype, multiplied into fp32 state (=> rounded to fp32).  Decreasing t gives negative dt, which is bit-identical
@@ -1072,7 +1155,14 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         step_size = options.get("step_size")
         if step_size is not None:
             if adjoint:
-                raise NotImplementedError("options['step_size'] is supported for odeint (backprop-through-solver) only")
+                # torchdiffeq: the adjoint solves inherit the forward options, i.e. every output interval is re-solved on its
+                # own step_size grid (gode_fixed_adjoint_bwd_substep); FP32 kernels of the reference shape
+                if (D, H) != (16, 16) or prec != _lib.PREC["fp32"]:
+                    raise NotImplementedError("options['step_size'] under odeint_adjoint exists for D=H=16 in fp32")
+                if adj is not None or t.is_cuda:
+                    raise NotImplementedError("step_size under odeint_adjoint: host-resident t, no separate adjoint options")
+                m = dict(meta, t=t, step_size=step_size)
+                return _FixedSubstepAdjoint.apply(y0, m, W1, b1, W2, b2)
             sub = dict(options)
             sub.pop("step_size")
 

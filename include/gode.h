@@ -298,6 +298,18 @@ int gode_sde_em_bwd(const float* states, const float* grad_frames, const float* 
                     uint64_t seed, int64_t traj_offset, int layout, float* grad_y0, float* grad_params,
                     void* workspace, size_t ws_bytes, gode_stream_t stream);
 
+/* ---- f4: options['step_size'] under odeint_adjoint (torchdiffeq FixedGridODESolver + adjoint.py) -------------------------
+ * The forward integrates on the grid t0, t0+h, ... and interpolates the requested times linearly (host: fine-grid
+ * gode_fixed_fwd + interpolation); the adjoint re-solves every output interval [t_i, t_{i-1}] on ITS OWN grid t_i, t_i -+ h, ...
+ * (last step clamped), carrying y along inside the interval and resetting it to traj[i-1] at the end.  Interval i
+ * (i = T-1 .. 1) takes the sub-steps sub_dt[sub_beg[i] .. sub_end[i]) — device arrays, signed like the dt of
+ * gode_rk4_adjoint_bwd (positive for an increasing t).  method: GODE_METHOD_RK4 / EULER / MIDPOINT.  traj: the forward's
+ * (interpolated) outputs. */
+int gode_fixed_adjoint_bwd_substep(int method, const float* traj, const float* grad_traj, const float* W1, const float* b1,
+                                   const float* W2, const float* b2, const float* sub_dt, const int32_t* sub_beg,
+                                   const int32_t* sub_end, int B, int D, int H, int T, int layout, float* grad_y0,
+                                   float* grad_params, void* workspace, size_t ws_bytes, gode_stream_t stream);
+
 /* ---- f2: the latent-motion sampler fused around the solve (models/mocogan_ode.py:133-148, models/mocogan.py:259-269) ----
  * OPT-IN (it changes which random numbers are consumed).  One launch does what sample_z_m does in five:
  *   x = randn(B, D)              Philox4x32-10, counter (global trajectory, 0, d/4, 2), oracle/philox.py::normals

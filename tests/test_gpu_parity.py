@@ -1325,8 +1325,30 @@ def test_step_size_substepping_matches_oracle(method, h, tname):
     assert rel_err(out_sol, ref_sol) <= TOL
     for a, b in zip(out_g, ref_g):
         assert rel_err(a, b) <= 2e-5, rel_err(a, b)
-    with pytest.raises(NotImplementedError):
-        gode.odeint_adjoint(clone_to(f, DEV), y0.to(DEV), t, method=method, options={"step_size": h})
+
+
+@pytest.mark.parametrize("method", ["rk4", "euler", "midpoint"])
+@pytest.mark.parametrize("h,tname,layout", [(1.0 / 45, "lin16", "tbd"), (0.07, "lin16", "btd"), (0.11, "decreasing", "tbd")])
+def test_step_size_under_the_adjoint_matches_oracle(method, h, tname, layout):
+    """options={'step_size': h} with odeint_adjoint: the forward interpolates a fine-grid solve, and the adjoint
+    re-solves every output interval on ITS OWN step_size grid (t_i, t_i -+ h, ..., clamped), carrying y inside the interval
+    — adjoint.py passes the forward options to its per-interval odeint calls."""
+    _need_gpu()
+    f = make_field(seed=int(h * 1000) + 1)
+    t = _t16() if tname == "lin16" else torch.tensor([1.0, 0.8, 0.75, 0.4, 0.1, 0.0])
+    y0 = torch.randn(33, 16)
+    g = torch.randn(len(t), 33, 16)
+
+    def run(mod, field, y, gg, **o):
+        y = y.clone().requires_grad_(True)
+        sol = mod.odeint_adjoint(field, y, t, method=method, options=dict({"step_size": h}, **o))
+        return sol.detach(), torch.autograd.grad((sol * gg).sum(), [y] + list(field.parameters()))
+
+    ref_sol, ref_g = run(tdq, f, y0, g)
+    _, ref64 = run(tdq, clone_to(f, "cpu", torch.float64), y0.double(), g.double())
+    out_sol, out_g = run(gode, clone_to(f, DEV), y0.to(DEV), g.to(DEV), layout=layout)
+    assert rel_err(out_sol, ref_sol) <= TOL
+    _assert_grads(out_g, ref_g, ref64)
 
 
 def test_odernn_fused_sampler_per_trajectory_step_control(monkeypatch):

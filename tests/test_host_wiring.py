@@ -18,7 +18,7 @@ api = importlib.import_module("gan_ode_b200.odeint")
 COMPUTE = ("gode_rk4_fwd", "gode_rk4_adjoint_bwd", "gode_rk4_backprop_bwd", "gode_fixed_fwd", "gode_fixed_adjoint_bwd",
            "gode_fixed_backprop_bwd", "gode_dopri5_fwd", "gode_dopri5_backprop_bwd", "gode_dopri5_adjoint_bwd",
            "gode_dopri5_traj_fwd", "gode_dopri5_traj_backprop_bwd", "gode_sde_em_fwd", "gode_sde_em_bwd", "gode_sde_em_fwd_cells",
-           "gode_sde_adjoint_bwd", "gode_rk4_sampler_fwd", "gode_rk4_adjoint_bwd_strided", "gode_odernn_fwd",
+           "gode_sde_adjoint_bwd", "gode_rk4_sampler_fwd", "gode_rk4_adjoint_bwd_strided", "gode_fixed_adjoint_bwd_substep", "gode_odernn_fwd",
            "gode_odernn_bwd", "gode_gru_jump_fwd", "gode_gru_jump_bwd")
 
 
@@ -96,8 +96,18 @@ def test_layout_precision_and_method_options_reach_the_abi(wired):
     assert name == "gode_fixed_fwd" and a[0] == _lib.METHODS["midpoint"]
     with pytest.raises(NotImplementedError):
         gode.odeint(f, y0, t, method="bosh3")
-    with pytest.raises(NotImplementedError):
-        gode.odeint_adjoint(f, y0, t, method="rk4", options={"step_size": 0.1})
+    # step_size under the adjoint: fine-grid forward launch, then the sub-stepped adjoint entry point with its device tables
+    wired.calls.clear()
+    yr = y0.clone().requires_grad_(True)
+    sol = gode.odeint_adjoint(f, yr, t, method="rk4", options={"step_size": 0.1})
+    assert [c[0] for c in wired.calls] == ["gode_rk4_fwd"] and wired.calls[0][1][10] == 11     # 1.0 -> 0.0 in steps of 0.1: 11 points
+    sol.sum().backward()
+    name, a = wired.calls[-1]
+    assert name == "gode_fixed_adjoint_bwd_substep" and a[0] == _lib.METHODS["rk4"] and list(a[10:15]) == [5, 16, 16, 3, _lib.LAYOUT_TBD]
+    sub_dt, beg, end = api._adjoint_substeps(t, 0.1, y0.device)
+    assert beg.tolist() == [0, 6, 0] and end.tolist() == [0, 10, 6]      # interval [0.0, 0.6]: 6 steps, then [0.6, 1.0]: 4
+    assert (sub_dt < 0).all() and abs(float(sub_dt[:6].sum()) + 0.6) < 1e-6                   # decreasing t: negative steps
+
 
 
 def test_dopri5_calls_continuous_adjoint_discrete_gradient_and_per_trajectory(wired):
