@@ -173,7 +173,7 @@ def _check_inputs(func, y0, t, rtol, atol, method, options):
         options = options.copy()
     if method is None:
         method = "dopri5"
-    if method not in ("rk4", "dopri5", "euler", "midpoint"):
+    if method not in ("rk4", "dopri5", "euler", "midpoint", "bosh3", "adaptive_heun"):
         raise ValueError('Invalid method "{}" (oracle restates rk4, dopri5, euler only)'.format(method))
 
     if is_tuple:
@@ -333,6 +333,36 @@ class DOPRI5:
     order = 5
 
 
+class BOSH3:
+    """bosh3.py — Bogacki–Shampine 3(2), FSAL."""
+
+    alpha = torch.tensor([1 / 2, 3 / 4, 1.0], dtype=torch.float64)
+    beta = [
+        torch.tensor([1 / 2], dtype=torch.float64),
+        torch.tensor([0.0, 3 / 4], dtype=torch.float64),
+        torch.tensor([2 / 9, 1 / 3, 4 / 9], dtype=torch.float64),
+    ]
+    c_sol = torch.tensor([2 / 9, 1 / 3, 4 / 9, 0.0], dtype=torch.float64)
+    c_error = torch.tensor([2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8], dtype=torch.float64)
+    c_mid = torch.tensor([0.0, 0.5, 0.0, 0.0], dtype=torch.float64)
+    order = 3
+
+
+class ADAPTIVE_HEUN:
+    """adaptive_heun.py — Heun–Euler 2(1).  Not FSAL: y1 = y0 + dt (k0 + k1) / 2 is formed from c_sol, and
+    rk_common.py::_runge_kutta_step still hands f1 = k[..., -1] = f(t1, y0 + dt k0) to the next step as its f0."""
+
+    alpha = torch.tensor([1.0], dtype=torch.float64)
+    beta = [torch.tensor([1.0], dtype=torch.float64)]
+    c_sol = torch.tensor([0.5, 0.5], dtype=torch.float64)
+    c_error = torch.tensor([0.5, -0.5], dtype=torch.float64)
+    c_mid = torch.tensor([0.5, 0.0], dtype=torch.float64)
+    order = 2
+
+
+ADAPTIVE = {"dopri5": DOPRI5, "bosh3": BOSH3, "adaptive_heun": ADAPTIVE_HEUN}
+
+
 class StepLog:
     """What the adaptive driver did — one entry per ATTEMPTED step (accepted or not)."""
 
@@ -374,7 +404,9 @@ def _runge_kutta_step(func, y0, f0, t0, dt, t1, tab):
         yi = y0 + torch.sum(k * (beta_i * dt), dim=-1).view_as(f0)
         ks.append(func(ti, yi))
     k = torch.stack(ks, dim=-1)
-    # c_sol[-1] == 0 and c_sol[:-1] == beta[-1]  (FSAL): y1 is the last stage input, f1 the last k.
+    if not (tab["c_sol"][-1] == 0 and (tab["c_sol"][:-1] == tab["beta"][-1]).all()):
+        # "This property (true for Dormand-Prince) lets us save a few FLOPs." — otherwise y1 comes from c_sol
+        yi = y0 + torch.sum(k * (dt * tab["c_sol"]), dim=-1).view_as(f0)
     y1 = yi
     f1 = ks[-1]
     y1_error = k.matmul(dt * tab["c_error"])
@@ -404,7 +436,7 @@ def _interp_evaluate(coefficients, t0, t1, t):
     return total
 
 
-def _dopri5_integrate(func, y0, t, rtol, atol, options):
+def _dopri5_integrate(func, y0, t, rtol, atol, options, TAB=DOPRI5):
     """solvers.py::AdaptiveStepsizeODESolver.integrate +
     rk_common.py::RKAdaptiveStepsizeODESolver.{_before_integrate,_advance,_adaptive_step}.
 
@@ -423,11 +455,12 @@ def _dopri5_integrate(func, y0, t, rtol, atol, options):
     dfactor = torch.as_tensor(options.get("dfactor", 0.2), dtype=tdtype, device=device)
     max_num_steps = options.get("max_num_steps", 2 ** 31 - 1)
     tab = {
-        "alpha": DOPRI5.alpha.to(device=device, dtype=y0.dtype),
-        "beta": [b.to(device=device, dtype=y0.dtype) for b in DOPRI5.beta],
-        "c_error": DOPRI5.c_error.to(device=device, dtype=y0.dtype),
+        "alpha": TAB.alpha.to(device=device, dtype=y0.dtype),
+        "beta": [b.to(device=device, dtype=y0.dtype) for b in TAB.beta],
+        "c_sol": TAB.c_sol.to(device=device, dtype=y0.dtype),
+        "c_error": TAB.c_error.to(device=device, dtype=y0.dtype),
     }
-    mid = DOPRI5.c_mid.to(device=device, dtype=y0.dtype)
+    mid = TAB.c_mid.to(device=device, dtype=y0.dtype)
     log = StepLog()
     _LAST_LOG[0] = log
 
@@ -442,7 +475,7 @@ def _dopri5_integrate(func, y0, t, rtol, atol, options):
     # _before_integrate
     f0 = counted(t[0], y0)
     if first_step is None:
-        dt = _select_initial_step(counted, t[0], y0, DOPRI5.order - 1, rtol, atol, norm, f0=f0)
+        dt = _select_initial_step(counted, t[0], y0, TAB.order - 1, rtol, atol, norm, f0=f0)
     else:
         dt = torch.as_tensor(first_step, dtype=tdtype, device=device)
     if options.get("_detach_dt0", False):
@@ -492,7 +525,7 @@ def _dopri5_integrate(func, y0, t, rtol, atol, options):
                 rk_y1, rk_f1 = y1, f1
             else:
                 rk_t0, rk_t1 = ts, ts
-            dt = _optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, DOPRI5.order)
+            dt = _optimal_step_size(dt, error_ratio, safety, ifactor, dfactor, TAB.order)
             dt = dt.clamp(min_step, max_step)
             n_steps += 1
         solution[i] = _interp_evaluate(interp_coeff, rk_t0, rk_t1, next_t)
@@ -512,8 +545,8 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     shapes, func, y0, t, rtol, atol, method, options, t_is_reversed = _check_inputs(
         func, y0, t, rtol, atol, method, options
     )
-    if method == "dopri5":
-        solution = _dopri5_integrate(func, y0, t, rtol, atol, options)
+    if method in ADAPTIVE:
+        solution = _dopri5_integrate(func, y0, t, rtol, atol, options, ADAPTIVE[method])
     else:
         solution = _fixed_grid_integrate(func, y0, t, method, options)
     if shapes is not None:
