@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GODE_LIB") or os.path.join(HERE, "csrc", "libgode.so")   # GODE_LIB: developer trace build only
 
 METHODS = {"rk4": 0, "euler": 1, "midpoint": 2}
+TABLEAUS = {"dopri5": 0, "bosh3": 1, "adaptive_heun": 2}
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
@@ -31,7 +32,7 @@ class GodeAdaptiveOpts(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("first_step", C.c_double), ("safety", C.c_double),
                 ("ifactor", C.c_double), ("dfactor", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double),
                 ("max_num_steps", C.c_int32), ("norm_scope", C.c_int32), ("log_capacity", C.c_int32),
-                ("ckpt_capacity", C.c_int32), ("fsign", C.c_float), ("_pad", C.c_int32)]
+                ("ckpt_capacity", C.c_int32), ("fsign", C.c_float), ("tableau", C.c_int32)]
 
 
 class GodeWorld(C.Structure):
@@ -72,6 +73,7 @@ _SIGS = {
                                             C.POINTER(GodeWorld), _P]),
     "gode_dopri5_adjoint_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_dopri5_adjoint_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 7 + [C.c_size_t, _P]),
+    "gode_adaptive_backprop_bwd": (_I, [_I] + [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P, C.c_size_t, _P]),
     "gode_dopri5_backprop_bwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P, C.c_size_t, _P]),
     "gode_dopri5_traj_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 11),
     "gode_dopri5_traj_backprop_bwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, C.c_float, _P, _P, _P,

@@ -261,6 +261,21 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
 }
 
+int gode_adaptive_backprop_bwd(int tableau, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                               const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                               size_t ws_bytes, gode_stream_t stream) {
+  if (bad_common(grad_traj, W1, b1, W2, b2, B, T, layout) || !t_host || !log || !ckpt || !acc_t0 || !acc_dt ||
+      ckpt_capacity <= 0 || !grad_y0 || !grad_params || !workspace || tableau < GODE_TAB_DOPRI5 ||
+      tableau > GODE_TAB_ADAPTIVE_HEUN)
+    return GODE_ERR_ARG;
+  if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
+  return dopri5_small_backprop_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, ckpt, acc_t0, acc_dt,
+                                   ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream,
+                                   nullptr, tableau);
+}
+
 int gode_dopri5_backprop_bwd_world(const float* grad_traj, const float* W1, const float* b1, const float* W2,
                                    const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
                                    const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,

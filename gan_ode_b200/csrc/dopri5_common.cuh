@@ -29,30 +29,76 @@ __device__ constexpr float kCMid[7] = {F32(6025192743.0 / 30085553152.0 / 2),
                                         F32(187940372067.0 / 1594534317056.0 / 2),
                                         F32(-1776094331.0 / 19743644256.0 / 2),
                                         F32(11237099.0 / 235043384.0 / 2)};
+// bosh3.py — Bogacki–Shampine 3(2) (FSAL) and adaptive_heun.py — Heun–Euler 2(1) (not FSAL), same construction
+__device__ constexpr float kBsBeta[3][3] = {{F32(1.0 / 2), 0, 0}, {0, F32(3.0 / 4), 0}, {F32(2.0 / 9), F32(1.0 / 3), F32(4.0 / 9)}};
+__device__ constexpr float kBsCErr[4] = {F32(2.0 / 9 - 7.0 / 24), F32(1.0 / 3 - 1.0 / 4), F32(4.0 / 9 - 1.0 / 3), F32(-1.0 / 8)};
+__device__ constexpr float kBsCMid[4] = {0, F32(0.5), 0, 0};
+__device__ constexpr float kAhBeta[1][1] = {{1.f}};
+__device__ constexpr float kAhCSol[2] = {0.5f, 0.5f};
+__device__ constexpr float kAhCErr[2] = {0.5f, -0.5f};
+__device__ constexpr float kAhCMid[2] = {0.5f, 0.f};
 #undef F32
+
+// Tableau of an adaptive solver (torchdiffeq RKAdaptiveStepsizeODESolver subclasses): NS stage evaluations per step (k has
+// NS + 1 entries, k[0] = f0), ORDER for the controller / the initial-step heuristic, FSAL: y1 is the last stage input
+// (c_sol[:-1] == beta[-1], c_sol[-1] == 0), otherwise y1 = y0 + dt sum_j c_sol[j] k[j].  In both cases f1 = k[NS] goes to
+// the next step as its f0 (rk_common.py::_runge_kutta_step) — for adaptive_heun that is f(t1, y0 + dt k0), not f(t1, y1).
+template <int TAB>
+struct Tableau;
+template <>
+struct Tableau<GODE_TAB_DOPRI5> {
+  static constexpr int NS = 6, ORDER = 5;
+  static constexpr bool FSAL = true;
+  __device__ static constexpr float beta(int i, int j) { return kBeta[i][j]; }
+  __device__ static constexpr float cerr(int j) { return kCErr[j]; }
+  __device__ static constexpr float cmid(int j) { return kCMid[j]; }
+  __device__ static constexpr float csol(int j) { return j < 6 ? kBeta[5][j] : 0.f; }
+};
+template <>
+struct Tableau<GODE_TAB_BOSH3> {
+  static constexpr int NS = 3, ORDER = 3;
+  static constexpr bool FSAL = true;
+  __device__ static constexpr float beta(int i, int j) { return kBsBeta[i][j]; }
+  __device__ static constexpr float cerr(int j) { return kBsCErr[j]; }
+  __device__ static constexpr float cmid(int j) { return kBsCMid[j]; }
+  __device__ static constexpr float csol(int j) { return j < 3 ? kBsBeta[2][j] : 0.f; }
+};
+template <>
+struct Tableau<GODE_TAB_ADAPTIVE_HEUN> {
+  static constexpr int NS = 1, ORDER = 2;
+  static constexpr bool FSAL = false;
+  __device__ static constexpr float beta(int i, int j) { return kAhBeta[i][j]; }
+  __device__ static constexpr float cerr(int j) { return kAhCErr[j]; }
+  __device__ static constexpr float cmid(int j) { return kAhCMid[j]; }
+  __device__ static constexpr float csol(int j) { return kAhCSol[j]; }
+};
 
 // misc.py::_optimal_step_size in fp64
 // er^(-1/5) without fp64 exp/log (they were ~1.2 k cycles per attempted step on the solver's critical path, trace in
 // profiles/README.md): MUFU-based fp32 guess (relative error ~1e-6), then two Newton steps for F(y) = y^-5 - er,
 // y <- y (6 - er y^5) / 5 — division-free, quadratic: 1e-6 -> 3e-12 -> 3e-23, i.e. correctly rounded to within an ulp.
-__device__ __forceinline__ double inv_fifth_root(float er32) {
-  double y = (double)__powf(er32, -0.2f);
+template <int ORDER = 5>
+__device__ __forceinline__ double inv_fifth_root(float er32) {   // er^(-1/ORDER): y <- y (ORDER + 1 - er y^ORDER) / ORDER
+  double y = (double)__powf(er32, -1.f / (float)ORDER);
   const double er = (double)er32;
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
-    const double y2 = y * y, y5 = y2 * y2 * y;
-    y = y * ((6.0 - er * y5) * 0.2);
+    double yn = y;
+#pragma unroll
+    for (int q = 1; q < ORDER; ++q) yn *= y;
+    y = y * (((double)(ORDER + 1) - er * yn) * (1.0 / (double)ORDER));
   }
   return y;
 }
 
+template <int ORDER = 5>
 __device__ __forceinline__ double optimal_step(double dt, float er32, const GodeAdaptiveOpts& o) {
   if (er32 == 0.f) return dt * o.ifactor;
   if (er32 != er32) return (double)er32;                       // torch.min/max propagate NaN; fmin/fmax do not
   const double dfactor = er32 < 1.f ? 1.0 : o.dfactor;
   // below 1e-30 (and for +inf) the factor is pinned by ifactor / dfactor whatever the root is; keep the guess in range
   const float erc = fminf(fmaxf(er32, 1e-30f), 1e30f);
-  const double factor = fmin(o.ifactor, fmax(o.safety * inv_fifth_root(erc), dfactor));
+  const double factor = fmin(o.ifactor, fmax(o.safety * inv_fifth_root<ORDER>(erc), dfactor));
   return dt * factor;
 }
 

@@ -131,9 +131,11 @@ __device__ __forceinline__ void world_allreduce_sum(double (&v)[NV], const Dp5Ar
 // WORLD: world-scope norm compiled in (gode_dopri5_fwd_world).  A template parameter, not a runtime flag: the mere presence
 // of the exchange code cost the ordinary solve 4 us of 30 at the bench shape (measured), so the default instantiation is
 // kept free of it.
-template <int D, int H, int L, int WARPS, bool WORLD>
+template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5>
 __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_constant__ Dp5Args p) {
   using S = Shape<D, H, L>;
+  using TB = Tableau<TAB>;
+  constexpr int NS = TB::NS;
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
   __shared__ float s_f[WARPS * kGsMaxVals];
   __shared__ double s_d[kGsMaxVals];
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   unsigned int wepoch = 0;
   if constexpr (WORLD) wepoch = *reinterpret_cast<volatile unsigned int*>(p.w_launch_ctr);
 
-  float y0[S::DL], k[7][S::DL], hk[S::HL];
+  float y0[S::DL], k[NS + 1][S::DL], hk[S::HL];
 #pragma unroll
   for (int c = 0; c < S::DL; ++c) y0[c] = 0.f;
   if (valid) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       const float d2 = sqrtf((float)(v2[0] * inv_n)) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-      else h1 = powf(0.01f / fmaxf(d1, d2), 0.2f);
+      else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / (float)TB::ORDER);   // _select_initial_step(order = ORDER - 1)
       dt = (double)fminf(100.f * h0, h1);
     }
   }
@@ -226,25 +228,35 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     const float dt32 = (float)dt;
     float u[S::DL];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
+    for (int i = 0; i < NS; ++i) {
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) {
-        float s = k[0][c] * (kBeta[i][0] * dt32);
+        float s = k[0][c] * (TB::beta(i, 0) * dt32);
 #pragma unroll
-        for (int j = 1; j <= i; ++j) s = fmaf(k[j][c], kBeta[i][j] * dt32, s);
+        for (int j = 1; j <= i; ++j) s = fmaf(k[j][c], TB::beta(i, j) * dt32, s);
         u[c] = y0[c] + s;
       }
       field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], hk);
     }
-    nfe += 6;
+    nfe += NS;
     GODE_TP(0, 4 + 3 * min(n_att, 8));
-    // u is y1 (FSAL: c_sol == beta[5]), k[6] is f1
+    // FSAL (c_sol == beta[NS-1], dopri5 / bosh3): u is y1.  Otherwise y1 comes from c_sol.  Either way k[NS] is f1.
+    if constexpr (!TB::FSAL) {
+#pragma unroll
+      for (int c = 0; c < S::DL; ++c) {
+        float s = k[0][c] * (dt32 * TB::csol(0));
+#pragma unroll
+        for (int j = 1; j <= NS; ++j) s = fmaf(k[j][c], dt32 * TB::csol(j), s);
+        u[c] = y0[c] + s;
+      }
+    }
     double v[1] = {0.0};
 #pragma unroll
     for (int c = 0; c < S::DL; ++c) {
-      float e = k[0][c] * (dt32 * kCErr[0]);
+      float e = k[0][c] * (dt32 * TB::cerr(0));
 #pragma unroll
-      for (int j = 2; j < 7; ++j) e = fmaf(k[j][c], dt32 * kCErr[j], e);
+      for (int j = 1; j <= NS; ++j)
+        if (TB::cerr(j) != 0.f) e = fmaf(k[j][c], dt32 * TB::cerr(j), e);
       const float tol = atol32 + rtol32 * fmaxf(fabsf(y0[c]), fabsf(u[c]));
       const float r = e / tol;
       if (valid) v[0] += (double)r * (double)r;
@@ -273,10 +285,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         float ca[S::DL], cb[S::DL], cc[S::DL], cd[S::DL];
 #pragma unroll
         for (int c = 0; c < S::DL; ++c) {
-          float m = k[0][c] * (dt32 * kCMid[0]);
+          float m = k[0][c] * (dt32 * TB::cmid(0));
 #pragma unroll
-          for (int j = 2; j < 7; ++j) m = fmaf(k[j][c], dt32 * kCMid[j], m);
-          const float ymid = y0[c] + m, f0 = k[0][c], f1 = k[6][c], y1 = u[c];
+          for (int j = 1; j <= NS; ++j)
+            if (TB::cmid(j) != 0.f) m = fmaf(k[j][c], dt32 * TB::cmid(j), m);
+          const float ymid = y0[c] + m, f0 = k[0][c], f1 = k[NS][c], y1 = u[c];
           ca[c] = 2.f * dt32 * (f1 - f0) - 8.f * (y1 + y0[c]) + 16.f * ymid;
           cb[c] = dt32 * (5.f * f0 - 3.f * f1) + 18.f * y0[c] + 14.f * y1 - 32.f * ymid;
           cc[c] = dt32 * (f1 - 4.f * f0) - 11.f * y0[c] - 5.f * y1 + 16.f * ymid;
@@ -307,11 +320,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         }
       }
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) { y0[c] = u[c]; k[0][c] = k[6][c]; }
+      for (int c = 0; c < S::DL; ++c) { y0[c] = u[c]; k[0][c] = k[NS][c]; }
       t0 = t1;
       ++n_acc;
     }
-    dt = optimal_step(dt, er, p.o);
+    dt = optimal_step<TB::ORDER>(dt, er, p.o);
     dt = fmin(fmax(dt, p.o.min_step), p.o.max_step);
     GODE_TP(0, 6 + 3 * min(n_att, 8));
     ++n_att;
@@ -331,10 +344,12 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int D, int H, int L, int WARPS>
+template <int D, int H, int L, int WARPS, int TAB = GODE_TAB_DOPRI5>
 __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const __grid_constant__ Dp5Args p) {
   using S = Shape<D, H, L>;
   using BL = BwdLines<D, H, L>;
+  using TB = Tableau<TAB>;
+  constexpr int NS = TB::NS;
   extern __shared__ __align__(16) float smem[];
   float* s_lines = smem;
   float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;
@@ -415,7 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       GODE_TP(1, 5 + 2 * min(s, 8));
       const double t0 = t0n, dtd = dtn, t1 = t0 + dtd;
       const float dt32 = (float)dtd;
-      float y0[S::DL], k[7][S::DL], h[7][S::HL], u[S::DL];
+      float y0[S::DL], k[NS + 1][S::DL], h[NS + 1][S::HL], u[S::DL];
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) y0[c] = y0n[c];
       if (s > 0) {
@@ -425,19 +440,19 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       // recompute the step exactly as the forward did
       field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], h[0]);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
+      for (int i = 0; i < NS; ++i) {
 #pragma unroll
         for (int c = 0; c < S::DL; ++c) {
-          float sum = k[0][c] * (kBeta[i][0] * dt32);
+          float sum = k[0][c] * (TB::beta(i, 0) * dt32);
 #pragma unroll
-          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], kBeta[i][j] * dt32, sum);
+          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], TB::beta(i, j) * dt32, sum);
           u[c] = y0[c] + sum;
         }
         field<D, H, L>(w, ln, l, p.o.fsign, u, k[i + 1], h[i + 1]);
       }
       GODE_TP(1, 6 + 2 * min(s, 8));
       // cotangents of the interpolation inputs (y0, y1, ymid, f0, f1) from every output inside (t0, t1]
-      float y0b[S::DL], ymb[S::DL], f0b[S::DL], kb[7][S::DL];
+      float y0b[S::DL], ymb[S::DL], f0b[S::DL], kb[NS + 1][S::DL];
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) { y0b[c] = 0.f; ymb[c] = 0.f; f0b[c] = 0.f; }
       const double inv_span = 1.0 / (t1 - t0);
@@ -464,36 +479,41 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
         }
         --iout;
       }
-      // ymid = y0 + sum_j k_j dt cmid_j ; f1 = k7 ; f0 = k1
+      // ymid = y0 + sum_j k_j dt cmid_j ; f1 = k[NS] ; f0 = k[0]
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) {
         y0b[c] += ymb[c];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) kb[j][c] = (dt32 * kCMid[j]) * ymb[c];
-        kb[6][c] += fbar[c];
+        for (int j = 0; j <= NS; ++j) kb[j][c] = (dt32 * TB::cmid(j)) * ymb[c];
+        kb[NS][c] += fbar[c];
         kb[0][c] += f0b[c];
+        if constexpr (!TB::FSAL) {   // y1 = y0 + dt sum_j c_sol[j] k[j]: its cotangent goes to y0 and to every k
+          y0b[c] += ybar[c];
+#pragma unroll
+          for (int j = 0; j <= NS; ++j) kb[j][c] = fmaf(TB::csol(j) * dt32, ybar[c], kb[j][c]);
+        }
       }
-      // stage 7: k7 = f(u7), u7 == y1 (lines still hold u7 / h7 from the recompute)
+      // last stage: k[NS] = f(u_last) (the lines still hold u_last / h[NS] from the recompute); FSAL: u_last == y1
       // k_j = fsign * f(u_j): the cotangent reaching f is fsign * kb_j
       float ub[S::DL], cot[S::DL];
 #pragma unroll
-      for (int c = 0; c < S::DL; ++c) cot[c] = p.o.fsign * kb[6][c];
-      mlp_vjp<D, H, L>(cw, ln, l, h[6], cot, sc, ub, acc);
+      for (int c = 0; c < S::DL; ++c) cot[c] = p.o.fsign * kb[NS][c];
+      mlp_vjp<D, H, L>(cw, ln, l, h[NS], cot, sc, ub, acc);
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) {
-        ub[c] += ybar[c];
+        if constexpr (TB::FSAL) ub[c] += ybar[c];
         y0b[c] += ub[c];
 #pragma unroll
-        for (int j = 0; j < 6; ++j) kb[j][c] = fmaf(kBeta[5][j] * dt32, ub[c], kb[j][c]);
+        for (int j = 0; j < NS; ++j) kb[j][c] = fmaf(TB::beta(NS - 1, j) * dt32, ub[c], kb[j][c]);
       }
-      // stages 6..2
+      // earlier stages, last to first
 #pragma unroll
-      for (int i = 4; i >= 0; --i) {
+      for (int i = NS - 2; i >= 0; --i) {
 #pragma unroll
         for (int c = 0; c < S::DL; ++c) {
-          float sum = k[0][c] * (kBeta[i][0] * dt32);
+          float sum = k[0][c] * (TB::beta(i, 0) * dt32);
 #pragma unroll
-          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], kBeta[i][j] * dt32, sum);
+          for (int j = 1; j <= i; ++j) sum = fmaf(k[j][c], TB::beta(i, j) * dt32, sum);
           u[c] = y0[c] + sum;
         }
         regather<D, H, L>(ln, l, u, h[i + 1]);
@@ -504,11 +524,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
         for (int c = 0; c < S::DL; ++c) {
           y0b[c] += ub[c];
 #pragma unroll
-          for (int j = 0; j <= i; ++j) kb[j][c] = fmaf(kBeta[i][j] * dt32, ub[c], kb[j][c]);
+          for (int j = 0; j <= i; ++j) kb[j][c] = fmaf(TB::beta(i, j) * dt32, ub[c], kb[j][c]);
         }
       }
       if (s > 0) {
-        // FSAL: k1 of this step IS f1 of the previous step (same autograd node) -> hand its cotangent back
+        // k[0] of this step IS f1 = k[NS] of the previous step (same autograd node) -> hand its cotangent back
 #pragma unroll
         for (int c = 0; c < S::DL; ++c) { ybar[c] = y0b[c]; fbar[c] = kb[0][c]; }
       } else {
@@ -552,10 +572,10 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   return (size_t)GODE_SYNC_REGION_BYTES;   // the persistent sync region only
 }
 
-template <int D, int H, int L, int WARPS, bool WORLD>
+template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5>
 static int launch_dp5_fwd_k(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   const int grid = dp5_fwd_grid<D, H, L, WARPS>(a.B);
-  auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD>;
+  auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD, TAB>;
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap || grid > kSyncMaxGrid) return GODE_ERR_COOP;
@@ -569,14 +589,17 @@ static int launch_dp5_fwd_k(Dp5Args& a, void* workspace, size_t ws_bytes, cudaSt
 
 template <int D, int H, int L, int WARPS = kDp5Warps>
 static int launch_dp5_fwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  if (a.o.tableau == GODE_TAB_BOSH3) return launch_dp5_fwd_k<D, H, L, WARPS, false, GODE_TAB_BOSH3>(a, workspace, ws_bytes, st);
+  if (a.o.tableau == GODE_TAB_ADAPTIVE_HEUN)
+    return launch_dp5_fwd_k<D, H, L, WARPS, false, GODE_TAB_ADAPTIVE_HEUN>(a, workspace, ws_bytes, st);
   return a.w_world > 1 ? launch_dp5_fwd_k<D, H, L, WARPS, true>(a, workspace, ws_bytes, st)
                        : launch_dp5_fwd_k<D, H, L, WARPS, false>(a, workspace, ws_bytes, st);
 }
 
-template <int D, int H, int L, int WARPS = 4>
+template <int D, int H, int L, int WARPS = 4, int TAB = GODE_TAB_DOPRI5>
 static int launch_dp5_bwd(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   using S = Shape<D, H, L>;
-  auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS>;
+  auto kern = dopri5_backprop_bwd_kernel<D, H, L, WARPS, TAB>;
   const size_t smem = sizeof(float) * (WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats + WARPS * S::P +
                                        (a.T <= kDp5StageT ? (size_t)WARPS * a.T * S::G * D : 0));
   cudaError_t e;
@@ -607,6 +630,8 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
                      const GodeWorld* world) {
   if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
   Dp5Args a{};
+  if (opts->tableau < GODE_TAB_DOPRI5 || opts->tableau > GODE_TAB_ADAPTIVE_HEUN || (world && opts->tableau != GODE_TAB_DOPRI5))
+    return GODE_ERR_ARG;
   if (world) {
     a.w_rank = world->rank; a.w_world = world->world; a.w_total_B = world->total_B;
     a.w_slots = reinterpret_cast<unsigned long long* const*>(world->slots_dev); a.w_launch_ctr = world->launch_ctr;
@@ -642,8 +667,9 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
                               const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
-                              size_t ws_bytes, cudaStream_t st, const GodeWorld* xchg) {
+                              size_t ws_bytes, cudaStream_t st, const GodeWorld* xchg, int tableau) {
   if (T > kMaxT) return GODE_ERR_T_TOO_LONG;
+  if (tableau != GODE_TAB_DOPRI5 && xchg) return GODE_ERR_ARG;
   Dp5Args a{};
   if (xchg) {
     a.ws.w_rank = xchg->rank; a.ws.w_world = xchg->world; a.ws.w_ctr = xchg->launch_ctr;
@@ -654,6 +680,9 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
   a.o.ckpt_capacity = ckpt_capacity; a.o.fsign = fsign; a.grad_y0 = grad_y0; a.grad_params = grad_params;
   a.B = B; a.T = T; a.layout = layout;
   for (int i = 0; i < T; ++i) a.t[i] = t_host[i];
+  if (D == 16 && H == 16 && tableau == GODE_TAB_BOSH3) return launch_dp5_bwd<16, 16, 8, 4, GODE_TAB_BOSH3>(a, workspace, ws_bytes, st);
+  if (D == 16 && H == 16 && tableau == GODE_TAB_ADAPTIVE_HEUN)
+    return launch_dp5_bwd<16, 16, 8, 4, GODE_TAB_ADAPTIVE_HEUN>(a, workspace, ws_bytes, st);
   if (D == 16 && H == 16) {
     // 4 trajectories per warp.  With 4-warp CTAs, 148 < CTAs <= 296 means 108 SMs carry two CTAs and 40 carry one: the kernel
     // is bound by shared-memory bandwidth, so the doubled SMs finish last and everyone waits for them in the final reduction

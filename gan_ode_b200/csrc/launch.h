@@ -116,7 +116,8 @@ int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const flo
                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
                               const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
-                              size_t ws_bytes, cudaStream_t st, const GodeWorld* xchg = nullptr);
+                              size_t ws_bytes, cudaStream_t st, const GodeWorld* xchg = nullptr,
+                              int tableau = GODE_TAB_DOPRI5);
 
 int tc_rk4_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
                int dt_on_device, int B, int D, int H, int T, int precision, int out_layout, float* traj,

@@ -768,7 +768,11 @@ class _Dopri5(torch.autograd.Function):
         pdl = config.pdl
         if pdl:
             L.gode_set_thread_launch_flags(_lib.LAUNCH_PDL_BWD)
-        if ex is not None:   # the all-reduce over ranks happens inside the kernel's reduction tail (NVLink peer memory)
+        tab = meta["opts"].tableau
+        if tab:              # bosh3 / adaptive_heun: same replay kernel, other tableau
+            rc = L.gode_adaptive_backprop_bwd(tab, *args, _stream())
+            ex = None
+        elif ex is not None:   # the all-reduce over ranks happens inside the kernel's reduction tail (NVLink peer memory)
             xs = ex.struct(grad_p.numel())
             rc = L.gode_dopri5_backprop_bwd_world(*args, C.byref(xs), _stream())
         else:
@@ -992,6 +996,7 @@ def _adaptive_opts(rtol, atol, options, fsign) -> GodeAdaptiveOpts:
     o.log_capacity = int(options.get("log_capacity", config.log_capacity))
     o.ckpt_capacity = int(options.get("ckpt_capacity", config.ckpt_capacity))
     o.fsign = fsign
+    o.tableau = 0
     return o
 
 
@@ -1043,6 +1048,8 @@ def _plan_for(tag, meta, dt, D, H):
                           dt.tobytes() if host else b"", None if host else dt, b"", b"", b"", 15, False)
         return (0, pid, 0)
     o = meta["opts"]
+    if o.tableau:      # bosh3 / adaptive_heun run on the Python Functions
+        return False
     if tag == "dopri5":
         pid = m.make_plan(1, meta["T"], meta["layout"], meta["precision"], 0, False, b"", None, meta["t64"].tobytes(), bytes(o),
                           b"", 15, bool(meta["keep_ckpt"]))
@@ -1174,11 +1181,11 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         dt = _rk4_dt(t, options, y0.device)
         return dispatch("rk4", _Rk4, meta, dt)
 
-    if method == "dopri5":
+    if method in _lib.TABLEAUS:     # dopri5 (torchdiffeq's default) and, SURVEY §8 f4, bosh3 / adaptive_heun on the same kernels
         if not (D == 16 and H == 16):
-            raise NotImplementedError("the fused dopri5 kernels exist for the reference shape D=H=16 only")
+            raise NotImplementedError("the fused adaptive kernels exist for the reference shape D=H=16 only")
         if prec != _lib.PREC["fp32"]:
-            raise NotImplementedError("dopri5 runs in fp32 only: its error estimate is below tf32/bf16 resolution")
+            raise NotImplementedError("adaptive solvers run in fp32 only: the error estimate is below tf32/bf16 resolution")
         # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): by default torchdiffeq's continuous
         # adjoint (gode_dopri5_adjoint_bwd).  options={'adjoint': 'discrete'} (or config.dopri5_adjoint) instead
         # differentiates the recorded accepted steps (gode_dopri5_backprop_bwd): one replay, no second adaptive solve, any
@@ -1186,12 +1193,23 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         # torchdiffeq: t -> float64 for adaptive solvers; the grid rides in the launch parameters (syncs iff t is on GPU)
         t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
+        meta["opts"].tableau = _lib.TABLEAUS[method]
         meta["t64"] = t64
         meta["traj_log_capacity"] = int(options.get("traj_log_capacity", 0))  # per-attempt logs per trajectory (tests)
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
+        other = method != "dopri5"
         if meta["opts"].norm_scope == _lib.NORM_TRAJ:
+            if other:
+                raise NotImplementedError("per-trajectory step control exists for dopri5 only")
             return dispatch("dopri5_traj", _Dopri5Traj, meta)
         mode = options.get("adjoint", config.dopri5_adjoint)
+        if other:
+            if options.get("norm") == "world":
+                raise NotImplementedError("the world-scope norm exists for dopri5 only")
+            if adjoint and mode == "continuous":
+                raise NotImplementedError('odeint_adjoint with method="{}": the continuous adjoint re-solve is built for dopri5 '
+                                          "only; pass options={{'adjoint': 'discrete'}} (gradient of the recorded steps) or use "
+                                          "odeint".format(method))
         if mode not in ("continuous", "discrete"):
             raise ValueError("options['adjoint'] must be 'continuous' or 'discrete'")
         if options.get("norm") == "world":
@@ -1215,7 +1233,8 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
             return dispatch("dopri5_adjoint", _Dopri5Adjoint, meta)
         return dispatch("dopri5", _Dopri5, meta)
 
-    raise NotImplementedError('method "{}" is not built (rk4, euler, midpoint and dopri5 are; SURVEY §8f-4)'.format(method))
+    raise NotImplementedError('method "{}" is not built (rk4, euler, midpoint, dopri5, bosh3 and adaptive_heun are; '
+                              'SURVEY §8f-4)'.format(method))
 
 
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):

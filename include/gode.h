@@ -82,6 +82,13 @@ enum {
   GODE_ST_PEER_TIMEOUT = 16 /* world-scope norm: a peer rank did not publish within 10 s   */
 };
 
+/* adaptive tableaus (GodeAdaptiveOpts.tableau; 0 keeps every existing caller on dopri5) */
+enum {
+  GODE_TAB_DOPRI5 = 0,        /* dopri5.py: Dormand–Prince 5(4), FSAL                                   */
+  GODE_TAB_BOSH3 = 1,         /* bosh3.py: Bogacki–Shampine 3(2), FSAL                                  */
+  GODE_TAB_ADAPTIVE_HEUN = 2  /* adaptive_heun.py: Heun–Euler 2(1); f1 = k[-1] handed on as upstream does */
+};
+
 #define GODE_MAX_HOST_STEPS 255
 #define GODE_SYNC_REGION_BYTES (256 * 1024) /* persistent grid-sync region at the front of every workspace */
 
@@ -119,7 +126,7 @@ typedef struct GodeAdaptiveOpts {
   int32_t log_capacity;  /* entries in the attempt arrays (t0/dt/er/accepted)              */
   int32_t ckpt_capacity; /* accepted steps the checkpoint buffer can hold (0: none kept)   */
   float fsign;           /* +1, or -1 when the caller negated a decreasing time grid (torchdiffeq _ReverseFunc) */
-  int32_t _pad;
+  int32_t tableau;       /* GODE_TAB_*: gode_dopri5_fwd / gode_dopri5_backprop_bwd (batch-global control); others: dopri5 only */
 } GodeAdaptiveOpts;
 
 /* ---- introspection ------------------------------------------------------------------------- */
@@ -216,6 +223,14 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
                              const GodeStepLog* log, const float* ckpt, const double* acc_t0,
                              const double* acc_dt, int ckpt_capacity, float fsign, float* grad_y0, float* grad_params,
                              void* workspace, size_t ws_bytes, gode_stream_t stream);
+
+/* f4: the same replay for the other adaptive tableaus (`tableau` = the GODE_TAB_* the forward ran with through
+ * GodeAdaptiveOpts.tableau: bosh3, adaptive_heun); tableau = GODE_TAB_DOPRI5 is gode_dopri5_backprop_bwd. */
+int gode_adaptive_backprop_bwd(int tableau, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                               const float* b2, const double* t_host, int B, int D, int H, int T, int layout,
+                               const GodeStepLog* log, const float* ckpt, const double* acc_t0, const double* acc_dt,
+                               int ckpt_capacity, float fsign, float* grad_y0, float* grad_params, void* workspace,
+                               size_t ws_bytes, gode_stream_t stream);
 
 /* ---- e: gode_dopri5_backprop_bwd with the data-parallel all-reduce of grad_params fused into its reduction tail ------ */
 /* Same computation; in addition grad_params leaves the kernel summed over all ranks (rank-order sum, bit-identical on every

@@ -89,7 +89,7 @@ def _grad_case(solver_ref, solver_gpu, B, method, layout="tbd", scale=1.0, t=Non
     opts = dict(kw_gpu.pop("options", None) or {})
     opts["layout"] = layout
     out = run(solver_gpu, fg, y0.to(DEV), t, g.to(DEV), method=method, options=opts, **kw_gpu)
-    if method == "dopri5":
+    if method in ("dopri5", "bosh3", "adaptive_heun"):
         # same discretisation on both sides: the oracle replays the dt of every attempt the kernel logged and
         # treats dt as data; accept/reject decisions must still agree
         glog = gode.last_step_log()
@@ -98,7 +98,7 @@ def _grad_case(solver_ref, solver_gpu, B, method, layout="tbd", scale=1.0, t=Non
         o.update(_replay_dt=glog.dt, _detach_dt0=True)
         kw = dict(kw, options=o)
     ref32 = run(solver_ref, f, y0, t, g, method=method, **kw)
-    if method == "dopri5":
+    if method in ("dopri5", "bosh3", "adaptive_heun"):
         assert tdq.last_step_log().accepted == glog.accepted
     f64 = clone_to(f, "cpu", torch.float64)
     ref64 = run(solver_ref, f64, y0.double(), t, g.double(), method=method, **kw)
@@ -1543,3 +1543,46 @@ def test_fused_sample_images_solves_only_the_kept_rows_and_generator_wrapper():
     finally:
         fs.uninstall()
     assert "sample_videos" not in gen.__dict__
+
+
+# ---- f4: the other adaptive tableaus on the dopri5 kernels -------------------------------------------------------------------
+@pytest.mark.parametrize("method,tol", [("bosh3", 1e-4), ("adaptive_heun", 1e-3)])
+@pytest.mark.parametrize("B,scale", [(16, 1.0), (37, 4.0), (4096, 1.0)])
+def test_bosh3_and_adaptive_heun_match_oracle(method, tol, B, scale):
+    """torchdiffeq's bosh3 (Bogacki-Shampine 3(2), FSAL) and adaptive_heun (Heun-Euler 2(1), not FSAL: y1 from c_sol, and
+    f1 = k[-1] handed to the next step as upstream's _runge_kutta_step does) on dopri5_fwd_kernel / dopri5_backprop_bwd_kernel
+    templated over the tableau: identical accept/reject sequence, dt sequence to 1e-4, trajectory, and backprop-through-solver
+    gradients on the replayed discretisation."""
+    _need_gpu()
+    order = {"bosh3": 3, "adaptive_heun": 2}[method]
+    opts = {"ckpt_capacity": 512}
+    for bump in range(8):
+        f = make_field(seed=7 + 1000 * bump, scale=scale)
+        torch.manual_seed(8 + 1000 * bump)
+        y0 = torch.randn(B, 16)
+        with torch.no_grad():
+            ref = tdq.odeint(f, y0, _t16(), method=method, rtol=tol, atol=tol)
+        rlog = tdq.last_step_log()
+        if not _near_tie(rlog):
+            break
+    with torch.no_grad():
+        out = gode.odeint(clone_to(f, DEV), y0.to(DEV), _t16(), method=method, rtol=tol, atol=tol, options=opts)
+    glog = gode.last_step_log()
+    assert glog.status == 0 and glog.accepted == rlog.accepted, (glog.accepted, rlog.accepted)
+    assert glog.nfe == rlog.nfe and abs(glog.dt0 - rlog.dt0) <= 1e-5 * abs(rlog.dt0)
+    for n in range(len(glog.dt) - 1):     # the kernel's controller arithmetic, exact on its own log (exponent 1/order)
+        er, dt = glog.error_ratio[n], glog.dt[n]
+        fac = 10.0 if er == 0 else min(10.0, max(0.9 / er ** (1.0 / order), 1.0 if er < 1 else 0.2))
+        assert abs(glog.dt[n + 1] - dt * fac) <= 1e-12 * glog.dt[n + 1]
+    same_dt = all(abs(a - b) <= 1e-4 * abs(b) for a, b in zip(glog.dt, rlog.dt))
+    assert rel_err(out, ref) <= (2e-5 if same_dt else 10 * tol), (rel_err(out, ref), same_dt)
+    if B <= 64:
+        outg, r32, r64 = _grad_case(tdq.odeint, gode.odeint, B, method, scale=scale, rtol=tol, atol=tol, options=opts)
+        _assert_grads(outg, r32, r64)
+        # odeint_adjoint: the recorded-step gradient is offered, the continuous re-solve is dopri5-only
+        with pytest.raises(NotImplementedError, match="discrete"):
+            gode.odeint_adjoint(clone_to(f, DEV), y0.to(DEV).requires_grad_(True), _t16(), method=method, rtol=tol, atol=tol)
+        ya = y0.to(DEV).requires_grad_(True)
+        sol = gode.odeint_adjoint(clone_to(f, DEV), ya, _t16(), method=method, rtol=tol, atol=tol,
+                                  options=dict(opts, adjoint="discrete"))
+        assert torch.isfinite(torch.autograd.grad(sol.sum(), [ya])[0]).all()

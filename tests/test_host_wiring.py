@@ -95,7 +95,7 @@ def test_layout_precision_and_method_options_reach_the_abi(wired):
     name, a = wired.calls[-1]
     assert name == "gode_fixed_fwd" and a[0] == _lib.METHODS["midpoint"]
     with pytest.raises(NotImplementedError):
-        gode.odeint(f, y0, t, method="bosh3")
+        gode.odeint(f, y0, t, method="dopri8")
     # step_size under the adjoint: fine-grid forward launch, then the sub-stepped adjoint entry point with its device tables
     wired.calls.clear()
     yr = y0.clone().requires_grad_(True)
