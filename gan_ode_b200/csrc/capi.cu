@@ -124,7 +124,9 @@ static int rk4_bwd_common(bool adjoint, const float* traj, const float* grad_tra
                             scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
   if (precision != GODE_PREC_FP32) return GODE_ERR_PRECISION;
   if (wide_shape(D, H)) {
-    if (!adjoint) return GODE_ERR_SHAPE;  // wide backprop-through-solver: not built
+    if (!adjoint)   // backprop through the solver for the wide fields (round 2)
+      return wide_rk4_backprop_bwd(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0, grad_params,
+                                   scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
     return wide_rk4_adjoint_bwd(traj, grad_traj, W1, b1, W2, b2, dt, dt_on_device, B, D, H, T, layout, grad_y0,
                                 grad_params, scratch_of(workspace), scratch_bytes(ws_bytes), (cudaStream_t)stream);
   }

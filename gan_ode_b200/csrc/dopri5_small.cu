@@ -275,6 +275,10 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       if (p.o.ckpt_capacity > 0) {
         if (n_acc < p.o.ckpt_capacity) {
           if (valid) store_frag<S::DL>(p.ckpt + ((size_t)n_acc * p.B + b) * D + l * S::DL, y0);
+          // not FSAL: the step's f0 is the PREVIOUS step's last stage derivative, not f(y0) — the replay cannot recompute
+          // it from y0, so it is checkpointed as well (second half of the checkpoint buffer: 2 * ckpt_capacity rows)
+          if constexpr (!TB::FSAL)
+            if (valid) store_frag<S::DL>(p.ckpt + ((size_t)(p.o.ckpt_capacity + n_acc) * p.B + b) * D + l * S::DL, k[0]);
           if (logger) { p.acc_t0[n_acc] = t0; p.acc_dt[n_acc] = dt; }
         } else {
           status |= GODE_ST_CKPT_OVERFLOW;
@@ -438,7 +442,15 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
         if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(s - 1) * p.B + b) * D + l * S::DL, y0n);
       }
       // recompute the step exactly as the forward did
-      field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], h[0]);
+      if (TB::FSAL || s == 0) {
+        field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], h[0]);
+      } else {   // not FSAL: f0 of this step is the previous step's k[NS] (checkpointed by the forward)
+#pragma unroll
+        for (int c = 0; c < S::DL; ++c) k[0][c] = 0.f;
+        if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(p.o.ckpt_capacity + s) * p.B + b) * D + l * S::DL, k[0]);
+#pragma unroll
+        for (int c = 0; c < S::HL; ++c) h[0][c] = 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < NS; ++i) {
 #pragma unroll

@@ -156,6 +156,10 @@ int wide_rk4_adjoint_bwd(const float* traj, const float* grad_traj, const float*
                          const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
                          float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+int wide_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                          const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
+                          float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 inline bool small_field_shape(int D, int H) { return D == 16 && H == 16; }
 int tc_rk4_fwd_wide(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
                     int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st);

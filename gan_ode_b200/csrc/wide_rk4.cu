@@ -218,6 +218,84 @@ __global__ void __launch_bounds__(kWideWarps * 32) wide_rk4_adjoint_kernel(const
   }
 }
 
+// Backprop through the solver (autograd-through-odeint semantics) for the wide fields: per step the four stage
+// inputs and tanh vectors are recomputed from the stored y_s exactly as the forward computed them, then the stages are
+// walked 4..1 (same algebra as rk4_backprop_bwd_kernel); every VJP emits its rows (cotangent on k_s, h_s, delta_s, u_s) to
+// the same scratch layout as the adjoint, so the same contraction kernels produce the parameter gradients.
+template <int D, int H>
+__global__ void __launch_bounds__(kWideWarps * 32) wide_rk4_backprop_kernel(const __grid_constant__ WideArgs p) {
+  using W = Wide<D, H>;
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, l = tid & 31, warp = tid >> 5;
+  W::stage(smem, p.W1, p.b1, p.W2, p.b2, tid, kWideWarps * 32);
+  W w;
+  w.bind(smem, warp);
+  __syncthreads();
+  const float* __restrict__ dtp = p.dt_dev ? p.dt_dev : p.dt_val;
+  for (int b = blockIdx.x * kWideWarps + warp; b < p.B; b += gridDim.x * kWideWarps) {
+    float yb[W::DL];  // cotangent of y_{s+1}
+#pragma unroll
+    for (int c = 0; c < W::DL; ++c) yb[c] = p.grad_traj[w_off(p.layout, p.T - 1, b, p.B, p.T, D) + l + 32 * c];
+    for (int s = p.T - 2; s >= 0; --s) {
+      const float dt = dtp[s];
+      float y[W::DL], gs[W::DL], k1[W::DL], k2[W::DL], k3[W::DL], k4[W::DL], u2[W::DL], u3[W::DL], u4[W::DL];
+      float h1[W::HL], h2[W::HL], h3[W::HL], h4[W::HL];
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) {
+        y[c] = p.traj_in[w_off(p.layout, s, b, p.B, p.T, D) + l + 32 * c];
+        gs[c] = p.grad_traj[w_off(p.layout, s, b, p.B, p.T, D) + l + 32 * c];
+      }
+      // recompute (same expressions as wide_rk4_fwd_kernel)
+      w.forward(l, y, k1, h1);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) u2[c] = y[c] + dt * k1[c] * kWThird;
+      w.forward(l, u2, k2, h2);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) u3[c] = y[c] + dt * (k2[c] - k1[c] * kWThird);
+      w.forward(l, u3, k3, h3);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) u4[c] = y[c] + dt * (k1[c] - k2[c] + k3[c]);
+      w.forward(l, u4, k4, h4);
+      (void)k4;
+      // reverse
+      const float c18 = dt * 0.125f, c38 = 3.f * c18, dt3 = dt * kWThird;
+      float kb1[W::DL], kb2[W::DL], kb3[W::DL], kb4[W::DL], ub[W::DL], dl_[W::HL];
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) { kb1[c] = c18 * yb[c]; kb2[c] = c38 * yb[c]; kb3[c] = c38 * yb[c]; kb4[c] = c18 * yb[c]; }
+      const size_t row0 = ((size_t)b * (p.T - 1) + s) * 4;
+      auto emit = [&](int stage, const float (&cot)[W::DL], const float (&u)[W::DL], const float (&hk)[W::HL]) {
+        const size_t r = row0 + stage;
+#pragma unroll
+        for (int c = 0; c < W::DL; ++c) { p.sa[r * D + l + 32 * c] = cot[c]; p.su[r * D + l + 32 * c] = u[c]; }
+#pragma unroll
+        for (int c = 0; c < W::HL; ++c) { p.sh[r * H + l + 32 * c] = hk[c]; p.sd[r * H + l + 32 * c] = dl_[c]; }
+      };
+      w.vjp(l, h4, kb4, ub, dl_);
+      emit(3, kb4, u4, h4);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) { yb[c] += ub[c]; kb1[c] += dt * ub[c]; kb2[c] -= dt * ub[c]; kb3[c] += dt * ub[c]; }
+      __syncwarp();
+      w.vjp(l, h3, kb3, ub, dl_);
+      emit(2, kb3, u3, h3);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) { yb[c] += ub[c]; kb2[c] += dt * ub[c]; kb1[c] -= dt3 * ub[c]; }
+      __syncwarp();
+      w.vjp(l, h2, kb2, ub, dl_);
+      emit(1, kb2, u2, h2);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) { yb[c] += ub[c]; kb1[c] += dt3 * ub[c]; }
+      __syncwarp();
+      w.vjp(l, h1, kb1, ub, dl_);
+      emit(0, kb1, y, h1);
+#pragma unroll
+      for (int c = 0; c < W::DL; ++c) yb[c] += ub[c] + gs[c];
+      __syncwarp();
+    }
+#pragma unroll
+    for (int c = 0; c < W::DL; ++c) p.grad_y0[(size_t)b * D + l + 32 * c] = yb[c];
+  }
+}
+
 // ---- contraction of the scratch rows: C[M][N] = sum_n A[n][M] * Bm[n][N], plus column sums of A -------------------------
 // split-K: CTA s handles rows [s*KS, (s+1)*KS); 256 threads, each an 8 x (N/32)... kept simple: thread t owns output
 // columns n = t % N_T .. and rows m in a strided set; partials go to [slices][M*N + M]; a second pass adds the slices
@@ -297,14 +375,14 @@ static int launch_wide_fwd(WideArgs& a, cudaStream_t st) {
   return launch_status();
 }
 
-template <int D, int H>
+template <int D, int H, bool ADJOINT = true>
 static int launch_wide_bwd(WideArgs& a, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st) {
   if (ws_bytes < wide_bwd_workspace_bytes(a.B, D, H, a.T)) return GODE_ERR_WORKSPACE;
   const size_t rows = wide_rows(a.B, a.T);
   float* base = reinterpret_cast<float*>(workspace);
   a.sa = base; a.su = a.sa + rows * D; a.sh = a.su + rows * D; a.sd = a.sh + rows * H;
   float* partial = a.sd + rows * H;
-  auto kern = wide_rk4_adjoint_kernel<D, H>;
+  auto kern = ADJOINT ? wide_rk4_adjoint_kernel<D, H> : wide_rk4_backprop_kernel<D, H>;
   const size_t smem = Wide<D, H>::smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return -(1000 + (int)e);
@@ -352,6 +430,19 @@ int wide_rk4_adjoint_bwd(const float* traj, const float* grad_traj, const float*
   if (D == 64 && H == 256) return launch_wide_bwd<64, 256>(a, grad_params, workspace, ws_bytes, st);
   if (D == 32 && H == 32) return launch_wide_bwd<32, 32>(a, grad_params, workspace, ws_bytes, st);
   if (D == 32 && H == 64) return launch_wide_bwd<32, 64>(a, grad_params, workspace, ws_bytes, st);
+  return GODE_ERR_SHAPE;
+}
+
+int wide_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,
+                          const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
+                          float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st) {
+  WideArgs a{};
+  a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj_in = traj; a.grad_traj = grad_traj; a.grad_y0 = grad_y0;
+  a.B = B; a.T = T; a.layout = layout;
+  if (int rc = fill_wide_dt(a, dt, dt_on_device, T)) return rc;
+  if (D == 64 && H == 256) return launch_wide_bwd<64, 256, false>(a, grad_params, workspace, ws_bytes, st);
+  if (D == 32 && H == 32) return launch_wide_bwd<32, 32, false>(a, grad_params, workspace, ws_bytes, st);
+  if (D == 32 && H == 64) return launch_wide_bwd<32, 64, false>(a, grad_params, workspace, ws_bytes, st);
   return GODE_ERR_SHAPE;
 }
 

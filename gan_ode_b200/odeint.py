@@ -716,7 +716,9 @@ class _Dopri5(torch.autograd.Function):
         kc = o.ckpt_capacity if keep else 0
         opts = GodeAdaptiveOpts.from_buffer_copy(bytes(o))
         opts.ckpt_capacity = kc
-        ckpt = torch.empty((max(kc, 1), B, D), dtype=torch.float32, device=dev) if keep else None
+        # adaptive_heun is not FSAL: the forward checkpoints every step's f0 beside its y0 (second half of the buffer)
+        rows = max(kc, 1) * (2 if o.tableau == _lib.TABLEAUS["adaptive_heun"] else 1)
+        ckpt = torch.empty((rows, B, D), dtype=torch.float32, device=dev) if keep else None
         acc = torch.empty(2 * max(kc, 1), dtype=torch.float64, device=dev) if keep else None
         ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
         ws = _workspace(dev, ws_bytes)

@@ -86,7 +86,8 @@ enum {
 enum {
   GODE_TAB_DOPRI5 = 0,        /* dopri5.py: Dormand–Prince 5(4), FSAL                                   */
   GODE_TAB_BOSH3 = 1,         /* bosh3.py: Bogacki–Shampine 3(2), FSAL                                  */
-  GODE_TAB_ADAPTIVE_HEUN = 2  /* adaptive_heun.py: Heun–Euler 2(1); f1 = k[-1] handed on as upstream does */
+  GODE_TAB_ADAPTIVE_HEUN = 2  /* adaptive_heun.py: Heun–Euler 2(1); f1 = k[-1] handed on as upstream does.  Not FSAL: the
+                                 checkpoint buffer must hold 2 * ckpt_capacity rows (y0 of every step, then its f0) */
 };
 
 #define GODE_MAX_HOST_STEPS 255

@@ -983,6 +983,12 @@ def test_wide_field_rk4_forward_and_adjoint(D, H, B):
     assert torch.equal(out_sol[0].cpu(), y0)
     assert rel_err(out_sol, ref_sol) <= TOL
     _assert_grads(out_g, ref_g, ref64)
+    # backprop through the solver (plain odeint) for the wide fields: autograd through the oracle's forward
+    ref_sol, ref_g = run(tdq.odeint, f, y0, g)
+    _, ref64 = run(tdq.odeint, clone_to(f, "cpu", torch.float64), y0.double(), g.double())
+    out_sol, out_g = run(gode.odeint, clone_to(f, DEV), y0.to(DEV), g.to(DEV), options={"layout": "btd" if B % 2 else "tbd"})
+    assert rel_err(out_sol, ref_sol) <= TOL
+    _assert_grads(out_g, ref_g, ref64)
 
 
 def test_wide_field_deterministic_and_unsupported_combinations():
@@ -995,8 +1001,9 @@ def test_wide_field_deterministic_and_unsupported_combinations():
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     with pytest.raises(NotImplementedError):  # no fused dopri5 for wide fields yet
         gode.odeint(f, y0, _t16(), method="dopri5")
-    with pytest.raises(gode.GodeError):       # wide backprop-through-solver not built
-        torch.autograd.grad(gode.odeint(f, y0, _t16(), method="rk4"), [y0], g)
+    c = torch.autograd.grad(gode.odeint(f, y0, _t16(), method="rk4"), [y0] + list(f.parameters()), g)
+    d = torch.autograd.grad(gode.odeint(f, y0, _t16(), method="rk4"), [y0] + list(f.parameters()), g)
+    assert all(torch.equal(x, y) for x, y in zip(c, d))     # backprop through the solver, wide field: deterministic too
 
 
 @pytest.mark.parametrize("B", [1, 129, 1000, 40000])
