@@ -8,6 +8,7 @@
 //                               dt sequence read from the device-side step log (no host round trip).
 #include <stdlib.h>
 #include "dopri5_common.cuh"
+#include "gru_cell.cuh"
 
 #ifdef GODE_TRACE
 // Developer build only (python -m gan_ode_b200.build --trace -> libgode_trace.so): thread 0 of CTA 0 stamps
@@ -51,6 +52,14 @@ struct Dp5Args {
   long long w_total_B;
   unsigned long long* const* w_slots;
   unsigned int* w_launch_ctr;
+  // persistent ODE-RNN sampler (RNN instantiation, models/mocogan_ode_rnn.py:45-52): F (solve over [0,1] -> GRU jump) pairs in
+  // ONE cooperative launch.  Frame f: traj = seg + f*2*B*D ([input copy, h']), log block at (char*)log + f*log_stride
+  // ([GodeStepLog | attempt arrays] as gode_dopri5_fwd lays them out), ckpt + f*kc*B*D, acc_t0/acc_dt + f*2*kc
+  int F;
+  size_t log_stride;
+  const float* eps;                           // (F,B,D) the per-frame noise inputs e_t
+  const float *g_wih, *g_whh, *g_bih, *g_bhh; // nn.GRUCell parameters
+  float* codes;                               // (F,B,D) h_f
   double t[kMaxT];
 };
 
@@ -131,7 +140,7 @@ __device__ __forceinline__ void world_allreduce_sum(double (&v)[NV], const Dp5Ar
 // WORLD: world-scope norm compiled in (gode_dopri5_fwd_world).  A template parameter, not a runtime flag: the mere presence
 // of the exchange code cost the ordinary solve 4 us of 30 at the bench shape (measured), so the default instantiation is
 // kept free of it.
-template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5>
+template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5, bool RNN = false>
 __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_constant__ Dp5Args p) {
   using S = Shape<D, H, L>;
   using TB = Tableau<TAB>;
@@ -139,6 +148,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   __shared__ __align__(16) float s_lines[WARPS * FwdLines<D, H, L>::kFloatsPerWarp];
   __shared__ float s_f[WARPS * kGsMaxVals];
   __shared__ double s_d[kGsMaxVals];
+  __shared__ float s_gru_raw[RNN ? sizeof(GruW) / sizeof(float) : 1];   // GRU weights (RNN instantiation only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane / L, l = lane % L;
   GODE_TP(0, 0);
   griddep_launch_dependents();   // a backward launched with PDL may stage its weights under this kernel's tail
@@ -148,6 +158,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   ln.bind(s_lines + warp * FwdLines<D, H, L>::kFloatsPerWarp, g);
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
+  GruW& s_gru = *reinterpret_cast<GruW*>(s_gru_raw);
+  if constexpr (RNN) {
+    load_w(s_gru, p.g_wih, p.g_whh, p.g_bih, p.g_bhh, tid, WARPS * 32);
+    __syncthreads();
+  }
   const int b = (blockIdx.x * WARPS + warp) * S::G + g;
   const bool valid = b < p.B;
   const bool logger = (blockIdx.x == 0 && tid == 0);
@@ -163,14 +178,34 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
   float y0[S::DL], k[NS + 1][S::DL], hk[S::HL];
 #pragma unroll
   for (int c = 0; c < S::DL; ++c) y0[c] = 0.f;
-  if (valid) {
-    load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y0);
-    store_frag<S::DL>(p.traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y0);
+  if (valid) load_frag<S::DL>(p.y0 + (size_t)b * D + l * S::DL, y0);
+  int status = 0;
+  const int n_frames = RNN ? p.F : 1;
+  for (int fr = 0; fr < n_frames; ++fr) {   // one pass for odeint; the ODE-RNN sampler runs its frames here
+  // this frame's outputs (the plain solve: the caller's buffers)
+  float* traj = p.traj;
+  GodeStepLog* log = p.log;
+  double* att_t0 = p.att_t0; double* att_dt = p.att_dt; float* att_er = p.att_er; uint8_t* att_acc = p.att_acc;
+  float* ckpt = p.ckpt; double* acc_t0 = p.acc_t0; double* acc_dt = p.acc_dt;
+  if constexpr (RNN) {
+    const size_t cap = (size_t)p.o.log_capacity, kc = (size_t)p.o.ckpt_capacity;
+    unsigned char* lg = reinterpret_cast<unsigned char*>(p.log) + (size_t)fr * p.log_stride;
+    traj = p.traj + (size_t)fr * 2 * p.B * D;
+    log = reinterpret_cast<GodeStepLog*>(lg);
+    att_t0 = reinterpret_cast<double*>(lg + 64); att_dt = reinterpret_cast<double*>(lg + 64 + 8 * cap);
+    att_er = reinterpret_cast<float*>(lg + 64 + 16 * cap); att_acc = lg + 64 + 20 * cap;
+    ckpt = p.ckpt ? p.ckpt + (size_t)fr * kc * p.B * D : nullptr;
+    acc_t0 = p.acc_t0 ? p.acc_t0 + (size_t)fr * 2 * kc : nullptr;
+    acc_dt = p.acc_t0 ? p.acc_t0 + (size_t)fr * 2 * kc + kc : nullptr;
   }
+  float hp[S::DL];   // RNN: the solve's last output h' (what the jump consumes)
+#pragma unroll
+  for (int c = 0; c < S::DL; ++c) hp[c] = 0.f;
+  if (valid) store_frag<S::DL>(traj + toff(p.layout, 0, b, p.B, p.T, D) + l * S::DL, y0);
   GODE_TP(0, 1);
   field<D, H, L>(w, ln, l, p.o.fsign, y0, k[0], hk);  // f0
   GODE_TP(0, 2);
-  int nfe = 1, status = 0;
+  int nfe = 1;
   double t0 = p.t[0];
   double dt;
 
@@ -216,7 +251,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
       dt = (double)fminf(100.f * h0, h1);
     }
   }
-  if (logger) p.log->dt0 = dt;
+  if (logger) log->dt0 = dt;
   GODE_TP(0, 3);
 
   // ---- solvers.py::AdaptiveStepsizeODESolver.integrate / rk_common.py::_adaptive_step ---------------------------
@@ -269,17 +304,17 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     if (dt > p.o.max_step) accept = false;
     if (dt <= p.o.min_step) accept = true;
     if (logger && n_att < p.o.log_capacity) {
-      p.att_t0[n_att] = t0; p.att_dt[n_att] = dt; p.att_er[n_att] = er; p.att_acc[n_att] = accept ? 1 : 0;
+      att_t0[n_att] = t0; att_dt[n_att] = dt; att_er[n_att] = er; att_acc[n_att] = accept ? 1 : 0;
     }
     if (accept) {
       if (p.o.ckpt_capacity > 0) {
         if (n_acc < p.o.ckpt_capacity) {
-          if (valid) store_frag<S::DL>(p.ckpt + ((size_t)n_acc * p.B + b) * D + l * S::DL, y0);
+          if (valid) store_frag<S::DL>(ckpt + ((size_t)n_acc * p.B + b) * D + l * S::DL, y0);
           // not FSAL: the step's f0 is the PREVIOUS step's last stage derivative, not f(y0) — the replay cannot recompute
           // it from y0, so it is checkpointed as well (second half of the checkpoint buffer: 2 * ckpt_capacity rows)
           if constexpr (!TB::FSAL)
-            if (valid) store_frag<S::DL>(p.ckpt + ((size_t)(p.o.ckpt_capacity + n_acc) * p.B + b) * D + l * S::DL, k[0]);
-          if (logger) { p.acc_t0[n_acc] = t0; p.acc_dt[n_acc] = dt; }
+            if (valid) store_frag<S::DL>(ckpt + ((size_t)(p.o.ckpt_capacity + n_acc) * p.B + b) * D + l * S::DL, k[0]);
+          if (logger) { acc_t0[n_acc] = t0; acc_dt[n_acc] = dt; }
         } else {
           status |= GODE_ST_CKPT_OVERFLOW;
         }
@@ -318,7 +353,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
             tot = tot + xp * ca[c];
             o[c] = tot;
           }
-          if (valid) store_frag<S::DL>(p.traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, o);
+          if (valid) store_frag<S::DL>(traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, o);
+          if constexpr (RNN) {
+#pragma unroll
+            for (int c = 0; c < S::DL; ++c) hp[c] = o[c];
+          }
           ++iout;
           n_steps = -1;  // max_num_steps is counted per output interval (per _advance call)
         }
@@ -335,12 +374,39 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
     ++n_steps;
   }
   if (logger) {
-    p.log->status = status;
+    log->status = status;
     if (status != 0 && p.mailbox) *reinterpret_cast<volatile int32_t*>(p.mailbox) = status;
-    p.log->n_attempts = n_att;
-    p.log->n_accepted = n_acc;
-    p.log->nfe = nfe;
-    p.log->t_final = t0;
+    log->n_attempts = n_att;
+    log->n_accepted = n_acc;
+    log->nfe = nfe;
+    log->t_final = t0;
+  }
+  if constexpr (RNN) {
+    if (status != 0) {   // a failed frame ends the sampler: the remaining frames' logs carry the status too
+      if (logger)
+        for (int f2 = fr + 1; f2 < n_frames; ++f2)
+          reinterpret_cast<GodeStepLog*>(reinterpret_cast<unsigned char*>(p.log) + (size_t)f2 * p.log_stride)->status = status;
+      break;
+    }
+    // the jump h_f = GRUCell(e_f, h'_f) (models/mocogan_ode_rnn.py:49): per trajectory, no grid-wide step
+    float xe[S::DL];
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) xe[c] = 0.f;
+    if (valid) load_frag<S::DL>(p.eps + ((size_t)fr * p.B + b) * D + l * S::DL, xe);
+    __syncwarp();
+    store_frag<S::DL>(ln.y + l * S::DL, xe);
+    store_frag<S::DL>(ln.h + l * S::DL, hp);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < S::DL; ++c) {
+      const Gates gt = gates(s_gru, ln.y, ln.h, l * S::DL + c);
+      y0[c] = (1.f - gt.z) * gt.n + gt.z * hp[c];
+    }
+    if (valid) store_frag<S::DL>(p.codes + ((size_t)fr * p.B + b) * D + l * S::DL, y0);
+    __syncwarp();
+  }
+  }   // frames
+  if (logger) {
     if constexpr (WORLD) *p.w_launch_ctr = wepoch;
     ss.finish(p.gs);   // every CTA has arrived at the last reduction, hence has read the bases
   }
@@ -584,10 +650,10 @@ size_t dopri5_small_workspace_bytes(int B, int D, int H) {
   return (size_t)GODE_SYNC_REGION_BYTES;   // the persistent sync region only
 }
 
-template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5>
+template <int D, int H, int L, int WARPS, bool WORLD, int TAB = GODE_TAB_DOPRI5, bool RNN = false>
 static int launch_dp5_fwd_k(Dp5Args& a, void* workspace, size_t ws_bytes, cudaStream_t st) {
   const int grid = dp5_fwd_grid<D, H, L, WARPS>(a.B);
-  auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD, TAB>;
+  auto kern = dopri5_fwd_kernel<D, H, L, WARPS, WORLD, TAB, RNN>;
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, 0, limit_cache);
   if (cap <= 0 || grid > cap || grid > kSyncMaxGrid) return GODE_ERR_COOP;
@@ -673,6 +739,33 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
     return launch_dp5_fwd<16, 16, 1>(a, workspace, ws_bytes, st);
   }
   return GODE_ERR_SHAPE;
+}
+
+// All F frames of the ODE-RNN sampler in ONE cooperative launch (models/mocogan_ode_rnn.py:45-52): per frame the same dopri5
+// solve over [0, 1] as gode_dopri5_fwd (batch-global control, its own initial-step selection, step log and checkpoints),
+// then the GRU jump per trajectory — no grid-wide step for the jump, the grid-sync tags just keep counting across frames.
+int dopri5_small_odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2,
+                            const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                            int B, int D, int H, int F, const GodeAdaptiveOpts* opts, float* codes, float* seg,
+                            unsigned char* logs, size_t log_stride, float* ckpt, double* acc, void* workspace,
+                            size_t ws_bytes, cudaStream_t st) {
+  if (!(D == 16 && H == 16) || opts->tableau != GODE_TAB_DOPRI5) return GODE_ERR_SHAPE;
+  Dp5Args a{};
+  a.y0 = h0; a.W1 = W1; a.b1 = b1; a.W2 = W2; a.b2 = b2; a.traj = seg; a.log = reinterpret_cast<GodeStepLog*>(logs);
+  a.mailbox = status_mailbox();
+  a.ckpt = ckpt; a.acc_t0 = acc; a.acc_dt = acc;
+  a.o = *opts; a.B = B; a.T = 2; a.layout = GODE_LAYOUT_TBD;
+  a.t[0] = 0.0; a.t[1] = 1.0;
+  a.F = F; a.log_stride = log_stride; a.eps = eps; a.g_wih = w_ih; a.g_whh = w_hh; a.g_bih = b_ih; a.g_bhh = b_hh;
+  a.codes = codes;
+  const bool first8 = B < 2048;
+  int rc = first8 ? launch_dp5_fwd_k<16, 16, 8, kDp5Warps, false, GODE_TAB_DOPRI5, true>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
+  if (rc != GODE_ERR_COOP) return rc;
+  rc = launch_dp5_fwd_k<16, 16, 4, kDp5Warps, false, GODE_TAB_DOPRI5, true>(a, workspace, ws_bytes, st);
+  if (rc != GODE_ERR_COOP) return rc;
+  rc = launch_dp5_fwd_k<16, 16, 2, kDp5Warps, false, GODE_TAB_DOPRI5, true>(a, workspace, ws_bytes, st);
+  if (rc != GODE_ERR_COOP) return rc;
+  return launch_dp5_fwd_k<16, 16, 1, kDp5Warps, false, GODE_TAB_DOPRI5, true>(a, workspace, ws_bytes, st);
 }
 
 int dopri5_small_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2,

@@ -105,6 +105,11 @@ int dopri5_small_fwd(const float* y0, const float* W1, const float* b1, const fl
                      float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
                      float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st,
                      const GodeWorld* world = nullptr);
+int dopri5_small_odernn_fwd(const float* h0, const float* eps, const float* W1, const float* b1, const float* W2,
+                            const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                            int B, int D, int H, int F, const GodeAdaptiveOpts* opts, float* codes, float* seg,
+                            unsigned char* logs, size_t log_stride, float* ckpt, double* acc, void* workspace,
+                            size_t ws_bytes, cudaStream_t st);
 // dopri5_adj_small.cu — torchdiffeq's continuous adjoint with the adaptive solver
 size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H);
 int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const float* W1, const float* b1, const float* W2,

@@ -10,51 +10,13 @@
 //   * the backward walks the frames in reverse: GRU VJP -> discrete adjoint of that frame's solve
 //     (dopri5_backprop_bwd_kernel over the frame's own device-side step log and checkpoints);
 //   * parameter gradients: one slot per frame, summed in frame order at the end (deterministic).
+#include <stdlib.h>
 #include "launch.h"
+#include "gru_cell.cuh"
 
 namespace gode {
 
 namespace {
-
-constexpr int GD = 16;             // dim_z_motion of the reference (models/mocogan.py:198: GRUCell(16, 16))
-constexpr int GT = 16;             // trajectories per tile
-constexpr int GP = 2 * 3 * GD * GD + 2 * 3 * GD;  // flat [w_ih (3D,D) | w_hh (3D,D) | b_ih (3D) | b_hh (3D)] = 1632
-
-constexpr int GS = GD + 1;         // padded row stride of the weights in shared memory (rows by lane: conflict-free)
-struct GruW {
-  float wih[3 * GD * GS], whh[3 * GD * GS], bih[3 * GD], bhh[3 * GD];
-};
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
-
-__device__ __forceinline__ void load_w(GruW& w, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
-                                       int tid, int n) {
-  for (int e = tid; e < 3 * GD * GD; e += n) { w.wih[(e / GD) * GS + e % GD] = w_ih[e]; w.whh[(e / GD) * GS + e % GD] = w_hh[e]; }
-  for (int e = tid; e < 3 * GD; e += n) { w.bih[e] = b_ih[e]; w.bhh[e] = b_hh[e]; }
-}
-
-// gates of unit j of trajectory t (x, h rows in shared memory)
-struct Gates { float r, z, n, hn; };
-__device__ __forceinline__ Gates gates(const GruW& w, const float* x, const float* h, int j) {
-  float ir = w.bih[j], iz = w.bih[GD + j], in = w.bih[2 * GD + j];
-  float hr = w.bhh[j], hz = w.bhh[GD + j], hn = w.bhh[2 * GD + j];
-#pragma unroll
-  for (int k = 0; k < GD; ++k) {
-    const float xv = x[k], hv = h[k];
-    ir = fmaf(w.wih[j * GS + k], xv, ir);
-    iz = fmaf(w.wih[(GD + j) * GS + k], xv, iz);
-    in = fmaf(w.wih[(2 * GD + j) * GS + k], xv, in);
-    hr = fmaf(w.whh[j * GS + k], hv, hr);
-    hz = fmaf(w.whh[(GD + j) * GS + k], hv, hz);
-    hn = fmaf(w.whh[(2 * GD + j) * GS + k], hv, hn);
-  }
-  Gates g;
-  g.r = sigmoidf_(ir + hr);
-  g.z = sigmoidf_(iz + hz);
-  g.hn = hn;
-  g.n = tanhf(in + g.r * hn);
-  return g;
-}
 
 // h_out = GRUCell(x, h); one thread per (trajectory, unit), 16 trajectories per 256-thread tile
 __global__ void __launch_bounds__(256) gru_jump_fwd_kernel(const float* __restrict__ x, const float* __restrict__ h,
@@ -209,6 +171,15 @@ int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* 
   const bool per_traj = opts->norm_scope == GODE_NORM_TRAJ;
   GodeAdaptiveOpts ot = *opts;
   ot.log_capacity = 0;  // per-trajectory mode keeps no per-attempt logs here
+  // batch-global control (torchdiffeq's): ONE persistent cooperative kernel runs all F (solve, jump) pairs
+  // (dopri5_small.cu::dopri5_fwd_kernel<..., RNN>).  GODE_ODERNN_PERFRAME=1 (developer switch) keeps the round-1 path:
+  // one solver launch + one jump launch per frame.
+  {
+    const char* pf = getenv("GODE_ODERNN_PERFRAME");
+    if (!per_traj && !(pf && pf[0] == '1'))
+      return dopri5_small_odernn_fwd(h0, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh, B, D, H, F, opts, codes, seg, logs, ls,
+                                     kc > 0 ? ckpt : nullptr, kc > 0 ? acc : nullptr, workspace, ws_bytes, st);
+  }
   for (int f = 0; f < F; ++f) {
     const float* y0 = f == 0 ? h0 : codes + (size_t)(f - 1) * bd;
     unsigned char* lg = logs + (size_t)f * ls;

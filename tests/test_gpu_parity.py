@@ -1593,3 +1593,35 @@ def test_bosh3_and_adaptive_heun_match_oracle(method, tol, B, scale):
         sol = gode.odeint_adjoint(clone_to(f, DEV), ya, _t16(), method=method, rtol=tol, atol=tol,
                                   options=dict(opts, adjoint="discrete"))
         assert torch.isfinite(torch.autograd.grad(sol.sum(), [ya])[0]).all()
+
+
+def test_odernn_persistent_forward_equals_the_per_frame_launches():
+    """Round 2: all F (solve -> GRU jump) pairs of the ODE-RNN sampler run in ONE persistent cooperative kernel
+    (dopri5_fwd_kernel<..., RNN>).  It must reproduce the round-1 path — one solver launch + one jump launch per frame,
+    kept behind GODE_ODERNN_PERFRAME=1 — bit for bit: codes, per-frame step logs, and the gradients computed from what it saved
+    (checkpoints for the recorded-step gradient, frame end points for the continuous adjoint)."""
+    _need_gpu()
+    import os
+    torch.manual_seed(12)
+    f = clone_to(make_field(seed=12, scale=2.0), DEV)
+    cell = torch.nn.GRUCell(16, 16).to(DEV)
+    params = list(f.parameters()) + list(cell.parameters())
+    for B, F in ((40, 6), (3000, 4), (8192, 3)):
+        h0 = torch.randn(B, 16, device=DEV, requires_grad=True)
+        eps = torch.randn(F, B, 16, device=DEV, requires_grad=True)
+        w = torch.randn(F, B, 16, device=DEV)
+        res = {}
+        for mode in ("discrete", "continuous"):
+            for perframe in ("0", "1"):
+                os.environ["GODE_ODERNN_PERFRAME"] = perframe
+                try:
+                    codes = gode.odernn_codes(f, cell, h0, eps, options={"adjoint": mode})
+                    logs = gode.odernn.last_log().frames()
+                    grads = torch.autograd.grad((codes * w).sum(), [h0, eps] + params)
+                finally:
+                    os.environ.pop("GODE_ODERNN_PERFRAME", None)
+                res[(mode, perframe)] = (codes.detach(), logs, grads)
+            a, b = res[(mode, "0")], res[(mode, "1")]
+            assert torch.equal(a[0], b[0]) and a[1] == b[1], (B, F, mode)
+            assert all(torch.equal(x, y) for x, y in zip(a[2], b[2])), (B, F, mode)
+            assert all(l["status"] == 0 and l["n_accepted"] >= 1 for l in a[1])
