@@ -280,6 +280,77 @@ def measure_extras(gode, dev):
     return out
 
 
+def measure_strong_scaling(gode, dev, rank, world):
+    """N > 1 side measurements, run by EVERY rank: BASELINE.json configs[2] (ODE-RNN sampler, B = 8192 TOTAL, 16 frames,
+    torchdiffeq default tolerances) and configs[4] (Euler-Maruyama, B = 16384 TOTAL, 41 steps, Philox keyed by the GLOBAL
+    trajectory index) sharded over the ranks — fixed total work, forward + backward, parameter gradients all-reduced.
+    CUDA events per step, barrier + synchronize on both sides, MAX over ranks."""
+    import torch.distributed as dist
+    from gan_ode_b200.dist import shard_bounds
+    from gan_ode_b200.fields import ODEFunc, SDEFunc
+    steps, warm = 10, 3
+    prev, prev_x = gode.config.grad_allreduce, gode.config.grad_exchange
+    if prev is None:
+        gode.config.grad_allreduce = True
+
+    def timed(fn):
+        for _ in range(warm):
+            fn()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in evs:
+            a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) / steps
+
+    out = {}
+    try:
+        torch.manual_seed(0)
+        ode_fn, gru = ODEFunc(16, 16).to(dev), torch.nn.GRUCell(16, 16).to(dev)
+        NB = 8192
+        lo, hi = shard_bounds(NB, rank, world)
+        g = torch.Generator().manual_seed(1)
+        h0 = torch.randn(NB, 16, generator=g)[lo:hi].to(dev)
+        eps = torch.randn(16, NB, 16, generator=g)[:, lo:hi].contiguous().to(dev)
+        w = torch.randn(16, NB, 16, generator=g)[:, lo:hi].contiguous().to(dev)
+        params = list(ode_fn.parameters()) + list(gru.parameters())
+
+        def rnn_step():
+            return torch.autograd.grad(gode.odernn_codes(ode_fn, gru, h0, eps), params, w)
+
+        ms = timed(rnn_step)
+        att = torch.tensor([sum(f["n_attempts"] for f in gode.odernn.last_log().frames())], device=dev)
+        dist.all_reduce(att, op=dist.ReduceOp.MAX)
+        out["configs2_odernn_B8192_total_16frames_default_tol_fwd_bwd"] = {
+            "scaling": "strong", "ms_per_step": ms, "attempted_steps_all_frames": int(att.item()),
+            "trajectory_steps_per_s": NB * int(att.item()) / ms * 1e3}
+
+        sde = SDEFunc(16, 16).to(dev)
+        NS = 16384
+        lo, hi = shard_bounds(NS, rank, world)
+        g = torch.Generator().manual_seed(2)
+        y0 = torch.randn(NS, 16, generator=g)[lo:hi].to(dev).requires_grad_(True)
+        gr = torch.randn(16, NS, 16, generator=g)[:, lo:hi].contiguous().to(dev)
+        ts = torch.linspace(0, 1, 16).float()
+        sp = list(sde.parameters())
+
+        def sde_step():
+            sol = gode.sdeint(sde, y0, ts, method="euler", dt=2.5e-2, bm=gode.PhiloxBrownian(1234, lo))
+            return torch.autograd.grad(sol, [y0] + sp, gr)
+
+        ms = timed(sde_step)
+        out["configs4_sde_em_B16384_total_41steps_philox_fwd_bwd"] = {
+            "scaling": "strong", "ms_per_step": ms, "trajectory_steps_per_s": NS * 41 / ms * 1e3}
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)[:200]
+    gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     import gan_ode_b200 as gode
@@ -291,6 +362,7 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     out_fd = 1
+    xchg_fallback = ""
     if world > 1:
         # stdout must carry exactly ONE JSON line (rank 0).  NCCL prints its version banner (and anything NCCL_DEBUG asks
         # for) on fd 1 from native code, so fd 1 is pointed at stderr for the whole run and the JSON line is written to
@@ -303,10 +375,13 @@ def run_gpu(args):
         from gan_ode_b200.dist import enable_fused_grad_exchange, enable_p2p_allreduce
         # parameter-gradient exchange, in order of preference: fused into the backward kernel's reduction tail over NVLink
         # peer memory; one-shot peer-memory kernel behind the backward; ncclAllReduce
-        fused = args.grad_exchange == "fused" and enable_fused_grad_exchange()
+        fused = args.grad_exchange == "fused" and enable_fused_grad_exchange(require=args.require_grad_exchange)
         if not fused:
-            p2p = args.grad_exchange != "nccl" and enable_p2p_allreduce()
+            xchg_fallback = getattr(fused, "why", "")
+            p2p = args.grad_exchange != "nccl" and enable_p2p_allreduce(
+                require=args.require_grad_exchange and args.grad_exchange == "p2p")
             if not p2p:
+                xchg_fallback = (xchg_fallback + " | " + getattr(p2p, "why", "")).strip(" |")
                 gode.config.grad_allreduce = True
     n_gpus = world
 
@@ -621,6 +696,9 @@ def run_gpu(args):
             torch.cuda.synchronize()
             os._exit(0)
 
+    strong = None
+    if world > 1 and not args.no_extras:
+        strong = measure_strong_scaling(gode, dev, rank, world)
     if rank != 0:
         finish()
         return
@@ -641,7 +719,7 @@ def run_gpu(args):
                "sample": "full workload (B=4096, {} attempted steps) x 7 timed steps, median {:.3f} s/step; "
                          "torchdiffeq-restatement oracle (PyTorch CPU)".format(na, sec)}
 
-    extras = None
+    extras = {"strong_scaling": strong} if strong is not None else None
     if n_gpus == 1 and not args.no_extras:
         try:
             extras = measure_extras(gode, dev)
@@ -679,7 +757,9 @@ def run_gpu(args):
                                    "fused into the backward kernel's reduction tail over NVLink peer memory "
                                    "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
                                    "one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
-                                   if callable(gode.config.grad_allreduce) else "ncclAllReduce")},
+                                   if callable(gode.config.grad_allreduce) else "ncclAllReduce"),
+                "grad_exchange_requested": args.grad_exchange if n_gpus > 1 else None,
+                "grad_exchange_fallback_reason": xchg_fallback or None},
         "parity_check": parity,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
@@ -704,6 +784,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--grad-exchange", choices=("fused", "p2p", "nccl"), default="fused",
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
+    ap.add_argument("--require-grad-exchange", action="store_true", help="N>1: fail instead of falling back when the "
+                    "requested peer-memory exchange cannot be set up")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "
                     "of the fused peer-memory kernel")
     ap.add_argument("--pdl", action="store_true", help="capture the backward as a programmatic dependent launch behind the "

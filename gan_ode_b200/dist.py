@@ -80,17 +80,33 @@ class P2PAllReduce:
         return flat
 
 
-def enable_p2p_allreduce(group=None, cap: int = 65536) -> bool:
-    """Route the parameter-gradient exchange through the fused peer-memory kernel instead of NCCL.  Returns False (and
-    leaves the NCCL path in place) if symmetric memory cannot be set up on this system."""
+class ExchangeMode(str):
+    """What an enable_* call selected ('p2p', 'fused', 'nccl', 'off').  Truthy exactly when the requested peer-memory
+    path is in place, so `if enable_…():` keeps working; compare or print it to see which path runs."""
+
+    def __new__(cls, mode: str, ok: bool, why: str = ""):
+        self = super().__new__(cls, mode)
+        self.ok, self.why = ok, why
+        return self
+
+    def __bool__(self):
+        return self.ok
+
+
+def enable_p2p_allreduce(group=None, cap: int = 65536, require: bool = False) -> ExchangeMode:
+    """Route the parameter-gradient exchange through the one-shot peer-memory kernel instead of NCCL.  Returns the mode
+    now in place: 'p2p' (truthy), or 'nccl' (falsy; NCCL stays) if symmetric memory cannot be set up on this system —
+    with require=True that case raises instead, so a caller that asked for peer memory never runs on NCCL unknowingly."""
     try:
         _api.config.grad_allreduce = P2PAllReduce(group, cap)
-        return True
+        return ExchangeMode("p2p", True)
     except Exception as e:  # noqa: BLE001
+        if require:
+            raise
         import sys
         sys.stderr.write("[gan_ode_b200] peer-memory all-reduce unavailable ({}); using NCCL\n".format(str(e)[:200]))
         _api.config.grad_allreduce = True if group is None else group
-        return False
+        return ExchangeMode("nccl", False, str(e)[:200])
 
 
 class WorldNorm:
@@ -169,16 +185,19 @@ class FusedGradExchange:
         return w
 
 
-def enable_fused_grad_exchange(group=None) -> bool:
+def enable_fused_grad_exchange(group=None, require: bool = False) -> ExchangeMode:
     """dopri5 backprop-through-solver: all-reduce the parameter gradient inside the backward kernel.  Other backward kernels
-    keep using config.grad_allreduce (set it as well).  Returns False if symmetric memory is unavailable."""
+    keep using config.grad_allreduce (set it as well).  Returns 'fused' (truthy) or 'off' (falsy: symmetric memory is
+    unavailable, config.grad_exchange stays None); require=True raises in the second case."""
     try:
         ex = FusedGradExchange(group)
         ex.struct(544)      # the reference shape: create its buffers now, outside any graph capture
         _api.config.grad_exchange = ex
-        return True
+        return ExchangeMode("fused", True)
     except Exception as e:  # noqa: BLE001
+        if require:
+            raise
         import sys
         sys.stderr.write("[gan_ode_b200] fused gradient exchange unavailable ({})\n".format(str(e)[:200]))
         _api.config.grad_exchange = None
-        return False
+        return ExchangeMode("off", False, str(e)[:200])
