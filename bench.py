@@ -15,9 +15,10 @@ value     inputs resident in HBM; the step (2 kernels; the grid-sync workspace i
           replayed from CUDA graphs, K steps back to back over 20 distinct resident batches (together larger than L2, so
           no flush kernel is needed and consecutive steps pipeline as in a training loop); one CUDA-event pair around the
           K steps.  The isolated-step time (flush + event pair per step) is reported as run.latency_ms_per_step.
-e2e       the same metric through the public API the reference calls (gan_ode_b200.odeint), eager, with the
-          batch's noise y0 in pinned HOST memory: H2D copy of y0 and D2H read of loss + parameter gradients are
-          inside the timed region, every step.
+e2e       the same metric through the public replay API (gan_ode_b200.GraphedSolvePipeline, two steps in flight) with the
+          batch's noise y0 in pinned HOST memory: H2D copy of y0, forward + backward and D2H read of the parameter
+          gradients are inside the timed region, every step; e2e.serial_* is one step at a time (GraphedSolveStep run +
+          sync), e2e.eager_api_* the plain eager odeint + autograd call the reference makes.
 roofline  dominant kernel, algorithmic HBM bytes / CUDA-event duration vs MEASURED_PEAKS.json.
 --impl reference   the CPU arm: the torchdiffeq-restatement oracle (the real torchdiffeq is neither vendored by the
           reference nor installable here) on all host threads, same config / metric / unit.
@@ -547,6 +548,7 @@ def run_gpu(args):
 
     y0_host = y0.cpu().pin_memory()
     n_param = sum(p.numel() for p in params)
+    e2e_serial_s = None
     e2e_api = "gan_ode_b200.GraphedSolveStep (H2D y0 + odeint fwd + backprop + D2H param grads, one graph launch, sync)"
     try:
         if args.no_graph:
@@ -563,6 +565,46 @@ def run_gpu(args):
         ref_flat = torch.cat([g.reshape(-1) for g in grads[1:]])
         assert torch.allclose(chk, ref_flat, rtol=1e-4, atol=1e-6), "graphed e2e step disagrees with the eager step"
         e2e_s = e2e_time(e2e_step, args.steps)
+        e2e_serial_s = e2e_s
+        # (a') the same step through GraphedSolvePipeline, two steps in flight: step i+1's H2D crosses PCIe while step i
+        #      computes; every step still has its own H2D and D2H and its result is read on the host before the step
+        #      after next is issued.
+        if not args.no_pipeline:
+            pipe = gode.GraphedSolvePipeline(f, B_PER_GPU, t, depth=2, adjoint=False, read_back=("param_grads",),
+                                             pdl=args.pdl, **kw)
+            for sl in pipe.slots:
+                sl.y0_host.copy_(y0_host)
+                sl.grad_traj.copy_(grad)
+            pipe.submit()
+            chk = pipe.result()["param_grads"].to(dev)
+            assert torch.allclose(chk, ref_flat, rtol=1e-4, atol=1e-6), "pipelined e2e step disagrees with the eager step"
+
+            def e2e_pipelined(k):
+                n_read = 0
+                for _ in range(k):
+                    if len(pipe._inflight) == len(pipe.slots):
+                        pipe.result()
+                        n_read += 1
+                    pipe.submit()
+                while pipe._inflight:
+                    pipe.result()
+                    n_read += 1
+                assert n_read == k
+
+            e2e_pipelined(6)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_pipelined(args.steps)
+            torch.cuda.synchronize()
+            te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            e2e_s = float(te.item())
+            e2e_api = ("gan_ode_b200.GraphedSolvePipeline, 2 steps in flight (per step: H2D y0 from pinned host, odeint fwd + "
+                       "backprop as one graph launch, D2H param grads, result read on the host; step i+1's H2D overlaps "
+                       "step i's kernels)")
     except Exception as e:  # noqa: BLE001
         sys.stderr.write("[bench] GraphedSolveStep unavailable ({}); e2e falls back to the eager API\n".format(str(e)[:200]))
         e2e_s = None
@@ -763,6 +805,9 @@ def run_gpu(args):
         "parity_check": parity,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
+                "serial_ms_per_step": (e2e_serial_s / args.steps * 1e3) if e2e_serial_s else None,
+                "serial_value": (units / (e2e_serial_s / args.steps)) if e2e_serial_s else None,
+                "serial_api": "gan_ode_b200.GraphedSolveStep.run() + .sync() per step (no overlap between steps)",
                 "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
         "gpu_launches": (2 + (1 if n_gpus > 1 and gode.config.grad_exchange is None and callable(gode.config.grad_allreduce)
                               else 0)) * args.steps,
@@ -784,6 +829,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--grad-exchange", choices=("fused", "p2p", "nccl"), default="fused",
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
+    ap.add_argument("--no-pipeline", action="store_true", help="e2e: one step at a time (GraphedSolveStep run + sync) "
+                    "instead of two steps in flight")
     ap.add_argument("--require-grad-exchange", action="store_true", help="N>1: fail instead of falling back when the "
                     "requested peer-memory exchange cannot be set up")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N>1: all-reduce the parameter gradient with NCCL instead "

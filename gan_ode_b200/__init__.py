@@ -7,7 +7,7 @@ or, without touching the reference files, `gan_ode_b200.install_shims()` registe
 """
 from .odeint import check_status, config, last_adjoint_log, last_step_log, odeint, odeint_adjoint, recognise_field  # noqa: F401
 from ._lib import GodeError  # noqa: F401
-from .graphed import GraphedSolveStep  # noqa: F401
+from .graphed import GraphedSolvePipeline, GraphedSolveStep  # noqa: F401
 from .sdeint import GridBrownian, PhiloxBrownian, TableBrownian, adjoint_grid, sdeint, sdeint_adjoint  # noqa: F401
 from .odernn import gru_jump, odernn_codes  # noqa: F401
 from .fused import FusedLatentSampler, fused_sample_z  # noqa: F401

@@ -23,7 +23,7 @@ import importlib
 
 _api = importlib.import_module(__package__ + ".odeint")  # the module, not the re-exported function
 
-__all__ = ["GraphedSolveStep"]
+__all__ = ["GraphedSolveStep", "GraphedSolvePipeline"]
 
 
 def _flat_param_grads(gs):
@@ -44,7 +44,8 @@ def _flat_param_grads(gs):
 class GraphedSolveStep:
     def __init__(self, func, batch: int, t: torch.Tensor, *, method: Optional[str] = None, rtol=1e-7, atol=1e-9,
                  adjoint: bool = True, options: Optional[dict] = None, device=None,
-                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = False):
+                 read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = False,
+                 copies_in_graph: bool = True):
         W1, _, _, _ = _api.recognise_field(func)
         D = W1.shape[1]
         dev = torch.device(device) if device is not None else W1.device
@@ -74,6 +75,8 @@ class GraphedSolveStep:
         self.traj = None
         self.grads = None
         self.log = None
+        self.copies_in_graph = bool(copies_in_graph)   # False: GraphedSolvePipeline issues the copies around the graph
+        self._d2h = []                                  # (pinned host buffer, device source) pairs of the last capture
 
         # In this graph the kernel right before the backward IS the matching forward (nothing in between writes the weights
         # or the upstream gradient), so the backward MAY be a programmatic dependent launch (config.pdl, `pdl=True`).  Off by
@@ -97,18 +100,31 @@ class GraphedSolveStep:
         self.stream = torch.cuda.current_stream(dev)
 
     def _body(self):
-        with torch.no_grad():
-            self.y0.copy_(self.y0_host, non_blocking=True)
+        if self.copies_in_graph:
+            self.copy_in()
         sol = self._solve(self.func, self.y0, self.t, **self._kw)
         self.log = _api.last_step_log() if (self._kw["method"] in (None, "dopri5")) else None
         grads = torch.autograd.grad(sol, [self.y0] + self.params, self.grad_traj)
         self.traj, self.grads = sol.detach(), grads
+        self._d2h = []
         if "param_grads" in self.host:
-            self.host["param_grads"].copy_(_flat_param_grads(grads[1:]), non_blocking=True)
+            self._d2h.append((self.host["param_grads"], _flat_param_grads(grads[1:])))
         if "grad_y0" in self.host:
-            self.host["grad_y0"].copy_(grads[0], non_blocking=True)
+            self._d2h.append((self.host["grad_y0"], grads[0]))
         if "traj" in self.host:
-            self.host["traj"].copy_(sol.detach(), non_blocking=True)
+            self._d2h.append((self.host["traj"], sol.detach()))
+        if self.copies_in_graph:
+            self.copy_out()
+
+    def copy_in(self):
+        """H2D of the pinned input on the current stream (a graph node when captured)."""
+        with torch.no_grad():
+            self.y0.copy_(self.y0_host, non_blocking=True)
+
+    def copy_out(self):
+        """D2H of the requested results on the current stream (graph nodes when captured)."""
+        for host, src in self._d2h:
+            host.copy_(src, non_blocking=True)
 
     def run(self, y0_host: Optional[torch.Tensor] = None):
         """Replay the step.  `y0_host` (optional) is copied into the pinned input buffer first; otherwise whatever the
@@ -123,3 +139,68 @@ class GraphedSolveStep:
         torch.cuda.current_stream(self.device).synchronize()
         _api.check_status()
         return self.host
+
+
+class GraphedSolvePipeline:
+    """`depth` GraphedSolveSteps in flight: while slot i computes, slot i+1's input is already crossing PCIe.
+
+        pipe = GraphedSolvePipeline(ode_fn, B, t, depth=2, method='dopri5', rtol=1e-5, atol=1e-5, adjoint=False)
+        for s in pipe.slots: s.grad_traj.copy_(upstream)
+        pipe.submit(y0_host)                 # H2D on the slot's stream -> wait for the previous slot's kernels -> graph
+        ...                                  #   (fwd + bwd, one cudaGraphLaunch) -> D2H on the slot's stream
+        out = pipe.result()                  # oldest step in flight: wait for ITS D2H only, status check, pinned buffers
+
+    Every step still does its own H2D and D2H; what changes against run() + sync() per step is that the host does not wait
+    for step i before it issues step i+1.  The solver kernels of consecutive slots are ordered by an event (they are
+    cooperative launches that want the whole GPU, and with the fused multi-GPU gradient exchange every rank must run them
+    in the same order); only the copies overlap them.  Results come back in submission order."""
+
+    def __init__(self, func, batch: int, t: torch.Tensor, *, depth: int = 2, **kw):
+        assert depth >= 1
+        kw.pop("copies_in_graph", None)
+        self.slots = [GraphedSolveStep(func, batch, t, copies_in_graph=False, **kw) for _ in range(depth)]
+        dev = self.slots[0].device
+        self.device = dev
+        self._streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self._computed = [torch.cuda.Event() for _ in range(depth)]   # the slot's kernels are done
+        self._done = [torch.cuda.Event() for _ in range(depth)]       # ... and its D2H copies
+        self._head, self._inflight, self._last = 0, [], None
+        for st in self._streams:
+            st.wait_stream(torch.cuda.current_stream(dev))
+
+    def next_input(self) -> torch.Tensor:
+        """The pinned input buffer the next submit() will send: write the batch there to save one host copy."""
+        return self.slots[self._head].y0_host
+
+    def submit(self, y0_host: Optional[torch.Tensor] = None) -> int:
+        if len(self._inflight) == len(self.slots):
+            raise RuntimeError("pipeline full: call result() before submitting another step")
+        i = self._head
+        slot, st = self.slots[i], self._streams[i]
+        if y0_host is not None:
+            slot.y0_host.copy_(y0_host)
+        with torch.cuda.stream(st):
+            slot.copy_in()
+            if self._last is not None and self._last != i:
+                st.wait_event(self._computed[self._last])
+            slot.graph.replay()
+            self._computed[i].record(st)
+            slot.copy_out()
+            self._done[i].record(st)
+        self._last = i
+        self._inflight.append(i)
+        self._head = (i + 1) % len(self.slots)
+        return i
+
+    def result(self):
+        """Block until the oldest submitted step has landed in its pinned buffers and return them."""
+        i = self._inflight.pop(0)
+        self._done[i].synchronize()
+        _api.check_status()
+        return self.slots[i].host
+
+    def drain(self):
+        out = None
+        while self._inflight:
+            out = self.result()
+        return out
