@@ -526,6 +526,54 @@ def run_gpu(args):
         total_ms, total_units = latency_ms, None
     eager_ms = timed_region(step, args.steps) if graph is not None else latency_ms
 
+    # N > 1: name what the step costs beyond N = 1.  The same K replays over the same batches with the gradient exchange
+    # taken out (every rank runs alone): the slowest rank's own rate is what lock-step exchange can reach at best (rank
+    # skew); the rest of the difference to the timed value is the exchange itself (NVLink store -> poll latency).
+    skew = None
+    if world > 1 and sets and not args.no_extras:
+        try:
+            prev, prev_x = gode.config.grad_allreduce, gode.config.grad_exchange
+            gode.config.grad_allreduce = gode.config.grad_exchange = None
+            alone = []
+            for (_, na_, _, yi, gri) in sets:
+                def step_a(yi=yi, gri=gri):
+                    return torch.autograd.grad(gode.odeint(f, yi, t, **kw), [yi] + params, gri)
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    step_a()
+                torch.cuda.current_stream().wait_stream(s_)
+                torch.cuda.synchronize()
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_):
+                    keep_a = step_a()
+                alone.append((g_, keep_a))
+            gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
+            for rep in range(2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier()
+                torch.cuda.synchronize()
+                a.record()
+                for j in range(args.steps):
+                    alone[j % len(alone)][0].replay()
+                b.record()
+                torch.cuda.synchronize()
+            mine = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            per_rank = [float(x.item()) for x in every]
+            skew = {"what": "same {} replays over the same batches WITHOUT the gradient exchange, every rank alone; "
+                            "ms per step".format(args.steps),
+                    "no_exchange_ms_per_step_per_rank": per_rank,
+                    "no_exchange_slowest_rank_ms": max(per_rank), "no_exchange_fastest_rank_ms": min(per_rank),
+                    "with_exchange_ms_per_step": total_ms / args.steps,
+                    "rank_skew_us": (max(per_rank) - min(per_rank)) * 1e3,
+                    "exchange_cost_over_slowest_rank_us": (total_ms / args.steps - max(per_rank)) * 1e3}
+            del alone
+        except Exception as e:  # noqa: BLE001
+            skew = {"error": str(e)[:200]}
+            gode.config.grad_allreduce, gode.config.grad_exchange = prev, prev_x
+
     # ---- e2e through the public API with host buffers -----------------------------------------------------------
     # (a) gan_ode_b200.GraphedSolveStep: the public replay API — H2D(y0 pinned) + fwd + bwd + D2H(param grads pinned)
     #     in one graph launch per step, then a stream sync so the host can read the result.
@@ -800,6 +848,7 @@ def run_gpu(args):
                                    "(gode_dopri5_backprop_bwd_world)" if gode.config.grad_exchange is not None else
                                    "one-shot kernel over NVLink peer memory (csrc/p2p_allreduce.cu)"
                                    if callable(gode.config.grad_allreduce) else "ncclAllReduce"),
+                "multi_gpu_step_cost": skew,
                 "grad_exchange_requested": args.grad_exchange if n_gpus > 1 else None,
                 "grad_exchange_fallback_reason": xchg_fallback or None},
         "parity_check": parity,

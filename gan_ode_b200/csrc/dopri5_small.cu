@@ -439,6 +439,18 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   SyncState ss;
   ss.begin(p.ws.gs);
   const int n4 = p.T * (S::G * D / 4);   // float4 elements of one trajectory group's upstream gradients
+  // float4 e: output time e / (G*D/4), trajectory, 4 components.  Asynchronous global -> shared copies (no registers, all in
+  // flight at once); rows past the batch are zero-filled.  The first group's copies are issued before the weight loads.
+  auto stage_grads = [&](int base) {
+    for (int e = lane; e < n4; e += 32) {
+      const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
+      const bool in = base + gg < p.B;
+      const float* src = in ? p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4 : p.grad_traj;
+      cp_async16(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4, src, in);
+    }
+  };
+  const int base_first = (blockIdx.x * WARPS + warp) * S::G;
+  if (staged && base_first < p.B) stage_grads(base_first);
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
@@ -465,29 +477,13 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
     for (int c = 0; c < S::DL; ++c) { ybar[c] = poison; fbar[c] = 0.f; }
     int iout = p.T - 1;
     if (staged) {
-      __syncwarp();
-      // float4 e: output time e / (G*D/4), trajectory, 4 components; eight loads in flight per lane before any store
-      for (int e0 = lane; e0 < n4; e0 += 8 * 32) {
-        float4 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = e0 + 32 * q;
-          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-          v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (e < n4 && base + gg < p.B)
-            v[q] = __ldg(reinterpret_cast<const float4*>(p.grad_traj + toff(p.layout, so, base + gg, p.B, p.T, D) + 4 * q4));
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int e = e0 + 32 * q;
-          const int so = e / (S::G * D / 4), r = e % (S::G * D / 4), gg = r / (D / 4), q4 = r % (D / 4);
-          if (e < n4) *reinterpret_cast<float4*>(my_gr + (size_t)so * (S::G * D) + gg * D + 4 * q4) = v[q];
-        }
+      if (base != base_first) {
+        __syncwarp();
+        stage_grads(base);
       }
-      __syncwarp();
     }
-    GODE_TP(1, 4);
-    // checkpoint and step table of the step about to be replayed are fetched one step ahead
+    // checkpoint and step table of the step about to be replayed are fetched one step ahead; the first fetch is issued
+    // before waiting for the staged gradients so that the two cold reads overlap
     float y0n[S::DL];
     double t0n = 0.0, dtn = 0.0;
 #pragma unroll
@@ -496,6 +492,11 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       t0n = p.acc_t0[n_acc - 1]; dtn = p.acc_dt[n_acc - 1];
       if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(n_acc - 1) * p.B + b) * D + l * S::DL, y0n);
     }
+    if (staged) {
+      cp_async_wait_all();
+      __syncwarp();
+    }
+    GODE_TP(1, 4);
     for (int s = n_acc - 1; s >= 0; --s) {
       GODE_TP(1, 5 + 2 * min(s, 8));
       const double t0 = t0n, dtd = dtn, t1 = t0 + dtd;
