@@ -65,6 +65,7 @@ _SIGS = {
     "gode_rk4_adjoint_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_rk4_backprop_bwd": (_I, [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_dopri5_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "gode_dopri5_backprop_workspace_bytes": (C.c_size_t, [_I, _I, _I, _I]),
     "gode_dopri5_fwd": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 + [C.c_size_t, _P]),
     "gode_dopri5_fwd_world": (_I, [_P] * 5 + [_P, _I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts), _I] + [_P] * 10 +
                               [C.c_size_t, C.POINTER(GodeWorld), _P]),

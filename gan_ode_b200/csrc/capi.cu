@@ -209,8 +209,14 @@ int gode_rk4_bwd_world(int adjoint, const float* traj, const float* grad_traj, c
 }
 
 size_t gode_dopri5_workspace_bytes(int B, int D, int H) {
+  if (wide_shape(D, H)) return wide_dopri5_workspace_bytes(B, D, H, 0, 0);
   const size_t a = dopri5_small_workspace_bytes(B, D, H), b = bwd_workspace_bytes(gode_param_count(D, H));
   return a > b ? a : b;
+}
+
+size_t gode_dopri5_backprop_workspace_bytes(int B, int D, int H, int ckpt_capacity) {
+  if (wide_shape(D, H)) return wide_dopri5_workspace_bytes(B, D, H, ckpt_capacity, 1);
+  return gode_dopri5_workspace_bytes(B, D, H);
 }
 
 int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
@@ -225,6 +231,9 @@ int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const flo
   if (opts->norm_scope != GODE_NORM_BATCH) return GODE_ERR_ARG;
   for (int i = 1; i < T; ++i)
     if (!(t_host[i] > t_host[i - 1])) return GODE_ERR_ARG;
+  if (wide_shape(D, H))
+    return wide_dopri5_fwd(y0, W1, b1, W2, b2, t_host, B, D, H, T, opts, out_layout, traj, log, att_t0, att_dt, att_er,
+                           att_acc, ckpt, acc_t0, acc_dt, workspace, ws_bytes, (cudaStream_t)stream);
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return dopri5_small_fwd(y0, W1, b1, W2, b2, t_host, B, D, H, T, opts, out_layout, traj, log, att_t0, att_dt, att_er,
                           att_acc, ckpt, acc_t0, acc_dt, workspace, ws_bytes, (cudaStream_t)stream);
@@ -258,6 +267,9 @@ int gode_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const floa
   if (bad_common(grad_traj, W1, b1, W2, b2, B, T, layout) || !t_host || !log || !ckpt || !acc_t0 || !acc_dt ||
       ckpt_capacity <= 0 || !grad_y0 || !grad_params || !workspace)
     return GODE_ERR_ARG;
+  if (wide_shape(D, H))
+    return wide_dopri5_backprop_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, ckpt, acc_t0, acc_dt,
+                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);
   if (!small_field_shape(D, H)) return GODE_ERR_SHAPE;
   return dopri5_small_backprop_bwd(grad_traj, W1, b1, W2, b2, t_host, B, D, H, T, layout, log, ckpt, acc_t0, acc_dt,
                                    ckpt_capacity, fsign, grad_y0, grad_params, workspace, ws_bytes, (cudaStream_t)stream);

@@ -165,6 +165,17 @@ int wide_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float
                           const float* b2, const float* dt, int dt_on_device, int B, int D, int H, int T, int layout,
                           float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+// wide_dopri5.cu: dopri5 with the batch-global controller for the wide shapes (any batch size: state in global memory)
+size_t wide_dopri5_workspace_bytes(int B, int D, int H, int ckpt_capacity, int backward);
+int wide_dopri5_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
+                    const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts, int out_layout,
+                    float* traj, GodeStepLog* log, double* att_t0, double* att_dt, float* att_er, uint8_t* att_acc,
+                    float* ckpt, double* acc_t0, double* acc_dt, void* workspace, size_t ws_bytes, cudaStream_t st);
+int wide_dopri5_backprop_bwd(const float* grad_traj, const float* W1, const float* b1, const float* W2, const float* b2,
+                             const double* t_host, int B, int D, int H, int T, int layout, const GodeStepLog* log,
+                             const float* ckpt, const double* acc_t0, const double* acc_dt, int ckpt_capacity, float fsign,
+                             float* grad_y0, float* grad_params, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 inline bool small_field_shape(int D, int H) { return D == 16 && H == 16; }
 int tc_rk4_fwd_wide(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2, const float* dt,
                     int dt_on_device, int B, int D, int H, int T, int out_layout, float* traj, cudaStream_t st);

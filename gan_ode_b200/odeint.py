@@ -761,7 +761,7 @@ class _Dopri5(torch.autograd.Function):
         g = _grad_in_layout(grad_traj, meta["layout"])
         grad_y0 = torch.empty((B, D), dtype=torch.float32, device=ckpt.device)
         grad_p = torch.empty(L.gode_param_count(D, H), dtype=torch.float32, device=ckpt.device)
-        ws_bytes = L.gode_dopri5_workspace_bytes(B, D, H)
+        ws_bytes = L.gode_dopri5_backprop_workspace_bytes(B, D, H, kc)   # wide fields: + the gradient rows of kc steps
         ws = _workspace(ckpt.device, ws_bytes)
         args = (_ptr(g), _ptr(W1c), _ptr(b1c), _ptr(W2c), _ptr(b2c), ctx.tarr.ctypes.data, B, D, H, T,
                 meta["layout"], raw.data_ptr(), _ptr(ckpt), _ptr(acc), acc.data_ptr() + 8 * kc, kc,
@@ -1184,8 +1184,10 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         return dispatch("rk4", _Rk4, meta, dt)
 
     if method in _lib.TABLEAUS:     # dopri5 (torchdiffeq's default) and, SURVEY §8 f4, bosh3 / adaptive_heun on the same kernels
-        if not (D == 16 and H == 16):
-            raise NotImplementedError("the fused adaptive kernels exist for the reference shape D=H=16 only")
+        wide = not (D == 16 and H == 16)   # csrc/wide_dopri5.cu: one warp per trajectory, state in global memory, any batch
+        if wide and method != "dopri5":
+            raise NotImplementedError('method "{}" exists for the reference shape D=H=16 only (the wide fields have rk4 and '
+                                      'dopri5)'.format(method))
         if prec != _lib.PREC["fp32"]:
             raise NotImplementedError("adaptive solvers run in fp32 only: the error estimate is below tf32/bf16 resolution")
         # odeint_adjoint + dopri5 (the ODE-RNN call, models/mocogan_ode_rnn.py:47-48): by default torchdiffeq's continuous
@@ -1200,6 +1202,13 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         meta["traj_log_capacity"] = int(options.get("traj_log_capacity", 0))  # per-attempt logs per trajectory (tests)
         meta["keep_ckpt"] = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in (W1, b1, W2, b2)))
         other = method != "dopri5"
+        if wide:
+            if meta["opts"].norm_scope == _lib.NORM_TRAJ or options.get("norm") == "world":
+                raise NotImplementedError("wide fields: dopri5 with torchdiffeq's batch-global norm only")
+            if adjoint and options.get("adjoint", config.dopri5_adjoint) == "continuous" and meta["keep_ckpt"]:
+                raise NotImplementedError("wide fields: the continuous dopri5 adjoint re-solve is not built; pass "
+                                          "options={'adjoint': 'discrete'} (gradient of the recorded steps) or use odeint")
+            return _Dopri5.apply(y0, meta, W1, b1, W2, b2)
         if meta["opts"].norm_scope == _lib.NORM_TRAJ:
             if other:
                 raise NotImplementedError("per-trajectory step control exists for dopri5 only")

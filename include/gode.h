@@ -182,8 +182,14 @@ int gode_rk4_backprop_bwd(const float* traj, const float* grad_traj, const float
  * opts->log_capacity entries (may be NULL when log_capacity==0).
  * ckpt: (ckpt_capacity,B,D) state at the START of each accepted step, for backprop (NULL if capacity 0).
  * acc_t0/acc_dt: (ckpt_capacity) doubles, (t0,dt) of each accepted step.
- * workspace: gode_dopri5_workspace_bytes(B,D,H) bytes. */
+ * workspace: gode_dopri5_workspace_bytes(B,D,H) bytes.
+ * Shapes: the reference's D = H = 16 (lane-split kernels, every trajectory in registers, batch co-resident) and the wide
+ * fields D=64/H=256, D=32/H=32, D=32/H=64 (csrc/wide_dopri5.cu: one warp per trajectory, the state between attempts in global
+ * memory behind the sync region of the workspace, any batch size; dopri5 tableau only). */
 size_t gode_dopri5_workspace_bytes(int B, int D, int H);
+/* workspace of gode_dopri5_backprop_bwd: equal to the above for D = H = 16; for the wide fields it also holds the per-(step,
+ * trajectory, stage) gradient rows of up to ckpt_capacity recorded steps, B * ckpt_capacity * 7 * (2D + 2H) floats. */
+size_t gode_dopri5_backprop_workspace_bytes(int B, int D, int H, int ckpt_capacity);
 int gode_dopri5_fwd(const float* y0, const float* W1, const float* b1, const float* W2, const float* b2,
                     const double* t_host, int B, int D, int H, int T, const GodeAdaptiveOpts* opts,
                     int out_layout, float* traj, GodeStepLog* log, double* att_t0, double* att_dt,
