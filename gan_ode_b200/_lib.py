@@ -17,6 +17,7 @@ PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
 LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
 MAX_HOST_STEPS = 255
+ADAPTIVE_MAX_T, SDE_MAX_STEPS, SDE_MAX_FRAMES, SDE_MAX_CELLS, SDE_MAX_REV_STEPS = 256, 320, 64, 768, 384   # include/gode.h
 SYNC_REGION_BYTES = 256 * 1024   # include/gode.h GODE_SYNC_REGION_BYTES
 LAUNCH_PDL_BWD = 1
 
@@ -85,7 +86,7 @@ _SIGS = {
     "gode_odernn_log_stride": (C.c_size_t, [_I]),
     "gode_odernn_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "gode_odernn_fwd": (_I, [_P] * 10 + [_I, _I, _I, _I, C.POINTER(GodeAdaptiveOpts)] + [_P] * 7 + [C.c_size_t, _P]),
-    "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 12 + [C.c_size_t, _P]),
+    "gode_odernn_bwd": (_I, [_P] * 10 + [_I, _I, _I, _I, _I, _I] + [_P] * 6 + [_I] + [_P] * 6 + [C.c_size_t, _P]),
     "gode_fixed_fwd": (_I, [_I] + [_P] * 5 + [_P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "gode_fixed_adjoint_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),
     "gode_fixed_backprop_bwd": (_I, [_I] + [_P] * 6 + [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, C.c_size_t, _P]),

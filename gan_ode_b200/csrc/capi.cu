@@ -48,7 +48,10 @@ const char* gode_strerror(int code) {
     case GODE_OK: return "ok";
     case GODE_ERR_SHAPE: return "no kernel compiled for this (D, H) at this precision";
     case GODE_ERR_ARG: return "invalid argument (null pointer, B <= 0, T < 2, bad layout)";
-    case GODE_ERR_T_TOO_LONG: return "host dt table longer than GODE_MAX_HOST_STEPS; pass dt on the device";
+    case GODE_ERR_T_TOO_LONG:
+      return "a time / step table exceeds its launch-parameter limit (include/gode.h: GODE_MAX_HOST_STEPS for a host dt table "
+             "of the fixed-grid solvers — pass dt on the device instead; GODE_ADAPTIVE_MAX_T output times; GODE_SDE_MAX_* "
+             "steps / frames / cells / reverse steps)";
     case GODE_ERR_WORKSPACE: return "workspace too small";
     case GODE_ERR_COOP: return "batch-global adaptive solve needs every CTA co-resident: batch too large";
     case GODE_ERR_PRECISION: return "precision mode not available for this entry point";
@@ -462,15 +465,17 @@ int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, 
                     const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
                     int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
                     const float* ckpt, const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts,
-                    float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
-                    size_t ws_bytes, gode_stream_t stream) {
+                    int adjoint_param_mask, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru,
+                    float* scratch, void* workspace, size_t ws_bytes, gode_stream_t stream) {
   if (!grad_codes || !eps || !W1 || !b1 || !W2 || !b2 || !w_ih || !w_hh || !b_ih || !b_hh || !seg || !grad_h0 ||
       !grad_ode || !grad_gru || !scratch || !workspace || B <= 0 || F < 1)
     return GODE_ERR_ARG;
   if (!adjoint_opts && (!logs || !ckpt || !acc || ckpt_capacity <= 0)) return GODE_ERR_ARG;
+  if (adjoint_opts && (adjoint_param_mask < 0 || adjoint_param_mask > 15)) return GODE_ERR_ARG;
   return odernn_bwd(grad_codes, eps, W1, b1, W2, b2, w_ih, w_hh, b_ih, b_hh, B, D, H, F, ckpt_capacity, seg,
                     reinterpret_cast<const unsigned char*>(logs), odernn_log_stride(log_capacity), ckpt, acc, n_acc,
-                    adjoint_opts, grad_h0, grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes, (cudaStream_t)stream);
+                    adjoint_opts, adjoint_param_mask, grad_h0, grad_eps, grad_ode, grad_gru, scratch, workspace, ws_bytes,
+                    (cudaStream_t)stream);
 }
 
 int gode_allreduce_p2p(float* data, int n, void* const* bufs_dev, void* const* pads_dev, int rank, int world, int cap,

@@ -30,7 +30,7 @@ extern "C" int gode_debug_trace_read(unsigned long long* host_out) {
 
 namespace gode {
 
-constexpr int kMaxT = 256;  // output times passed by value
+constexpr int kMaxT = GODE_ADAPTIVE_MAX_T;  // output times passed by value
 constexpr int kDp5StageT = 32;  // output grids up to this length have their upstream gradients staged in shared memory
 
 struct Dp5Args {

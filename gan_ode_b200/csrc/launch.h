@@ -197,8 +197,9 @@ int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* 
 int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
                int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
-               const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts, float* grad_h0, float* grad_eps,
-               float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, cudaStream_t st);
+               const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts, int adjoint_param_mask,
+               float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
+               size_t ws_bytes, cudaStream_t st);
 int p2p_allreduce(float* data, int n, float* const* bufs_dev, unsigned int* const* pads_dev, int rank, int world, int cap,
                   unsigned int* epoch_ctr, cudaStream_t st);
 size_t tc_rk4_adj_small_workspace_bytes(int B);

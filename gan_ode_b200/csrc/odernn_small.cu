@@ -213,8 +213,9 @@ int odernn_fwd(const float* h0, const float* eps, const float* W1, const float* 
 int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2, const float* b2,
                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B, int D, int H, int F,
                int ckpt_capacity, const float* seg, const unsigned char* logs, size_t log_stride, const float* ckpt,
-               const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts, float* grad_h0, float* grad_eps,
-               float* grad_ode, float* grad_gru, float* scratch, void* workspace, size_t ws_bytes, cudaStream_t st) {
+               const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts, int adjoint_param_mask,
+               float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
+               size_t ws_bytes, cudaStream_t st) {
   if (D != GD || !small_field_shape(D, H)) return GODE_ERR_SHAPE;
   const double t01[2] = {0.0, 1.0};
   const int P1 = H * D + H + D * H + D, kc = ckpt_capacity;
@@ -234,7 +235,7 @@ int odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const
     if (rc) return rc;
     const unsigned char* lg = logs + (size_t)f * log_stride;
     if (adjoint_opts) {  // torchdiffeq's continuous adjoint of this frame's solve (dopri5_adj_small.cu); needs no checkpoints
-      rc = dopri5_small_adjoint_bwd(tr, gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD, adjoint_opts, 15,
+      rc = dopri5_small_adjoint_bwd(tr, gtraj, W1, b1, W2, b2, t01, B, D, H, 2, GODE_LAYOUT_TBD, adjoint_opts, adjoint_param_mask,
                                     f == 0 ? grad_h0 : carry, slots + (size_t)f * P1, nullptr, nullptr, nullptr, nullptr,
                                     workspace, dp_ws, st);
       if (rc) return rc;

@@ -17,8 +17,8 @@
 
 namespace gode {
 
-constexpr int kSdeMaxSteps = 320;
-constexpr int kSdeMaxT = 64;
+constexpr int kSdeMaxSteps = GODE_SDE_MAX_STEPS;
+constexpr int kSdeMaxT = GODE_SDE_MAX_FRAMES;
 
 struct SdeArgs {
   const float *y0, *fW1, *fb1, *fW2, *fb2, *gW1, *gb1, *gW2, *gb2;
@@ -64,8 +64,8 @@ __device__ __forceinline__ void brownian(const SdeArgs& p, int b, bool valid, in
 // N(0, len_r) increment — Philox counter (global trajectory, cell, d_block, stream = 1) or row r of a caller's (R,B,D)
 // table — and the increment of any step is the left-to-right fp32 sum of the cells it covers.  Forward and backward regenerate
 // the same cells from the same counters: nothing is stored, and the result does not depend on how the batch is sharded.
-constexpr int kSdeMaxCells = 768;
-constexpr int kSdeMaxRev = 384;
+constexpr int kSdeMaxCells = GODE_SDE_MAX_CELLS;
+constexpr int kSdeMaxRev = GODE_SDE_MAX_REV_STEPS;
 
 struct SdeCellArgs {
   int R;                             // number of cells

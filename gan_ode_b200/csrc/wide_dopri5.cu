@@ -26,7 +26,7 @@
 
 namespace gode {
 
-constexpr int kWideMaxT = 256;   // output times passed by value
+constexpr int kWideMaxT = GODE_ADAPTIVE_MAX_T;   // output times passed by value
 constexpr int kWideKS = 1024;    // rows per split-K slice of the gradient contraction
 
 struct WideDp5Args {

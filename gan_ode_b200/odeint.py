@@ -85,20 +85,60 @@ def _nvtx(name):
 
 
 # ------------------------------------------------------------------------------------------------------------
+_FORWARD_OK = set()   # types whose call has been probed: obj(t, y) == obj.<mlp>(y) for two values of t
+
+
+def _has_hooks(*mods):
+    for m in mods:
+        if getattr(m, "_forward_hooks", None) or getattr(m, "_forward_pre_hooks", None):
+            return True
+    return False
+
+
+def verify_call_is_mlp(obj, calls, what):
+    """The kernels integrate the MLPs found by STRUCTURE; this checks that the object's own call really is that MLP and
+    nothing more (a forward that is time-dependent, negated, scaled or residual around self.fn would otherwise be solved as
+    self.fn(x) without an error).  `calls`: [(callable(t, y), mlp module)].  Forward hooks are rejected on every call; the
+    numeric probe — two values of t on a fixed 3-row batch, bit-exact comparison, no RNG consumed — runs once per type."""
+    mods = [m for _, m in calls]
+    if _has_hooks(obj, *mods) or any(_has_hooks(*m._modules.values()) for m in mods):
+        raise NotImplementedError("{} has forward hooks registered; the fused kernels would not run them".format(what))
+    tp = type(obj)
+    if tp in _FORWARD_OK:
+        return
+    w = calls[0][1][0].weight
+    if w.is_cuda and torch.cuda.is_current_stream_capturing():
+        return   # cannot synchronise inside a capture: probed at the next eager call
+    with torch.no_grad():
+        y = torch.linspace(-1.0, 1.0, 3 * w.shape[1], dtype=torch.float32).view(3, w.shape[1]).to(device=w.device, dtype=w.dtype)
+        for call, mlp in calls:
+            ref = mlp(y)
+            for tv in (0.0, 0.73):
+                out = call(torch.tensor(tv, dtype=w.dtype).to(w.device), y)
+                if not (torch.is_tensor(out) and out.shape == ref.shape and torch.equal(out, ref)):
+                    raise NotImplementedError(
+                        "{}: calling it does not return its Linear-Tanh-Linear stack applied to x (time-dependent, scaled or "
+                        "residual forward?); gan_ode_b200 fuses the solver with the reference's field only, there is no "
+                        "generic fallback".format(what))
+    _FORWARD_OK.add(tp)
+
+
 def recognise_field(func):
-    """Return (W1, b1, W2, b2) if `func` is the reference's ODEFunc structure, else raise NotImplementedError."""
+    """Return (W1, b1, W2, b2) if `func` is the reference's ODEFunc — structure AND forward — else raise NotImplementedError."""
     fn = getattr(func, "fn", None)
     mods = getattr(fn, "_modules", None) if type(fn) is nn.Sequential else None   # fast path: no Sequential.__getitem__
     if mods is not None and len(mods) == 3:
         l0, act, l2 = mods.get("0"), mods.get("1"), mods.get("2")
         if (type(l0) is nn.Linear and type(act) is nn.Tanh and type(l2) is nn.Linear and l0.bias is not None
                 and l2.bias is not None and l0.out_features == l2.in_features and l0.in_features == l2.out_features):
+            verify_call_is_mlp(func, [(func, fn)], "func ({})".format(type(func).__name__))
             return l0.weight, l0.bias, l2.weight, l2.bias
     if mods is not None and len(mods) == 2:
         # models/mocogan_mnist.py:6-16: f(x) = tanh(W x + b).  Runs on the same kernels as W2 tanh(W1 x + b1) + b2 with
         # W2 = I, b2 = 0 — bit-exact in fp32 (sum of h_d and exact zeros); the two constants take no gradient.
         l0, act = mods.get("0"), mods.get("1")
         if (type(l0) is nn.Linear and type(act) is nn.Tanh and l0.bias is not None and l0.in_features == l0.out_features):
+            verify_call_is_mlp(func, [(func, fn)], "func ({})".format(type(func).__name__))
             return (l0.weight, l0.bias) + _identity_layer(l0.in_features, l0.weight.device)
     ok = (isinstance(fn, nn.Sequential) and len(fn) == 3 and isinstance(fn[0], nn.Linear)
           and isinstance(fn[1], nn.Tanh) and isinstance(fn[2], nn.Linear)
@@ -110,6 +150,7 @@ def recognise_field(func):
             "nn.Sequential(nn.Linear(D,H), nn.Tanh(), nn.Linear(H,D)) — or nn.Sequential(nn.Linear(D,D), nn.Tanh()), "
             "models/mocogan_mnist.py:6-16; got {!r}. There is no generic fallback."
             .format(type(func).__name__))
+    verify_call_is_mlp(func, [(func, fn)], "func ({})".format(type(func).__name__))
     return fn[0].weight, fn[0].bias, fn[2].weight, fn[2].bias
 
 
@@ -1195,6 +1236,9 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         # differentiates the recorded accepted steps (gode_dopri5_backprop_bwd): one replay, no second adaptive solve, any
         # batch the forward holds; the two gradients agree to O(tolerance).
         # torchdiffeq: t -> float64 for adaptive solvers; the grid rides in the launch parameters (syncs iff t is on GPU)
+        if len(t) > _lib.ADAPTIVE_MAX_T:
+            raise NotImplementedError("the adaptive kernels take at most {} output times (they travel in the launch "
+                                      "parameters); got {} — split t".format(_lib.ADAPTIVE_MAX_T, len(t)))
         t64, _, fsign = _host_steps(t.cpu() if t.is_cuda else t)
         meta["opts"] = _adaptive_opts(rtol, atol, options, fsign)
         meta["opts"].tableau = _lib.TABLEAUS[method]
@@ -1212,6 +1256,11 @@ def _solve_on_device(func, y0, t, rtol, atol, method, options, adjoint, adj, wei
         if meta["opts"].norm_scope == _lib.NORM_TRAJ:
             if other:
                 raise NotImplementedError("per-trajectory step control exists for dopri5 only")
+            if adjoint and meta["keep_ckpt"] and (adj is not None or options.get("adjoint", config.dopri5_adjoint) == "continuous"):
+                # (silently handing back the recorded-step gradient would ignore adjoint_rtol / adjoint_atol / adjoint_options)
+                raise NotImplementedError("odeint_adjoint with options['norm']='trajectory': the continuous adjoint re-solve uses "
+                                          "torchdiffeq's batch-global norm; pass options={'adjoint': 'discrete'} (gradient of "
+                                          "the recorded per-trajectory steps, no adjoint_* arguments) or use odeint")
             return dispatch("dopri5_traj", _Dopri5Traj, meta)
         mode = options.get("adjoint", config.dopri5_adjoint)
         if other:

@@ -147,7 +147,7 @@ class _OdeRnn(torch.autograd.Function):
         _lib.check(L.gode_odernn_bwd(g.data_ptr(), eps.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                      w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), B, D, H, F,
                                      o.log_capacity, ctx.kc, seg.data_ptr(), logs.data_ptr(), _ptr(ckpt), _ptr(acc),
-                                     _ptr(n_acc), C.byref(ao) if ao is not None else None, gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
+                                     _ptr(n_acc), C.byref(ao) if ao is not None else None, ctx.meta["param_mask"], gh0.data_ptr(), _ptr(geps), gode_.data_ptr(), ggru.data_ptr(), scratch.data_ptr(),
                                      ws.data_ptr(), wsb, _stream()), "gode_odernn_bwd")
         from .odeint import _maybe_allreduce
         _maybe_allreduce(gode_)
@@ -181,6 +181,9 @@ def odernn_codes(ode_fn, gru_cell, h0, eps, *, rtol=1e-7, atol=1e-9, options=Non
         if o.norm_scope != _lib.NORM_BATCH:
             raise NotImplementedError("the continuous adjoint uses torchdiffeq's batch-global norm")
         adj = _adaptive_opts(rtol, atol, {k: v for k, v in options.items() if k != "norm"}, 1.0)
-    meta = dict(opts=o, keep=keep, adj_opts=adj)
+    # adjoint.py: adjoint_params = the parameters with requires_grad; only those are in the augmented state and its norm (the
+    # single-layer field's W2 = I, b2 = 0 are constants, frozen parameters drop out) — as odeint_adjoint derives it
+    mask = sum(1 << k for k, q in enumerate((W1, b1, W2, b2)) if q.requires_grad)
+    meta = dict(opts=o, keep=keep, adj_opts=adj, param_mask=mask)
     with _api._on_device(h0.device):
         return _OdeRnn.apply(h0, eps, meta, W1, b1, W2, b2, *gp)

@@ -67,7 +67,7 @@ enum {
   GODE_OK = 0,
   GODE_ERR_SHAPE = -1,       /* (D,H) has no compiled kernel for this precision            */
   GODE_ERR_ARG = -2,         /* null pointer, B<=0, T<2 ...                                */
-  GODE_ERR_T_TOO_LONG = -3,  /* host-side dt table longer than GODE_MAX_HOST_STEPS         */
+  GODE_ERR_T_TOO_LONG = -3,  /* a time / step table exceeds its launch-parameter limit (below) */
   GODE_ERR_WORKSPACE = -4,   /* workspace smaller than gode_*_workspace_bytes()            */
   GODE_ERR_COOP = -5,        /* batch-global dopri5 needs all CTAs co-resident; B too big  */
   GODE_ERR_PRECISION = -6    /* precision mode not available for this entry point          */
@@ -91,6 +91,12 @@ enum {
 };
 
 #define GODE_MAX_HOST_STEPS 255
+/* other tables that travel in the launch parameters (exceeding one returns GODE_ERR_T_TOO_LONG) */
+#define GODE_ADAPTIVE_MAX_T 256    /* output times of gode_dopri5_* / gode_adaptive_*                                 */
+#define GODE_SDE_MAX_STEPS 320     /* Euler–Maruyama steps of one gode_sde_* solve (the reference: 41)                 */
+#define GODE_SDE_MAX_FRAMES 64     /* output frames of one gode_sde_* solve (the reference: 16)                        */
+#define GODE_SDE_MAX_CELLS 768     /* Brownian cells = distinct forward + reverse step end points (gode_sde_em_fwd_cells) */
+#define GODE_SDE_MAX_REV_STEPS 384 /* reverse steps of gode_sde_adjoint_bwd (the reference: 45)                        */
 #define GODE_SYNC_REGION_BYTES (256 * 1024) /* persistent grid-sync region at the front of every workspace */
 
 /* per-thread launch flags (gode_set_thread_launch_flags) */
@@ -409,12 +415,15 @@ int gode_odernn_fwd(const float* h0, const float* eps, const float* W1, const fl
  * grad_eps may be NULL.  grad_ode ([W1|b1|W2|b2]) and grad_gru are OVERWRITTEN (per-frame slots summed in frame order).
  * scratch: (3*B*D + F*gode_param_count(D,H)) floats.  adjoint_opts non-NULL: each frame's solve is differentiated by
  * torchdiffeq's continuous adjoint instead (gode_dopri5_adjoint_bwd with these tolerances / controller options, what the
- * reference loop computes); logs / ckpt / acc are then unused and may be NULL, and B is limited as there. */
+ * reference loop computes); logs / ckpt / acc are then unused and may be NULL, and B is limited as there.
+ * adjoint_param_mask: as gode_dopri5_adjoint_bwd's param_mask (bit k = tensor k of W1, b1, W2, b2 is an adjoint parameter,
+ * i.e. part of the augmented state and of its error norm: torchdiffeq takes the parameters with requires_grad); ignored
+ * when adjoint_opts is NULL. */
 int gode_odernn_bwd(const float* grad_codes, const float* eps, const float* W1, const float* b1, const float* W2,
                     const float* b2, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, int B,
                     int D, int H, int F, int log_capacity, int ckpt_capacity, const float* seg, const void* logs,
                     const float* ckpt, const double* acc, const int32_t* n_acc, const GodeAdaptiveOpts* adjoint_opts,
-                    float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
+                    int adjoint_param_mask, float* grad_h0, float* grad_eps, float* grad_ode, float* grad_gru, float* scratch, void* workspace,
                     size_t ws_bytes, gode_stream_t stream);
 
 /* ---- e: data-parallel exchange ------------------------------------------------------------------------------------ */

@@ -1299,6 +1299,44 @@ def test_odernn_fused_sampler_matches_oracle_and_unfused_path(monkeypatch):
     assert rel_err(h0c.grad, h0u.grad) <= 1e-4 and rel_err(epsc.grad, epsu.grad) <= 1e-4
 
 
+def test_odernn_continuous_adjoint_uses_only_the_parameters_that_require_grad():
+    """torchdiffeq's adjoint_params are the parameters with requires_grad: a frozen tensor is neither integrated nor part of
+    the adjoint's error norm.  The fused sampler passes the same mask as odeint_adjoint does, so with two frozen tensors its
+    continuous-adjoint gradients agree with those of the reference loop through the shim (same kernel, same mask, frame by
+    frame; tests/test_host_wiring.py checks the mask that crosses the C ABI)."""
+    _need_gpu()
+    import sys
+    from tests.caller_model import LatentMotionODERNN
+
+    torch.manual_seed(9)
+    F, B = 4, 48
+    m = LatentMotionODERNN(16, F).to(DEV)
+    m.ode_fn.fn[0].bias.requires_grad_(False)
+    m.ode_fn.fn[2].weight.requires_grad_(False)
+    h0, eps, w = torch.randn(B, 16, device=DEV), torch.randn(F, B, 16, device=DEV), torch.randn(B * F, 16, device=DEV)
+    h0a, epsa = h0.clone().requires_grad_(True), eps.clone().requires_grad_(True)
+    codes = gode.odernn_codes(m.ode_fn, m.recurrent, h0a, epsa, options={"adjoint": "continuous"})
+    (codes.transpose(0, 1).reshape(-1, 16) * w).sum().backward()
+    fused = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+    assert "ode_fn.fn.0.bias" not in fused and "ode_fn.fn.2.weight" not in fused
+    m.zero_grad()
+    gode.install_shims()
+    try:
+        h0u, epsu = h0.clone().requires_grad_(True), eps.clone().requires_grad_(True)
+        out_u = m.sample_z_m(B, h0=h0u, eps=epsu)
+        (out_u * w).sum().backward()
+    finally:
+        sys.modules.pop("torchdiffeq", None)
+        sys.modules.pop("torchsde", None)
+    # (the jump is nn.GRUCell in PyTorch on the shim path and this library's kernel on the fused one: not bit-identical)
+    assert rel_err(h0a.grad, h0u.grad) <= 2e-5 and rel_err(epsa.grad, epsu.grad) <= 2e-5
+    for n, p in m.named_parameters():
+        if p.grad is not None:
+            assert rel_err(fused[n], p.grad) <= 5e-5, (n, rel_err(fused[n], p.grad))
+        else:
+            assert n in ("ode_fn.fn.0.bias", "ode_fn.fn.2.weight")
+
+
 @pytest.mark.parametrize("mode", ["continuous", "discrete"])
 def test_odernn_fused_sampler_at_config2_batch(monkeypatch, mode):
     """BASELINE.json configs[2] at its stated batch: B = 8192 trajectories through the fused ODE-RNN sampler (3 frames of

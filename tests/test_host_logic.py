@@ -56,6 +56,9 @@ def test_field_recognition():
             super().__init__()
             self.fn = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.Tanh())
 
+        def forward(self, t, x):
+            return self.fn(x)
+
     one = OneLayer()
     W1, b1, W2, b2 = gode.recognise_field(one)
     assert W1 is one.fn[0].weight and torch.equal(W2, torch.eye(16)) and not W2.requires_grad and not b2.any()
@@ -65,6 +68,55 @@ def test_field_recognition():
     assert f[0].shape == (16, 16) and g[2].shape == (16, 16)
     with pytest.raises(NotImplementedError):
         recognise_sde(ODEFunc(16, 16))
+
+
+def test_field_recognition_checks_the_forward_not_only_the_structure():
+    """A func that HAS the reference's fn stack but whose forward is something else (time-dependent, negated, residual) must
+    not be integrated as fn(x); forward hooks would be skipped by the kernels, so they are refused too."""
+    def variant(body):
+        class F(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.fn = torch.nn.Sequential(torch.nn.Linear(16, 16), torch.nn.Tanh(), torch.nn.Linear(16, 16))
+            forward = body
+        return F()
+
+    for body in (lambda self, t, x: -self.fn(x), lambda self, t, x: self.fn(x) * torch.cos(t), lambda self, t, x: x + self.fn(x),
+                 lambda self, t, x: self.fn(x)[:, :8]):
+        with pytest.raises(NotImplementedError, match="does not return"):
+            gode.recognise_field(variant(body))
+    good = variant(lambda self, t, x: self.fn(x))
+    gode.recognise_field(good)
+    h = good.fn[1].register_forward_hook(lambda m, i, o: o * 2)
+    with pytest.raises(NotImplementedError, match="hooks"):
+        gode.recognise_field(good)
+    h.remove()
+    gode.recognise_field(good)
+
+    class TimeSDE(SDEFunc):
+        def g(self, t, x):
+            return self.diffusion_fn(x) * (1 + t)
+
+    with pytest.raises(NotImplementedError, match="does not return"):
+        recognise_sde(TimeSDE(16, 16))
+
+
+def test_table_limits_are_reported_with_their_real_names(monkeypatch):
+    """The step / frame / output-time tables travel in the launch parameters; exceeding one is reported by the host with the
+    actual numbers (torchsde's default dt = 1e-3 on [0, 1] is 1000 steps), not by a generic error from the C side."""
+    from gan_ode_b200 import _lib
+    sdeint_mod = importlib.import_module("gan_ode_b200.sdeint")
+    api = importlib.import_module("gan_ode_b200.odeint")
+    monkeypatch.setattr(api, "_require_cuda", lambda *a, **k: None)
+    monkeypatch.setattr(_lib.lib(), "gode_supported", lambda *a: 1, raising=False)
+    sde, y0 = SDEFunc(16, 16), torch.randn(4, 16)
+    with pytest.raises(NotImplementedError, match="100[01] Euler-Maruyama steps.*at most 320 steps and 64 frames"):
+        gode.sdeint(sde, y0, torch.linspace(0, 1, 16))                      # torchsde's default dt
+    with pytest.raises(NotImplementedError, match="at most 320 steps and 64 frames"):
+        gode.sdeint(sde, y0, torch.linspace(0, 1, 100), dt=0.05)
+    with pytest.raises(NotImplementedError, match="at most 256 output times"):
+        gode.odeint(ODEFunc(16, 16), torch.randn(4, 16), torch.linspace(0, 1, 300), method="dopri5")
+    assert b"GODE_SDE_MAX" in _lib.lib().gode_strerror(-3) and b"GODE_ADAPTIVE_MAX_T" in _lib.lib().gode_strerror(-3)
 
 
 def test_boundary_rejects_cpu_and_bad_inputs_without_touching_the_gpu():

@@ -249,6 +249,16 @@ def test_odernn_sampler_calls_one_entry_point_per_direction(wired):
     torch.autograd.grad(codes.sum(), [h0])
     a = wired.calls[1][1]
     assert (a[21]._obj.rtol, a[21]._obj.atol) == (1e-6, 1e-8)
+    assert a[22] == 15                                                               # all four tensors are adjoint parameters
+    wired.calls.clear()
+    # adjoint_params = the parameters that require grad (adjoint.py): frozen tensors leave the augmented state and its norm
+    f.fn[0].bias.requires_grad_(False)
+    f.fn[2].weight.requires_grad_(False)
+    codes = gode.odernn_codes(f, cell, h0, eps, options={"adjoint": "continuous"})
+    torch.autograd.grad(codes.sum(), [h0])
+    assert wired.calls[1][1][22] == 0b1001                                           # W1 and b2 only
+    f.fn[0].bias.requires_grad_(True)
+    f.fn[2].weight.requires_grad_(True)
     wired.calls.clear()
     # per-trajectory step control: the counts buffer crosses
     codes = gode.odernn_codes(f, cell, h0, eps, options={"norm": "trajectory"})
