@@ -339,27 +339,37 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_fwd_kernel(const __grid_con
         double inv_span = (double)__frcp_rn((float)span);
         inv_span = inv_span * (2.0 - span * inv_span);
         inv_span = inv_span * (2.0 - span * inv_span);
-        while (iout < p.T && p.t[iout] <= t1) {
-          const float x = (float)((p.t[iout] - t0) * inv_span);
-          float o[S::DL];
+        // Which outputs land in (t0, t1] and their normalised positions: lane q examines output iout + q, so the fp64
+        // subtract / multiply / convert (slow, dependent) of all of them run side by side instead of once per loop trip;
+        // the output times increase, so the hits are a prefix.  Identical in every warp of the grid.
+        while (iout < p.T) {
+          const int io = iout + lane;
+          const bool in = io < p.T && p.t[io < p.T ? io : p.T - 1] <= t1;
+          const float xq = in ? (float)((p.t[io < p.T ? io : p.T - 1] - t0) * inv_span) : 0.f;
+          const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+          for (int q = 0; q < cnt; ++q) {
+            const float x = __shfl_sync(0xffffffffu, xq, q);
+            float o[S::DL];
 #pragma unroll
-          for (int c = 0; c < S::DL; ++c) {
-            float tot = y0[c] + x * cd[c];
-            float xp = x * x;
-            tot = tot + xp * cc[c];
-            xp = xp * x;
-            tot = tot + xp * cb[c];
-            xp = xp * x;
-            tot = tot + xp * ca[c];
-            o[c] = tot;
-          }
-          if (valid) store_frag<S::DL>(traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, o);
-          if constexpr (RNN) {
+            for (int c = 0; c < S::DL; ++c) {
+              float tot = y0[c] + x * cd[c];
+              float xp = x * x;
+              tot = tot + xp * cc[c];
+              xp = xp * x;
+              tot = tot + xp * cb[c];
+              xp = xp * x;
+              tot = tot + xp * ca[c];
+              o[c] = tot;
+            }
+            if (valid) store_frag<S::DL>(traj + toff(p.layout, iout + q, b, p.B, p.T, D) + l * S::DL, o);
+            if constexpr (RNN) {
 #pragma unroll
-            for (int c = 0; c < S::DL; ++c) hp[c] = o[c];
+              for (int c = 0; c < S::DL; ++c) hp[c] = o[c];
+            }
           }
-          ++iout;
-          n_steps = -1;  // max_num_steps is counted per output interval (per _advance call)
+          iout += cnt;
+          if (cnt > 0) n_steps = -1;  // max_num_steps is counted per output interval (per _advance call)
+          if (cnt < 32) break;
         }
       }
 #pragma unroll
@@ -450,12 +460,15 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
     }
   };
   const int base_first = (blockIdx.x * WARPS + warp) * S::G;
+  GODE_TP(1, 2);
   if (staged && base_first < p.B) stage_grads(base_first);
+  GODE_TP(1, 50);
   BL ln;
   ln.bind(s_lines + warp * BL::kFloatsPerWarp, g);
   ColWeights<D, H, L> cw;
   cw.bind(s_cw);
   cw.stage(p.W1, p.W2, tid, WARPS * 32);
+  GODE_TP(1, 51);
   RowWeights<D, H, L> w;
   w.load(p.W1, p.b1, p.W2, p.b2, l);
   GradAcc<D, H, L> acc;
@@ -535,28 +548,37 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
 #pragma unroll
       for (int c = 0; c < S::DL; ++c) { y0b[c] = 0.f; ymb[c] = 0.f; f0b[c] = 0.f; }
       const double inv_span = 1.0 / (t1 - t0);
-      while (iout >= 1 && p.t[iout] > t0) {
-        float gout[S::DL];
+      // lane q examines output iout - q (see the forward: the fp64 position arithmetic of all outputs of the step in parallel)
+      while (iout >= 1) {
+        const int io = iout - lane;
+        const bool in = io >= 1 && p.t[io >= 1 ? io : 1] > t0;
+        const float xq = in ? (float)((p.t[io >= 1 ? io : 1] - t0) * inv_span) : 0.f;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, in));
+        for (int q = 0; q < cnt; ++q) {
+          const int ic = iout - q;
+          float gout[S::DL];
 #pragma unroll
-        for (int c = 0; c < S::DL; ++c) gout[c] = 0.f;
-        if (staged) load_frag<S::DL>(my_gr + (size_t)iout * (S::G * D) + g * D + l * S::DL, gout);
-        else if (valid) load_frag<S::DL>(p.grad_traj + toff(p.layout, iout, b, p.B, p.T, D) + l * S::DL, gout);
-        const float x = (float)((p.t[iout] - t0) * inv_span);
-        const float p2 = x * x, p3 = p2 * x, p4 = p3 * x;
-        const float cy0 = 1.f - 11.f * p2 + 18.f * p3 - 8.f * p4;
-        const float cy1 = -5.f * p2 + 14.f * p3 - 8.f * p4;
-        const float cym = 16.f * p2 - 32.f * p3 + 16.f * p4;
-        const float cf0 = dt32 * (x - 4.f * p2 + 5.f * p3 - 2.f * p4);
-        const float cf1 = dt32 * (p2 - 3.f * p3 + 2.f * p4);
+          for (int c = 0; c < S::DL; ++c) gout[c] = 0.f;
+          if (staged) load_frag<S::DL>(my_gr + (size_t)ic * (S::G * D) + g * D + l * S::DL, gout);
+          else if (valid) load_frag<S::DL>(p.grad_traj + toff(p.layout, ic, b, p.B, p.T, D) + l * S::DL, gout);
+          const float x = __shfl_sync(0xffffffffu, xq, q);
+          const float p2 = x * x, p3 = p2 * x, p4 = p3 * x;
+          const float cy0 = 1.f - 11.f * p2 + 18.f * p3 - 8.f * p4;
+          const float cy1 = -5.f * p2 + 14.f * p3 - 8.f * p4;
+          const float cym = 16.f * p2 - 32.f * p3 + 16.f * p4;
+          const float cf0 = dt32 * (x - 4.f * p2 + 5.f * p3 - 2.f * p4);
+          const float cf1 = dt32 * (p2 - 3.f * p3 + 2.f * p4);
 #pragma unroll
-        for (int c = 0; c < S::DL; ++c) {
-          y0b[c] = fmaf(cy0, gout[c], y0b[c]);
-          ybar[c] = fmaf(cy1, gout[c], ybar[c]);
-          ymb[c] = fmaf(cym, gout[c], ymb[c]);
-          f0b[c] = fmaf(cf0, gout[c], f0b[c]);
-          fbar[c] = fmaf(cf1, gout[c], fbar[c]);
+          for (int c = 0; c < S::DL; ++c) {
+            y0b[c] = fmaf(cy0, gout[c], y0b[c]);
+            ybar[c] = fmaf(cy1, gout[c], ybar[c]);
+            ymb[c] = fmaf(cym, gout[c], ymb[c]);
+            f0b[c] = fmaf(cf0, gout[c], f0b[c]);
+            fbar[c] = fmaf(cf1, gout[c], fbar[c]);
+          }
         }
-        --iout;
+        iout -= cnt;
+        if (cnt < 32) break;
       }
       // ymid = y0 + sum_j k_j dt cmid_j ; f1 = k[NS] ; f0 = k[0]
 #pragma unroll

@@ -109,10 +109,28 @@ struct ColWeights {
   __device__ __forceinline__ static int row_d(int d) { return (d % S::DL) * L + d / S::DL; }
 
   // all threads of the CTA cooperate; caller must __syncthreads() afterwards
+  // (all global loads are issued before the first shared-memory store: written as one load -> store loop with a run-time
+  // trip count, the two or three trips each waited a full L2 / HBM latency at the start of every backward kernel)
   __device__ __forceinline__ void stage(const float* __restrict__ W1, const float* __restrict__ W2, int tid, int nthreads) {
-    for (int e = tid; e < D * H; e += nthreads) {
-      { const int d = e / H, j = e % H; w2t[row_h(j) * S::YS + d] = W2[e]; }   // W2[d][j]
-      { const int j = e / D, i = e % D; w1t[row_d(i) * S::HS + j] = W1[e]; }   // W1[j][i]
+    constexpr int kAhead = 4;
+    float a[kAhead], b[kAhead];
+#pragma unroll
+    for (int it = 0; it < kAhead; ++it) {
+      const int e = tid + it * nthreads;
+      a[it] = e < D * H ? __ldg(W2 + e) : 0.f;
+      b[it] = e < D * H ? __ldg(W1 + e) : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < kAhead; ++it) {
+      const int e = tid + it * nthreads;
+      if (e < D * H) {
+        { const int d = e / H, j = e % H; w2t[row_h(j) * S::YS + d] = a[it]; }   // W2[d][j]
+        { const int j = e / D, i = e % D; w1t[row_d(i) * S::HS + j] = b[it]; }   // W1[j][i]
+      }
+    }
+    for (int e = tid + kAhead * nthreads; e < D * H; e += nthreads) {   // CTAs below 64 threads
+      { const int d = e / H, j = e % H; w2t[row_h(j) * S::YS + d] = W2[e]; }
+      { const int j = e / D, i = e % D; w1t[row_d(i) * S::HS + j] = W1[e]; }
     }
   }
 };

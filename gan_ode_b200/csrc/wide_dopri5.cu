@@ -141,6 +141,13 @@ __global__ void __launch_bounds__(kWideWarps * 32) wide_dopri5_fwd_kernel(const 
     double inv_span = (double)__frcp_rn((float)span);
     inv_span = inv_span * (2.0 - span * inv_span);
     inv_span = inv_span * (2.0 - span * inv_span);
+    // outputs inside this (candidate) step and their normalised positions, once per attempt: lane q examines output iout + q
+    // (the fp64 arithmetic of all of them side by side; the output times increase, so the hits are a prefix).  More than 32
+    // hits in one step: the rest is evaluated per trajectory below.
+    const int ioq = iout + l < p.T ? iout + l : p.T - 1;
+    const bool inq = iout + l < p.T && p.t[ioq] <= t1;
+    const float xq = inq ? (float)((p.t[ioq] - t0) * inv_span) : 0.f;
+    const int n_out = __popc(__ballot_sync(0xffffffffu, inq));
     const float* sc = st[cur];
     float* sn = st[cur ^ 1];
     double v[1] = {0.0};
@@ -192,8 +199,8 @@ __global__ void __launch_bounds__(kWideWarps * 32) wide_dopri5_fwd_kernel(const 
           cc[c] = dt32 * (f1 - 4.f * f0) - 11.f * y0[c] - 5.f * y1 + 16.f * ymid;
           cd[c] = dt32 * f0;
         }
-        for (int io = iout; io < p.T && p.t[io] <= t1; ++io) {
-          const float x = (float)((p.t[io] - t0) * inv_span);
+        for (int io = iout; io < p.T && (io - iout < n_out || (n_out == 32 && p.t[io] <= t1)); ++io) {
+          const float x = io - iout < 32 ? __shfl_sync(0xffffffffu, xq, io - iout) : (float)((p.t[io] - t0) * inv_span);
 #pragma unroll
           for (int c = 0; c < DL; ++c) {
             float tot = y0[c] + x * cd[c];

@@ -15,7 +15,7 @@ import gan_ode_b200 as gode
 from gan_ode_b200 import _lib
 from gan_ode_b200.fields import make_field
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 4096
 dev = torch.device("cuda", 0)
 f = make_field(16, 16, seed=0).to(dev)
 params = list(f.parameters())
@@ -56,7 +56,8 @@ for pdl in (False, True):
         step()
     gode.config.pdl = False
     for _ in range(5):
-        flush.fill_(1)
+        if "--warm" not in sys.argv:
+            flush.fill_(1)
         gr.replay()
     torch.cuda.synchronize()
     fw, bw = read()
@@ -66,7 +67,8 @@ for pdl in (False, True):
         names_f[4 + 3 * a] = "att%d stages" % a
         names_f[5 + 3 * a] = "att%d reduced" % a
         names_f[6 + 3 * a] = "att%d end" % a
-    names_b = {0: "entry", 1: "weights staged", 2: "after griddep_wait", 3: "log+sync state", 4: "grads staged", 30: "replay done", 31: "exit"}
+    names_b = {0: "entry", 1: "row weights loaded", 2: "griddep_wait + log read", 50: "grad copies issued", 51: "column weights staged",
+               3: "CTA barrier", 4: "grads staged", 30: "replay done", 31: "exit"}
     for st in range(4):
         names_b[5 + 2 * st] = "step%d begin" % st
         names_b[6 + 2 * st] = "step%d recomputed" % st
