@@ -7,9 +7,7 @@
 //   dopri5_backprop_bwd_kernel  reverse-mode through the accepted steps + dense-output interpolation,
 //                               dt sequence read from the device-side step log (no host round trip).
 #include <stdlib.h>
-#include "dopri5_common.cuh"
-#include "gru_cell.cuh"
-
+#include <cuda_runtime.h>
 #ifdef GODE_TRACE
 // Developer build only (python -m gan_ode_b200.build --trace -> libgode_trace.so): thread 0 of CTA 0 stamps
 // (%globaltimer ns, clock64) at fixed points of the two headline kernels; scripts/headline_trace.py reads them back.
@@ -24,9 +22,20 @@ __device__ unsigned long long g_gode_trace[2 * 64 * 2];
 extern "C" int gode_debug_trace_read(unsigned long long* host_out) {
   return (int)cudaMemcpyFromSymbol(host_out, g_gode_trace, sizeof(g_gode_trace));
 }
+#define GODE_TP_R(slot) GODE_TP(1, slot)   // trace points inside reduce_param_grads (small_field.cuh)
+// latest time ANY CTA passes this point (the global timer only grows, so the maximum belongs to the last launch)
+#define GODE_TP_LAST(slot)                                                                    \
+  if (threadIdx.x == 0) {                                                                     \
+    unsigned long long gt_;                                                                   \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                                   \
+    atomicMax(&g_gode_trace[(64 + (slot)) * 2], gt_);                                         \
+  }
 #else
 #define GODE_TP(kern, slot)
 #endif
+#include "dopri5_common.cuh"
+#include "gru_cell.cuh"
+
 
 namespace gode {
 

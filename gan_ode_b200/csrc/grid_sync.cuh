@@ -46,17 +46,21 @@ constexpr int kGsFlagMaxCtas = 16;  // measured inside dopri5_fwd_kernel (script
 struct GridSyncWs {
   unsigned int* counter;      // 256-byte header: [0] arrival counter, [1] epoch base, [2] counter base
   unsigned long long* slots;  // [2][kGsMaxVals][gridDim.x] tagged words
+  unsigned long long* rows;   // tagged parameter-gradient rows [gridDim.x][P] (small_field.cuh::reduce_param_grads)
 };
 
 // Fixed size of the sync region at the front of every workspace (so that scratch data behind it can never be mistaken for
 // a tagged word by a later launch with a larger grid): header + slots for up to kSyncMaxGrid CTAs.
 constexpr size_t kSyncRegionBytes = GODE_SYNC_REGION_BYTES;
-constexpr int kSyncMaxGrid = (int)((kSyncRegionBytes - 256) / (sizeof(unsigned long long) * 2 * kGsMaxVals));
+constexpr size_t kSyncSlotBytes = 256 * 1024;                       // header + all-reduce slots
+constexpr size_t kSyncRowBytes = kSyncRegionBytes - kSyncSlotBytes;  // tagged gradient rows (only ever written as tagged words)
+constexpr int kSyncMaxGrid = (int)((kSyncSlotBytes - 256) / (sizeof(unsigned long long) * 2 * kGsMaxVals));
 
 __host__ __device__ inline size_t grid_sync_bytes(int /*grid*/) { return kSyncRegionBytes; }
 __host__ __device__ inline void grid_sync_bind(GridSyncWs& ws, void* base) {
   ws.counter = reinterpret_cast<unsigned int*>(base);
   ws.slots = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + 256);
+  ws.rows = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(base) + kSyncSlotBytes);
 }
 
 // Programmatic dependent launch (PDL): a kernel launched with programmatic stream serialisation may start while the

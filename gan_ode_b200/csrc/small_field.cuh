@@ -308,6 +308,9 @@ struct ReduceWs {
   unsigned int* w_ctr;
 };
 
+__device__ __forceinline__ void ld_relaxed_v2_u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -328,6 +331,13 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+#ifndef GODE_TP_R
+#define GODE_TP_R(slot)   // developer trace points (dopri5_small.cu defines them in the trace build)
+#endif
+#ifndef GODE_TP_LAST
+#define GODE_TP_LAST(slot)
+#endif
 
 // LAST: this is the kernel's last grid-wide operation.  Then only the CTAs that own columns (and CTA 0, which stores the sync
 // bases) wait at the barrier; the others arrive and are done — 222 of 256 CTAs stop polling the counter the 34 consumers
@@ -372,50 +382,13 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
     }
   }
   __syncthreads();
-  float* mine = ws.partials + (size_t)blockIdx.x * P;
-  for (int p = tid; p < P; p += NT) {
-    float s = smem_red[p];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
-    __stcg(mine + p, s);
-  }
+  GODE_TP_R(32);
   const bool xchg = ws.w_world > 1;
-  const unsigned int wtag = xchg ? *reinterpret_cast<volatile unsigned int*>(ws.w_ctr) + 1u : 0u;  // read before the barrier
-  if constexpr (LAST) {
-    const bool waits = blockIdx.x == 0 || (int)blockIdx.x * WARPS < P / 4;
-    ss.ctarget += gridDim.x;
-    __syncthreads();
-    if (tid == 0) {
-      __threadfence();
-      arrive_counter(ws.gs.counter);
-      if (waits) {
-        wait_counter(ws.gs.counter, ss.ctarget);
-        __threadfence();
-      }
-    }
-    if (!waits) return;
-    __syncthreads();
-  } else {
-    grid_barrier(ws.gs, ss);
-  }
-  if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;  // every thread of the grid has read it
-  // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
-  // in order, then a shuffle tree.  No block-level synchronisation.
   const int nb = gridDim.x;
   const int gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
-  for (int p4 = gw; p4 < P / 4; p4 += nw) {
-    const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
-    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = lane; b < nb; b += 32) {
-      const float4 v = __ldcg(col + (size_t)b * (P / 4));
-      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    }
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
-      s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
-    }
-    if (xchg) {  // publish this column to every rank (self included); gathered below once all of the warp's columns are out
+  // publish one reduced float4 column: to every rank's exchange buffer (gathered at the end) or straight to grad_params
+  auto publish = [&](int p4, const float4& s, unsigned int wtag) {
+    if (xchg) {
       const int W = ws.w_world, par = (int)(wtag & 1u), j = lane & 3;
       const float mine = j == 0 ? s.x : j == 1 ? s.y : j == 2 ? s.z : s.w;
       const unsigned long long word = (unsigned long long)__float_as_uint(mine) | ((unsigned long long)wtag << 32);
@@ -423,6 +396,120 @@ __device__ __forceinline__ void reduce_param_grads(GradAcc<D, H, L>& acc, float*
         st_sys_u64(ws.w_slots[r] + ((size_t)(par * W + ws.w_rank) * P + 4 * p4 + j), word);
     } else if (lane == 0) {
       reinterpret_cast<float4*>(grad_params)[p4] = s;
+    }
+  };
+  unsigned int wtag = 0u;
+  // TAGGED rows (the kernel's last reduction): every CTA stores its P sums as 64-bit words {fp32 | tag << 32} into its row of
+  // the persistent region (st.relaxed.gpu: value and tag cannot be seen torn), and the column owners poll the rows directly —
+  // no fence, no arrival counter, no barrier between "last CTA done" and "totals out": one L2 write -> read latency instead of
+  // store-ack + atomic + poll + fence + reload (2.7 us -> see profiles/README.md).  Tags count across launches (SyncState),
+  // the rows are only ever written as tagged words, so a stale word always carries an older tag; CTAs that own no column
+  // are done after their stores.
+  const bool tagged = LAST && (size_t)nb * P * sizeof(unsigned long long) <= kSyncRowBytes;
+  if (tagged) {
+    const unsigned int tag = ++ss.epoch;
+    // (acquire: the row stores below must not become visible before this launch count was read — CTA 0 advances it once it
+    // has seen every CTA's row)
+    if (xchg) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(wtag) : "l"(ws.w_ctr) : "memory");
+      wtag += 1u;
+    }
+    unsigned long long* mine = ws.gs.rows + (size_t)blockIdx.x * P;
+    for (int p = tid; p < P; p += NT) {
+      float s = smem_red[p];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
+      st_relaxed_u64(mine + p, (unsigned long long)__float_as_uint(s) | ((unsigned long long)tag << 32));
+    }
+    GODE_TP_R(33);
+    GODE_TP_LAST(36);
+    if ((int)blockIdx.x * WARPS >= P / 4) return;   // owns no column
+    for (int p4 = gw; p4 < P / 4; p4 += nw) {
+      const unsigned long long* col = ws.gs.rows + 4 * p4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b0 = lane; b0 < nb; b0 += 256) {   // eight rows per lane, every load in flight; rows added in order
+        unsigned long long x[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + 32 * u;
+          if (b < nb) {
+            ld_relaxed_v2_u64(col + (size_t)b * P, x[u][0], x[u][1]);
+            ld_relaxed_v2_u64(col + (size_t)b * P + 2, x[u][2], x[u][3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + 32 * u;
+          if (b < nb) {
+            while ((unsigned int)(x[u][0] >> 32) != tag || (unsigned int)(x[u][1] >> 32) != tag ||
+                   (unsigned int)(x[u][2] >> 32) != tag || (unsigned int)(x[u][3] >> 32) != tag) {
+              ld_relaxed_v2_u64(col + (size_t)b * P, x[u][0], x[u][1]);
+              ld_relaxed_v2_u64(col + (size_t)b * P + 2, x[u][2], x[u][3]);
+            }
+            s.x += __uint_as_float((unsigned int)x[u][0]); s.y += __uint_as_float((unsigned int)x[u][1]);
+            s.z += __uint_as_float((unsigned int)x[u][2]); s.w += __uint_as_float((unsigned int)x[u][3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+      }
+      publish(p4, s, wtag);
+    }
+    GODE_TP_R(34);
+    if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;   // warp 0 of CTA 0 has seen every CTA's row: all have read it
+  } else {
+    float* mine = ws.partials + (size_t)blockIdx.x * P;
+    for (int p = tid; p < P; p += NT) {
+      float s = smem_red[p];
+#pragma unroll
+      for (int w = 1; w < WARPS; ++w) s += smem_red[w * P + p];
+      __stcg(mine + p, s);
+    }
+    wtag = xchg ? *reinterpret_cast<volatile unsigned int*>(ws.w_ctr) + 1u : 0u;  // read before the barrier
+    if constexpr (LAST) {
+      const bool waits = blockIdx.x == 0 || (int)blockIdx.x * WARPS < P / 4;
+      ss.ctarget += gridDim.x;
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        arrive_counter(ws.gs.counter);
+        if (waits) {
+          wait_counter(ws.gs.counter, ss.ctarget);
+          __threadfence();
+        }
+      }
+      if (!waits) return;
+      __syncthreads();
+    } else {
+      grid_barrier(ws.gs, ss);
+    }
+    if (xchg && blockIdx.x == 0 && tid == 0) *ws.w_ctr = wtag;  // every thread of the grid has read it
+    // one warp per float4 column, columns dealt round-robin over all warps of the grid; lane r adds rows r, r+32, ...
+    // in order, then a shuffle tree.  No block-level synchronisation.
+    for (int p4 = gw; p4 < P / 4; p4 += nw) {
+      const float4* col = reinterpret_cast<const float4*>(ws.partials) + p4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int b0 = lane; b0 < nb; b0 += 256) {   // eight rows per lane with every load in flight before the first add
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int b = b0 + 32 * u;
+          v[u] = b < nb ? __ldcg(col + (size_t)b * (P / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (b0 + 32 * u < nb) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+      }
+      publish(p4, s, wtag);
     }
   }
   if (xchg) {

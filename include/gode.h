@@ -97,7 +97,9 @@ enum {
 #define GODE_SDE_MAX_FRAMES 64     /* output frames of one gode_sde_* solve (the reference: 16)                        */
 #define GODE_SDE_MAX_CELLS 768     /* Brownian cells = distinct forward + reverse step end points (gode_sde_em_fwd_cells) */
 #define GODE_SDE_MAX_REV_STEPS 384 /* reverse steps of gode_sde_adjoint_bwd (the reference: 45)                        */
-#define GODE_SYNC_REGION_BYTES (256 * 1024) /* persistent grid-sync region at the front of every workspace */
+/* persistent region at the front of every workspace: 256 KB of grid-sync words (counters, tagged all-reduce slots) followed by
+ * 1280 KB of tagged parameter-gradient rows (the backward kernels' final reduction: 296 CTAs x 544 values x 8 bytes) */
+#define GODE_SYNC_REGION_BYTES (1536 * 1024)
 
 /* per-thread launch flags (gode_set_thread_launch_flags) */
 enum {
