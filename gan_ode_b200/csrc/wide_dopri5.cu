@@ -27,7 +27,6 @@
 namespace gode {
 
 constexpr int kWideMaxT = GODE_ADAPTIVE_MAX_T;   // output times passed by value
-constexpr int kWideKS = 1024;    // rows per split-K slice of the gradient contraction
 
 struct WideDp5Args {
   const float *y0, *W1, *b1, *W2, *b2;
@@ -400,6 +399,17 @@ __global__ void __launch_bounds__(kWideWarps * 32) wide_dopri5_backprop_kernel(c
 }
 
 // ---- contraction of the valid rows: C[M][N] = sum_r A[r][M] * Bm[r][N], column sums of A; row count from the device log --------
+// A FIXED number of slices (kWideSlices CTAs) shares whatever rows the solve recorded: slice s takes rows [s*per, (s+1)*per),
+// per = ceil(rows / slices) rounded up to 16 — the host cannot size the grid by n_accepted without a sync, and sizing it by the
+// checkpoint capacity left a handful of CTAs with all the work (3 recorded steps of 64: 25 busy CTAs of 518).  The second pass
+// adds the slices in order: deterministic for a given (batch, n_accepted).
+constexpr int kWideSlices = 592;
+
+__device__ __forceinline__ long long wide_dp5_rows_per_slice(long long rows, int slices) {
+  const long long per = (rows + slices - 1) / slices;
+  return ((per + 15) / 16) * 16;
+}
+
 template <int M, int N>
 __global__ void __launch_bounds__(256) wide_dp5_wgrad_partial_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
                                                                      const GodeStepLog* __restrict__ log, int ckpt_capacity,
@@ -410,9 +420,10 @@ __global__ void __launch_bounds__(256) wide_dp5_wgrad_partial_kernel(const float
   __shared__ __align__(16) float sB[16][N];
   const int t = threadIdx.x;
   const long long rows = (long long)min(log->n_accepted, ckpt_capacity) * rows_per_step;
-  const long long r0 = (long long)blockIdx.x * kWideKS;
+  const long long per = wide_dp5_rows_per_slice(rows, gridDim.x);
+  const long long r0 = (long long)blockIdx.x * per;
   if (r0 >= rows) return;   // beyond the recorded steps: the reduction below does not read this slice
-  const long long r1 = r0 + kWideKS < rows ? r0 + kWideKS : rows;
+  const long long r1 = r0 + per < rows ? r0 + per : rows;
   float acc[OUT];
 #pragma unroll
   for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
@@ -440,12 +451,13 @@ __global__ void __launch_bounds__(256) wide_dp5_wgrad_partial_kernel(const float
 }
 
 __global__ void wide_dp5_wgrad_reduce_kernel(const float* __restrict__ partial, const GodeStepLog* __restrict__ log,
-                                             int ckpt_capacity, long long rows_per_step, int len, float* __restrict__ out_w,
-                                             int len_w, float* __restrict__ out_b) {
+                                             int ckpt_capacity, long long rows_per_step, int n_slices, int len,
+                                             float* __restrict__ out_w, int len_w, float* __restrict__ out_b) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= len) return;
   const long long rows = (long long)min(log->n_accepted, ckpt_capacity) * rows_per_step;
-  const int slices = (int)((rows + kWideKS - 1) / kWideKS);
+  const long long per = wide_dp5_rows_per_slice(rows, n_slices);
+  const int slices = rows > 0 ? (int)((rows + per - 1) / per) : 0;
   float s = log->status != 0 ? __int_as_float(0x7fc00000) : 0.f;
   for (int k = 0; k < slices; ++k) s += partial[(size_t)k * len + e];
   if (e < len_w) out_w[e] = s;
@@ -458,7 +470,7 @@ static size_t wide_dp5_rows(int B, int kc) { return (size_t)B * (size_t)kc * 7; 
 size_t wide_dopri5_workspace_bytes(int B, int D, int H, int ckpt_capacity, int backward) {
   if (!backward) return (size_t)GODE_SYNC_REGION_BYTES + sizeof(float) * (size_t)B * 4 * D + 256;
   const size_t rows = wide_dp5_rows(B, ckpt_capacity);
-  const size_t slices = (rows + kWideKS - 1) / kWideKS;
+  const size_t slices = kWideSlices;
   return (size_t)GODE_SYNC_REGION_BYTES + sizeof(float) * (rows * (size_t)(2 * D + 2 * H) +
                                                           slices * (size_t)(H * D + (H > D ? H : D))) + 1024;
 }
@@ -501,15 +513,15 @@ static int launch_wide_dp5_bwd(WideDp5Args& a, float* grad_params, void* workspa
   if (grid > cap) grid = cap;
   kern<<<grid, kWideWarps * 32, smem, st>>>(a);
   if (int rc = launch_status()) return rc;
-  const int slices = (int)((rows + kWideKS - 1) / kWideKS);
+  const int slices = kWideSlices;
   const long long rps = (long long)a.B * 7;
   // dW1 (H x D) = delta^T u ; db1 = colsum(delta)     flat layout [W1 | b1 | W2 | b2]
   wide_dp5_wgrad_partial_kernel<H, D><<<slices, 256, 0, st>>>(a.sd, a.su, a.log, kc, rps, partial);
-  wide_dp5_wgrad_reduce_kernel<<<(H * D + H + 255) / 256, 256, 0, st>>>(partial, a.log, kc, rps, H * D + H, grad_params, H * D,
-                                                                       grad_params + H * D);
+  wide_dp5_wgrad_reduce_kernel<<<(H * D + H + 255) / 256, 256, 0, st>>>(partial, a.log, kc, rps, slices, H * D + H, grad_params,
+                                                                       H * D, grad_params + H * D);
   // dW2 (D x H) = cot^T h ; db2 = colsum(cot)
   wide_dp5_wgrad_partial_kernel<D, H><<<slices, 256, 0, st>>>(a.sa, a.sh, a.log, kc, rps, partial);
-  wide_dp5_wgrad_reduce_kernel<<<(D * H + D + 255) / 256, 256, 0, st>>>(partial, a.log, kc, rps, D * H + D,
+  wide_dp5_wgrad_reduce_kernel<<<(D * H + D + 255) / 256, 256, 0, st>>>(partial, a.log, kc, rps, slices, D * H + D,
                                                                        grad_params + H * D + H, D * H,
                                                                        grad_params + H * D + H + D * H);
   return launch_status();

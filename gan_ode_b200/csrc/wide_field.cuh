@@ -7,6 +7,10 @@
 
 namespace gode {
 
+// 8 warps per CTA.  16 were measured (round 2: the weights fill 136 KB of shared memory at D=64 / H=256, so a fatter CTA is the
+// only way to more warps per scheduler): no gain at B >= 4096 (0.541 vs 0.549 ms for the dopri5 forward) and half the SMs idle
+// at B = 1184 — the mat-vecs are bound by shared-memory operand BANDWIDTH (every warp streams all weights per evaluation), not
+// by its latency.
 constexpr int kWideWarps = 8;
 
 template <int D, int H>
