@@ -71,11 +71,17 @@ __device__ __forceinline__ uint32_t tcw2_hcol(int c) { return 8u * c; }
 #ifndef GODE_TANH_FMA_EVERY
 #define GODE_TANH_FMA_EVERY 1000
 #endif
+// Measured (round 2, scripts/tanh_poly_probe.py; B = 18 944 / 151 552): all MUFU 184.7 / 817.5 us, one pair in 4 on the FMA pipe
+// 176.5 / 797.1 us, one in 3: 176.7 / 806.3 us, one in 2: 182.5 / 870.8 us; error against the FP32 solve unchanged (3.5e-4).
+// The epilogue is not bound by MUFU throughput alone: with two epilogue warps per scheduler the twelve extra issue slots of
+// a polynomial pair are only partly hidden, so a quarter is the most that pays.
+constexpr int kTanhPolyDefault = 4;   // GODE_TANH_POLY_EVERY default (0: every tanh on the MUFU pipe)
 constexpr int kTanhFmaEvery = GODE_TANH_FMA_EVERY;  // one pair in every kTanhFmaEvery goes to the FMA pipe (1000: none).
 // Measured (B = 151 552): none 844 us, every 4th pair 858 us, every 2nd pair 930 us -- the extra ~11 issue slots per pair
 // cost more than the MUFU cycles they free with only two epilogue warps per scheduler, so the default is OFF.
 
-template <int D, int H>
+// POLY_EVERY: one pair of tanh in every POLY_EVERY is evaluated by tc::tanh_pair_poly on the FMA pipe (no MUFU op); 1000: none
+template <int D, int H, int POLY_EVERY>
 __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_constant__ TcWideArgs p) {
   using S = TcWide2Shape<D, H>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -162,6 +168,9 @@ __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_c
     for (int i = 0; i < 16; i += 2) {
       if ((i / 2) % kTanhFmaEvery == kTanhFmaEvery - 1) {  // this pair on the FMA pipe + one MUFU.RCP (tc_common.cuh)
         const float2 th = tc::tanh_pair_fma(__uint_as_float(z[i]), __uint_as_float(z[i + 1]));
+        q[i / 2] = tc::pack_bf16x2(th.x, th.y);
+      } else if ((i / 2) % POLY_EVERY == POLY_EVERY - 1) {  // this pair on the FMA pipe alone (polynomial)
+        const float2 th = tc::tanh_pair_poly(__uint_as_float(z[i]), __uint_as_float(z[i + 1]));
         q[i / 2] = tc::pack_bf16x2(th.x, th.y);
       } else {
         q[i / 2] = tc::pack_bf16x2(tc::tanh_approx(__uint_as_float(z[i])), tc::tanh_approx(__uint_as_float(z[i + 1])));
@@ -337,7 +346,17 @@ int tc_rk4_fwd_wide(const float* y0, const float* W1, const float* b1, const flo
   const int ntiles = (B + S2::TILE - 1) / S2::TILE;
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
-  auto kern = tc_rk4_fwd_wide2_kernel<64, 256>;
+  // share of the tanh evaluations moved from the MUFU pipe to the FMA pipe (polynomial): developer switch GODE_TANH_POLY_EVERY
+  // = 2 / 3 / 4 (one pair in every 2 / 3 / 4) or 0 (none); default: see profiles/README.md round 2
+  static int poly_every = -1;
+  if (poly_every < 0) {
+    const char* pe = getenv("GODE_TANH_POLY_EVERY");
+    poly_every = pe ? atoi(pe) : kTanhPolyDefault;
+  }
+  auto kern = poly_every == 2 ? tc_rk4_fwd_wide2_kernel<64, 256, 2>
+              : poly_every == 3 ? tc_rk4_fwd_wide2_kernel<64, 256, 3>
+              : poly_every == 4 ? tc_rk4_fwd_wide2_kernel<64, 256, 4>
+                                : tc_rk4_fwd_wide2_kernel<64, 256, 1000>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::BYTES);
   if (e != cudaSuccess) return -(1000 + (int)e);
 #ifdef GODE_TCW_TIMING
