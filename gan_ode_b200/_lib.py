@@ -18,7 +18,7 @@ LAYOUT_TBD, LAYOUT_BTD = 0, 1
 NORM_BATCH, NORM_TRAJ = 0, 1
 MAX_HOST_STEPS = 255
 ADAPTIVE_MAX_T, SDE_MAX_STEPS, SDE_MAX_FRAMES, SDE_MAX_CELLS, SDE_MAX_REV_STEPS = 256, 320, 64, 768, 384   # include/gode.h
-SYNC_REGION_BYTES = 1536 * 1024   # include/gode.h GODE_SYNC_REGION_BYTES
+SYNC_REGION_BYTES = 6400 * 1024   # include/gode.h GODE_SYNC_REGION_BYTES
 LAUNCH_PDL_BWD = 1
 
 ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_CKPT_OVERFLOW, ST_PEER_TIMEOUT = 1, 2, 4, 8, 16

@@ -44,16 +44,20 @@ def _deps_mtime() -> float:
     return max(newest, os.path.getmtime(__file__))
 
 
-def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, trace: bool = False, defines=(), tag: str = "") -> str:
     """trace=True: developer build libgode_trace.so with -DGODE_TRACE (in-kernel time stamps; scripts/headline_trace.py loads it
-    through GODE_LIB).  Never used by the product path."""
-    lib = LIB.replace("libgode.so", "libgode_trace.so") if trace else LIB
+    through GODE_LIB).  defines + tag: any other developer variant, libgode_<tag>.so with -D<define>... (e.g. --define
+    GODE_ADJ_TIMING --tag adjtiming: per-phase clock64 accounting of the continuous adjoint kernel).  Never used by the product
+    path."""
+    if trace:
+        defines, tag = tuple(defines) + ("GODE_TRACE",), tag or "trace"
+    lib = LIB.replace("libgode.so", "libgode_{}.so".format(tag)) if tag else LIB
     if not force and os.path.exists(lib) and os.path.getmtime(lib) >= _deps_mtime():
         return lib
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build_trace" if trace else "build")
+    objdir = os.path.join(CSRC, "build_" + tag if tag else "build")
     os.makedirs(objdir, exist_ok=True)
-    extra = ["-DGODE_TRACE"] if trace else []
+    extra = ["-D" + d for d in defines]
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -110,6 +114,11 @@ def build_torch_ext(force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
-    if "--trace" not in sys.argv:
-        print(build_torch_ext(force="--force" in sys.argv))
+    argv = sys.argv[1:]
+    defs = [argv[i + 1] for i, a in enumerate(argv) if a == "--define" and i + 1 < len(argv)]
+    tags = [argv[i + 1] for i, a in enumerate(argv) if a == "--tag" and i + 1 < len(argv)]
+    if defs and not tags:
+        raise SystemExit("--define needs --tag NAME (the variant is written to csrc/libgode_NAME.so)")
+    print(build(force="--force" in argv, verbose="-v" in argv, trace="--trace" in argv, defines=defs, tag=tags[0] if tags else ""))
+    if "--trace" not in argv and not tags:
+        print(build_torch_ext(force="--force" in argv))

@@ -39,8 +39,6 @@ struct Dp5AdjArgs {
   int32_t* mailbox;  // mapped host int (gode_set_status_mailbox) or null
   double* att_dt; float* att_er; uint8_t* att_acc;  // optional per-attempt log, all intervals concatenated
   GridSyncWs gs;
-  float* partials;  // [grid][VT]
-  float* totals;    // [VT]
   GodeAdaptiveOpts o;
   int B, T, layout;
   int param_mask;  // bit k: parameter tensor k (W1, b1, W2, b2) is an adjoint parameter, i.e. enters the norm (adjoint.py)
@@ -226,7 +224,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
     GADJ_TICK(tc_t);
   };
 
-  // sum `nvec` accumulator vectors and the per-lane scalars over the whole grid; totals land in s_tot
+  // Sum `nvec` accumulator vectors and the per-lane scalars over the whole grid; totals land in s_tot.
+  // No barrier: every CTA stores its VT sums as tagged 64-bit words {fp32 | tag} into ITS row of the persistent region, the
+  // warp that owns a float4 column polls that column in all rows (rows added in CTA order, then a fixed shuffle tree: the same
+  // order as before), stores the four totals as tagged words, and every CTA polls the totals.  Two L2 write -> read latencies
+  // per reduction instead of two fence + atomic + poll + fence barriers around the same traffic.  Reuse is safe without
+  // double buffering: a CTA writes its row for reduction n+1 only after it has seen ALL totals of n, i.e. after every column
+  // owner has finished reading the rows of n; an owner writes total n+1 only after it has seen every CTA's row n+1, each
+  // written after that CTA consumed the totals of n.  Tags count across launches (SyncState), rows are only ever written
+  // as tagged words.
   auto grid_reduce = [&](int nvec, float (&sc)[kAdjNS]) {
 #pragma unroll
     for (int k = 0; k < kAdjNS; ++k) {
@@ -238,54 +244,77 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
       for (int k = 0; k < kAdjNS; ++k) s_sc[warp * kAdjNS + k] = sc[k];
     }
     __syncthreads();
-    float* mine = p.partials + (size_t)blockIdx.x * VT;
+    const unsigned int tag = ++ss.epoch;
+    const unsigned long long tag_hi = (unsigned long long)tag << 32;
+    unsigned long long* mine = p.gs.rows + (size_t)blockIdx.x * VT;
     for (int n = tid; n < P; n += NT) {
       for (int v = 0; v < nvec; ++v) {
         const float* col = s_acc + (size_t)v * WARPS * P + n;
         float x = col[0];
 #pragma unroll
         for (int q = 1; q < WARPS; ++q) x += col[q * P];
-        __stcg(mine + v * P + n, x);
+        st_relaxed_u64(mine + v * P + n, (unsigned long long)__float_as_uint(x) | tag_hi);
       }
     }
     if (tid < kAdjNS) {
       float x = s_sc[tid];
 #pragma unroll
       for (int q = 1; q < WARPS; ++q) x += s_sc[q * kAdjNS + tid];
-      __stcg(mine + kAdjNV * P + tid, x);
+      st_relaxed_u64(mine + kAdjNV * P + tid, (unsigned long long)__float_as_uint(x) | tag_hi);
     }
-    grid_barrier(p.gs, ss);
     const int nb = gridDim.x, gw = blockIdx.x * WARPS + warp, nw = nb * WARPS;
-    // (with few CTAs a warp owns several columns: issue the loads of up to four of them before the first shuffle tree)
-    for (int c0 = gw; c0 < VT / 4; c0 += 4 * nw) {
-      float4 s[4];
+    unsigned long long* totals = p.gs.rows + (size_t)nb * VT;
+    for (int c4 = gw; c4 < VT / 4; c4 += nw) {
+      if (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4)) continue;
+      const unsigned long long* col = p.gs.rows + 4 * c4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      // kRows rows per lane with every load in flight (four where the registers allow it: the 4-lane instantiation); rows
+      // added in order
+      constexpr int kRows = L == 4 ? 4 : 2;
+      for (int r0 = lane; r0 < nb; r0 += 32 * kRows) {
+        unsigned long long x[kRows][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c4 = c0 + k * nw;
-        s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c4 >= VT / 4 || (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4))) continue;
-        const float4* col = reinterpret_cast<const float4*>(p.partials) + c4;
-        for (int r = lane; r < nb; r += 32) {
-          const float4 v = __ldcg(col + (size_t)r * (VT / 4));
-          s[k].x += v.x; s[k].y += v.y; s[k].z += v.z; s[k].w += v.w;
+        for (int u = 0; u < kRows; ++u) {
+          const int r = r0 + 32 * u;
+          if (r < nb) {
+            ld_relaxed_v2_u64(col + (size_t)r * VT, x[u][0], x[u][1]);
+            ld_relaxed_v2_u64(col + (size_t)r * VT + 2, x[u][2], x[u][3]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+          const int r = r0 + 32 * u;
+          if (r < nb) {
+            while ((unsigned int)(x[u][0] >> 32) != tag || (unsigned int)(x[u][1] >> 32) != tag ||
+                   (unsigned int)(x[u][2] >> 32) != tag || (unsigned int)(x[u][3] >> 32) != tag) {
+              ld_relaxed_v2_u64(col + (size_t)r * VT, x[u][0], x[u][1]);
+              ld_relaxed_v2_u64(col + (size_t)r * VT + 2, x[u][2], x[u][3]);
+            }
+            s.x += __uint_as_float((unsigned int)x[u][0]); s.y += __uint_as_float((unsigned int)x[u][1]);
+            s.z += __uint_as_float((unsigned int)x[u][2]); s.w += __uint_as_float((unsigned int)x[u][3]);
+          }
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c4 = c0 + k * nw;
-        if (c4 >= VT / 4 || (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4))) continue;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          s[k].x += __shfl_xor_sync(0xffffffffu, s[k].x, off); s[k].y += __shfl_xor_sync(0xffffffffu, s[k].y, off);
-          s[k].z += __shfl_xor_sync(0xffffffffu, s[k].z, off); s[k].w += __shfl_xor_sync(0xffffffffu, s[k].w, off);
-        }
-        if (lane == 0) __stcg(reinterpret_cast<float4*>(p.totals) + c4, s[k]);
+      for (int off = 16; off >= 1; off >>= 1) {
+        s.x += __shfl_xor_sync(0xffffffffu, s.x, off); s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_xor_sync(0xffffffffu, s.z, off); s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+      }
+      if (lane < 4) {
+        const float v = lane == 0 ? s.x : lane == 1 ? s.y : lane == 2 ? s.z : s.w;
+        st_relaxed_u64(totals + 4 * c4 + lane, (unsigned long long)__float_as_uint(v) | tag_hi);
       }
     }
-    grid_barrier(p.gs, ss);
     for (int c4 = tid; c4 < VT / 4; c4 += NT) {
       if (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4)) continue;
-      reinterpret_cast<float4*>(s_tot)[c4] = __ldcg(reinterpret_cast<const float4*>(p.totals) + c4);
+      unsigned long long a0, a1, a2, a3;
+      do {
+        ld_relaxed_v2_u64(totals + 4 * c4, a0, a1);
+        ld_relaxed_v2_u64(totals + 4 * c4 + 2, a2, a3);
+      } while ((unsigned int)(a0 >> 32) != tag || (unsigned int)(a1 >> 32) != tag || (unsigned int)(a2 >> 32) != tag ||
+               (unsigned int)(a3 >> 32) != tag);
+      reinterpret_cast<float4*>(s_tot)[c4] = make_float4(__uint_as_float((unsigned int)a0), __uint_as_float((unsigned int)a1),
+                                                         __uint_as_float((unsigned int)a2), __uint_as_float((unsigned int)a3));
     }
     __syncthreads();
   };
@@ -616,7 +645,8 @@ size_t dopri5_small_adjoint_workspace_bytes(int B, int D, int H) {
   (void)D; (void)H;
   using A = AdjLayout<16, 16, 8, kAdjWarps>;
   const int grid = adj_grid<16, 16, 8, kAdjWarps>(B);
-  return (size_t)GODE_SYNC_REGION_BYTES + align256(sizeof(float) * (size_t)grid * A::VT) + align256(sizeof(float) * A::VT);
+  (void)grid;
+  return (size_t)GODE_SYNC_REGION_BYTES;   // rows and totals of the per-attempt reduction live in the persistent region
 }
 
 template <int L, int MINB>
@@ -631,10 +661,9 @@ static int launch_adj(Dp5AdjArgs& a, void* workspace, size_t ws_bytes, cudaStrea
   static int limit_cache = 0;
   const int cap = coop_limit(kern, WARPS * 32, smem, limit_cache);
   if (cap <= 0 || grid > cap || grid > kSyncMaxGrid) return GODE_ERR_COOP;
+  if ((size_t)(grid + 1) * A::VT * sizeof(unsigned long long) > kSyncRowBytes) return GODE_ERR_COOP;
   char* base = reinterpret_cast<char*>(workspace);
   grid_sync_bind(a.gs, base);
-  a.partials = reinterpret_cast<float*>(ws_scratch(workspace));
-  a.totals = reinterpret_cast<float*>(ws_scratch(workspace) + align256(sizeof(float) * (size_t)grid * A::VT));
   void* args[] = {(void*)&a};
   e = cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(WARPS * 32), args, smem, st);
   if (e != cudaSuccess) return -(1000 + (int)e);

@@ -98,8 +98,9 @@ enum {
 #define GODE_SDE_MAX_CELLS 768     /* Brownian cells = distinct forward + reverse step end points (gode_sde_em_fwd_cells) */
 #define GODE_SDE_MAX_REV_STEPS 384 /* reverse steps of gode_sde_adjoint_bwd (the reference: 45)                        */
 /* persistent region at the front of every workspace: 256 KB of grid-sync words (counters, tagged all-reduce slots) followed by
- * 1280 KB of tagged parameter-gradient rows (the backward kernels' final reduction: 296 CTAs x 544 values x 8 bytes) */
-#define GODE_SYNC_REGION_BYTES (1536 * 1024)
+ * 6 MB of tagged rows: the backward kernels' final reduction (296 CTAs x 544 values x 8 bytes) and the per-attempt reduction
+ * of the continuous dopri5 adjoint (up to 296 CTAs x 2184 values x 8 bytes + one row of totals) */
+#define GODE_SYNC_REGION_BYTES (6400 * 1024)
 
 /* per-thread launch flags (gode_set_thread_launch_flags) */
 enum {
