@@ -268,9 +268,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
       if (c4 >= nvec * (P / 4) && c4 < kAdjNV * (P / 4)) continue;
       const unsigned long long* col = p.gs.rows + 4 * c4;
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      // kRows rows per lane with every load in flight (four where the registers allow it: the 4-lane instantiation); rows
+      // kRows rows per lane with every load in flight (four where the registers allow it: the 8- and 4-lane instantiations); rows
       // added in order
-      constexpr int kRows = L == 4 ? 4 : 2;
+      constexpr int kRows = L >= 4 ? 4 : 2;
       for (int r0 = lane; r0 < nb; r0 += 32 * kRows) {
         unsigned long long x[kRows][4];
 #pragma unroll
@@ -688,14 +688,12 @@ int dopri5_small_adjoint_bwd(const float* traj, const float* grad_traj, const fl
   // B = 4096 (scripts/dp5_adj_lanes.py).  Developer switch GODE_ADJ_LANES = '8' | '4' forces the first choice.
   const char* force = getenv("GODE_ADJ_LANES");
   const bool first8 = force ? force[0] == '8' : B <= 32 * sm_count();
-  int rc = first8 ? launch_adj<8, 2>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
+  // (one CTA per SM is all the 8-lane mapping is asked for — B <= 32 * SMs — so it is compiled for 255 registers; the
+  // two-per-SM, 128-register build it used to be spilled around the reduction)
+  int rc = first8 ? launch_adj<8, 1>(a, workspace, ws_bytes, st) : GODE_ERR_COOP;
   if (rc != GODE_ERR_COOP) return rc;
   rc = launch_adj<4, 1>(a, workspace, ws_bytes, st);
   if (rc != GODE_ERR_COOP) return rc;
-  if (!first8) {
-    rc = launch_adj<8, 2>(a, workspace, ws_bytes, st);
-    if (rc != GODE_ERR_COOP) return rc;
-  }
   return launch_adj<2, 1>(a, workspace, ws_bytes, st);  // 128 trajectories per CTA: holds 18 944
 }
 
