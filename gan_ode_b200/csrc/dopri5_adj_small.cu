@@ -31,6 +31,7 @@ constexpr int kAdjMaxT = 256;
 constexpr int kAdjWarps = 8;
 constexpr int kAdjNV = 4;  // reduced theta-shaped vectors: 0 = last stage (K7), 1 = solution combo, 2 = error combo, 3 = mid-point combo
 constexpr int kAdjNS = 8;  // reduced scalars (norm sums of the y / a parts, non-finite count)
+constexpr int kAdjStages = 6;  // stage derivatives k_2..k_7 evaluated per attempted step
 
 struct Dp5AdjArgs {
   const float *traj, *grad_traj, *W1, *b1, *W2, *b2;
@@ -108,7 +109,7 @@ struct AdjLayout {
   static_assert(VT % 4 == 0 && P % 4 == 0, "float4 columns");
   static constexpr int kSmemFloats = WARPS * BwdLines<D, H, L>::kFloatsPerWarp + ColWeights<D, H, L>::kFloats +
                                      SmemRowWeights<D, H, L>::kFloats +
-                                     kAdjNV * WARPS * P + 2 * P + VT + WARPS * kAdjNS + WARPS * 4;
+                                     (L == 8 ? kAdjStages : kAdjNV) * WARPS * P + 2 * P + VT + WARPS * kAdjNS + WARPS * 4;
   // native index n = lane*Q + q -> index in the flat [W1|b1|W2|b2] vector, tensor id 0..3
   __device__ static __forceinline__ int canon(int n, int& tensor) {
     const int lane = n / Q, q = n % Q, r = lane & 15;
@@ -133,8 +134,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
   float* s_lines = smem;
   float* s_cw = s_lines + WARPS * BL::kFloatsPerWarp;
   float* s_rw = s_cw + ColWeights<D, H, L>::kFloats;
-  float* s_acc = s_rw + SmemRowWeights<D, H, L>::kFloats;  // [kAdjNV][WARPS][P]
-  float* s_th = s_acc + kAdjNV * WARPS * P;            // theta_bar at the start of the current step (native order)
+  // Theta-part of the augmented stage derivatives, summed over the warp's trajectories.  Two layouts:
+  //   kSlots (8-lane mapping): one slot per stage k_2..k_7, [stage][WARPS][P]; the tableau combinations (solution, error,
+  //     mid-point) are formed once per attempt when the CTA's row is written — 17 stores per lane and stage instead of 51 loads
+  //     + 51 stores (stage glue 8.0k -> 3.9k cycles per attempt at B = 1024);
+  //   else (4- and 2-lane mappings): the combinations are accumulated stage by stage, [kAdjNV][WARPS][P].  With eight
+  //     trajectories per warp the slot layout measured SLOWER in total (+4 % at B = 8192: what the glue saved came back in the
+  //     stage evaluations), so it is kept for the mapping where it pays.
+  constexpr bool kSlots = L == 8;
+  float* s_k = s_rw + SmemRowWeights<D, H, L>::kFloats;
+  float* s_th = s_k + (kSlots ? kAdjStages : kAdjNV) * WARPS * P;   // theta_bar at the start of the current step (native order)
   float* s_k1 = s_th + P;                              // theta-part of the first stage (FSAL)
   float* s_tot = s_k1 + P;                             // [VT] grid totals of the last reduction
   float* s_sc = s_tot + VT;                            // [WARPS][kAdjNS]
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
   const float asign = -p.o.fsign;  // the adjoint runs against the forward direction
   SyncState ss;
   ss.begin(p.gs);
-  float* my_acc = s_acc + (size_t)warp * P + lane * Q;  // + vec * WARPS * P
+  float* my_k = s_k + (size_t)warp * P + lane * Q;  // + (stage or vector) * WARPS * P
 
 #ifdef GODE_ADJ_TIMING
   long long tc_stage = 0, tc_red = 0, tc_rest = 0, tc_f = 0, tc_v = 0, tc_t = 0, tc_a = 0, tc_mark = clock64();
@@ -233,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
   // owner has finished reading the rows of n; an owner writes total n+1 only after it has seen every CTA's row n+1, each
   // written after that CTA consumed the totals of n.  Tags count across launches (SyncState), rows are only ever written
   // as tagged words.
-  auto grid_reduce = [&](int nvec, float (&sc)[kAdjNS]) {
+  auto grid_reduce = [&](int nvec, float (&sc)[kAdjNS], float dt32) {
 #pragma unroll
     for (int k = 0; k < kAdjNS; ++k) {
 #pragma unroll
@@ -247,14 +256,56 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
     const unsigned int tag = ++ss.epoch;
     const unsigned long long tag_hi = (unsigned long long)tag << 32;
     unsigned long long* mine = p.gs.rows + (size_t)blockIdx.x * VT;
-    for (int n = tid; n < P; n += NT) {
-      for (int v = 0; v < nvec; ++v) {
-        const float* col = s_acc + (size_t)v * WARPS * P + n;
-        float x = col[0];
+    // tableau weights of the theta-part of k_j, j = st + 2 in 1-based stage numbering (k_1 carries zero weight in all three
+    // combinations): solution = row 5 of beta, error, mid-point
+    float wsol[kAdjStages], werr[kAdjStages], wmid[kAdjStages];
 #pragma unroll
-        for (int q = 1; q < WARPS; ++q) x += col[q * P];
-        st_relaxed_u64(mine + v * P + n, (unsigned long long)__float_as_uint(x) | tag_hi);
+    for (int st = 0; st < kAdjStages; ++st) {
+      wsol[st] = st < 5 ? kBeta[5][st + 1] * dt32 : 0.f;
+      werr[st] = kCErr[st + 1] * dt32;
+      wmid[st] = kCMid[st + 1] * dt32;
+    }
+    if constexpr (!kSlots) {
+      for (int n = tid; n < P; n += NT) {
+        for (int v = 0; v < nvec; ++v) {
+          const float* col = s_k + (size_t)v * WARPS * P + n;
+          float x = col[0];
+#pragma unroll
+          for (int q = 1; q < WARPS; ++q) x += col[q * P];
+          st_relaxed_u64(mine + v * P + n, (unsigned long long)__float_as_uint(x) | tag_hi);
+        }
       }
+    } else {
+    for (int n = tid; n < P; n += NT) {
+      // per warp: the combinations in stage order (zero, then one fma per stage: the order the per-stage accumulation had),
+      // then the warps in order
+      float xk = 0.f, xs = 0.f, xe = 0.f, xm = 0.f;
+#pragma unroll
+      for (int q = 0; q < WARPS; ++q) {
+        const float* col = s_k + (size_t)q * P + n;
+        const float k7 = col[(size_t)(kAdjStages - 1) * WARPS * P];
+        xk = q == 0 ? k7 : xk + k7;
+        if (nvec > 1) {
+          float as = 0.f, ae = 0.f, am = 0.f;
+#pragma unroll
+          for (int st = 0; st < kAdjStages; ++st) {
+            const float v = st == kAdjStages - 1 ? k7 : col[(size_t)st * WARPS * P];
+            as = fmaf(wsol[st], v, as);
+            ae = fmaf(werr[st], v, ae);
+            am = fmaf(wmid[st], v, am);
+          }
+          xs = q == 0 ? as : xs + as;
+          xe = q == 0 ? ae : xe + ae;
+          xm = q == 0 ? am : xm + am;
+        }
+      }
+      st_relaxed_u64(mine + n, (unsigned long long)__float_as_uint(xk) | tag_hi);
+      if (nvec > 1) {
+        st_relaxed_u64(mine + P + n, (unsigned long long)__float_as_uint(xs) | tag_hi);
+        st_relaxed_u64(mine + 2 * P + n, (unsigned long long)__float_as_uint(xe) | tag_hi);
+        if (nvec > 3) st_relaxed_u64(mine + 3 * P + n, (unsigned long long)__float_as_uint(xm) | tag_hi);
+      }
+    }
     }
     if (tid < kAdjNS) {
       float x = s_sc[tid];
@@ -383,7 +434,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
       eval_aug(u, ua, f1y, f1a, r2);
       nfe++;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) my_acc[q] = r2[q];
+      for (int q = 0; q < Q; ++q) my_k[(size_t)(kSlots ? kAdjStages - 1 : 0) * WARPS * P + q] = r2[q];
 #pragma unroll
       for (int k = 0; k < kAdjNS; ++k) sc[k] = 0.f;
       if (ph == 0) {
@@ -406,7 +457,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
           if (valid) { sc[0] += ry * ry; sc[1] += ra * ra; }
         }
       }
-      grid_reduce(1, sc);
+      grid_reduce(1, sc, 0.f);
       if (ph == 0) {
         for (int n = tid; n < P; n += NT) s_k1[n] = s_tot[n];
         if (s_tot[kAdjNV * P + 4] > 0.f) status |= GODE_ST_NONFINITE;
@@ -441,10 +492,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
       const double t1 = t0 + dt;
       const float dt32 = (float)dt;
       const bool fin = !(s_end > t1);
+      if constexpr (!kSlots) {
 #pragma unroll
-      for (int v = 1; v < kAdjNV; ++v) {
+        for (int v = 1; v < kAdjNV; ++v) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) my_acc[(size_t)v * WARPS * P + q] = 0.f;
+          for (int q = 0; q < Q; ++q) my_k[(size_t)v * WARPS * P + q] = 0.f;
+        }
       }
       GADJ_TICK(tc_rest);
       float u[S::DL], ua[S::DL];
@@ -476,8 +529,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
         }
         float kny[S::DL], kna[S::DL];
         eval_aug(u, ua, kny, kna, r2);
-        // k_j = this stage's derivative (0-based j = st + 1); tableau weights of its theta-part as compile-time constants
-        // (k_1 carries zero weight in all three combinations)
+        // tableau weights of this stage's theta-part as compile-time constants (a dynamically indexed table would be loads)
         float ws = 0.f, we = 0.f, wm = 0.f;
         auto stage_store = [&](auto ST) {
           constexpr int j = decltype(ST)::value + 1;
@@ -495,14 +547,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
           case 4: stage_store(std::integral_constant<int, 4>{}); break;
           default: stage_store(std::integral_constant<int, 5>{}); break;
         }
-        const int j = st + 1;
-        {  // all loads first, then the FMAs, then the stores: written as one += per element the chain was serialised
+        if constexpr (kSlots) {
+          // the stage's theta-part (this lane's 17 of the warp's 544 values) into its slot; combined when the row is written
+#pragma unroll
+          for (int q = 0; q < Q; ++q) my_k[(size_t)st * WARPS * P + q] = r2[q];
+        } else {
+          // k_j = this stage's derivative (0-based j = st + 1); k_1 carries zero weight in all three combinations.  All loads
+          // first, then the FMAs, then the stores: written as one += per element the chain was serialised
+          const int j = st + 1;
           float t1[Q], t2[Q], t3[Q];
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            t1[q] = my_acc[(size_t)1 * WARPS * P + q];
-            t2[q] = my_acc[(size_t)2 * WARPS * P + q];
-            t3[q] = my_acc[(size_t)3 * WARPS * P + q];
+            t1[q] = my_k[(size_t)1 * WARPS * P + q];
+            t2[q] = my_k[(size_t)2 * WARPS * P + q];
+            t3[q] = my_k[(size_t)3 * WARPS * P + q];
           }
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
@@ -512,14 +570,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
           }
 #pragma unroll
           for (int q = 0; q < Q; ++q) {
-            my_acc[(size_t)1 * WARPS * P + q] = t1[q];
-            my_acc[(size_t)2 * WARPS * P + q] = t2[q];
-            my_acc[(size_t)3 * WARPS * P + q] = t3[q];
+            my_k[(size_t)1 * WARPS * P + q] = t1[q];
+            my_k[(size_t)2 * WARPS * P + q] = t2[q];
+            my_k[(size_t)3 * WARPS * P + q] = t3[q];
           }
-        }
-        if (j == 6) {
+          if (j == 6) {
 #pragma unroll
-          for (int q = 0; q < Q; ++q) my_acc[q] = r2[q];
+            for (int q = 0; q < Q; ++q) my_k[q] = r2[q];
+          }
         }
       }
       nfe += 6;
@@ -542,7 +600,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dopri5_adjoint_bwd_kernel(co
         }
       }
       GADJ_TICK(tc_stage);
-      grid_reduce(fin ? 4 : 3, sc);
+      grid_reduce(fin ? 4 : 3, sc, dt32);
       GADJ_TICK(tc_red);
       const float* tK7 = s_tot;
       const float* tSol = s_tot + P;
