@@ -14,7 +14,10 @@ installable in this image.  This file therefore restates torchdiffeq's published
 algorithm (module paths cited per function) in plain PyTorch on CPU tensors, op
 for op, and is pinned by analytic / known-answer tests in
 `tests/test_oracle_pins.py` (expm, order-of-convergence slopes, Butcher order
-conditions, scipy RK45 cross-check, fp64 finite differences) — not by the real
+conditions, fp64 finite differences, and — for the adaptive solvers' tableau,
+error estimate, tolerance scale, batch-global norm and initial-step heuristic —
+SciPy's own Dormand-Prince / Bogacki-Shampine step pieces, equal to 1e-9 up to
+the documented 2/3 factor of the Shampine error weights) — not by the real
 package.  If `import torchdiffeq` ever succeeds, `tests/test_oracle_vs_real.py`
 compares the two and should be preferred.
 

@@ -212,6 +212,83 @@ def test_dopri5_vs_scipy_rk45_on_odefunc():
     assert np.abs(sol.detach().numpy().reshape(16, -1) - ref.y.T).max() < 1e-6
 
 
+def _scipy_first_attempt(RK, f, y0, rtol, atol, t_bound=1.0):
+    """SciPy's own pieces of an explicit adaptive Runge-Kutta step (scipy.integrate._ivp: select_initial_step, rk_step, the
+    method's tableau and error estimator, RMS norm) on the WHOLE batch as one state vector — the batch-global norm torchdiffeq
+    applies to a (B, D) state.  Returns (h0, y1, error_norm of the first attempted step)."""
+    from scipy.integrate._ivp import common, rk
+
+    B, D = y0.shape
+
+    def fun(tt, y):
+        with torch.no_grad():
+            return f(None, torch.from_numpy(y).view(B, D)).reshape(-1).numpy()
+
+    y = y0.reshape(-1).numpy().copy()
+    f0 = fun(0.0, y)
+    h0 = common.select_initial_step(fun, 0.0, y, t_bound, np.inf, f0, 1.0, RK.error_estimator_order, rtol, atol)
+    K = np.empty((RK.n_stages + 1, y.size))
+    y1, f1 = rk.rk_step(fun, 0.0, y, f0, h0, RK.A, RK.B, RK.C, K)
+    scale = atol + np.maximum(np.abs(y), np.abs(y1)) * rtol
+    err = common.norm(np.dot(K.T, RK.E) * h0 / scale)
+    return h0, y1, err
+
+
+@pytest.mark.parametrize("method,rk_name,scale", [("dopri5", "RK45", 1.0), ("dopri5", "RK45", 4.0), ("bosh3", "RK23", 2.0)])
+def test_adaptive_step_pieces_equal_scipys_independent_implementation(method, rk_name, scale):
+    """Algorithmic pin against an independent implementation that IS installed: SciPy's RK45 is the Dormand-Prince 5(4) pair
+    and RK23 the Bogacki-Shampine 3(2) pair torchdiffeq calls dopri5 / bosh3, and torchdiffeq's initial-step heuristic is
+    SciPy's (Hairer's).  In fp64 the restatement's first step size, the state after the first attempted step and its error
+    ratio equal what SciPy's own select_initial_step / rk_step / error estimator give on the same field — tableau, FSAL
+    bookkeeping, error weights, tolerance scale and the RMS norm over the whole batch all have to agree for that.
+    One documented difference: torchdiffeq's dopri5 is the Dormand-Prince-SHAMPINE tableau, whose error weights
+    (35/384 - 1951/21600, ...) are exactly 2/3 of the classical pair's b - b^ (35/384 - 5179/57600 = 71/57600 against 71/86400),
+    so its error ratio is 2/3 of SciPy's; bosh3's weights are SciPy's.  (The two CONTROLLERS differ by design: torchdiffeq never
+    shrinks an accepted step; the dense outputs differ too.)"""
+    from scipy.integrate._ivp import rk
+
+    RK = getattr(rk, rk_name)
+    k_err = {"dopri5": 1.5, "bosh3": 1.0}[method]            # SciPy's error estimate / torchdiffeq's
+    tab = {"dopri5": tdq.DOPRI5, "bosh3": tdq.BOSH3}[method]
+    assert np.allclose(np.abs(tab.c_error.numpy()) * k_err, np.abs(RK.E), rtol=1e-14, atol=0)
+    assert np.allclose(tab.c_sol.numpy()[:RK.n_stages], RK.B, rtol=1e-14, atol=1e-18)
+    torch.manual_seed(11)
+    f = ODEFunc(16, 16).double()
+    with torch.no_grad():
+        for p in f.parameters():
+            p.mul_(scale)
+    y0 = torch.randn(24, 16, dtype=torch.float64)
+    rtol, atol = 1e-5, 1e-6
+    h0, y1, err = _scipy_first_attempt(RK, f, y0, rtol, atol)
+    with torch.no_grad():
+        # the output time is the end of the first step: the dense output at x = 1 is y1 itself
+        sol = tdq.odeint(f, y0, torch.tensor([0.0, h0], dtype=torch.float64), method=method, rtol=rtol, atol=atol)
+    log = tdq.last_step_log()
+    assert abs(log.dt0 - h0) <= 1e-12 * h0, (log.dt0, h0)
+    assert abs(log.dt[0] - h0) <= 1e-12 * h0
+    # (after the heuristic's tiny first step the error estimate is ~1e-13 absolute: its own fp64 round-off is ~1e-7 of it)
+    assert abs(k_err * log.error_ratio[0] - err) <= 1e-6 * err, (log.error_ratio[0], err)
+    assert log.accepted[0] and np.abs(sol[1].numpy().reshape(-1) - y1).max() <= 1e-13 * np.abs(y1).max()
+    # ... and a forced over-long first step: same rejected-attempt error ratio
+    from scipy.integrate._ivp import common
+    B, D = y0.shape
+
+    def fun(tt, y):
+        with torch.no_grad():
+            return f(None, torch.from_numpy(y).view(B, D)).reshape(-1).numpy()
+
+    y = y0.reshape(-1).numpy().copy()
+    K = np.empty((RK.n_stages + 1, y.size))
+    big = 2.0
+    yb, _ = rk.rk_step(fun, 0.0, y, fun(0.0, y), big, RK.A, RK.B, RK.C, K)
+    errb = common.norm(np.dot(K.T, RK.E) * big / (atol + np.maximum(np.abs(y), np.abs(yb)) * rtol))
+    with torch.no_grad():
+        tdq.odeint(f, y0, torch.tensor([0.0, 1.0], dtype=torch.float64), method=method, rtol=rtol, atol=atol,
+                   options={"first_step": big})
+    log = tdq.last_step_log()
+    assert abs(k_err * log.error_ratio[0] - errb) <= 1e-9 * errb and log.accepted[0] == (errb <= k_err)
+
+
 def test_dopri5_step_sequence_is_independent_of_output_times():
     torch.manual_seed(6)
     f = ODEFunc(16, 16)
