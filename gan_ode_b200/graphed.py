@@ -1,7 +1,7 @@
 """CUDA-graph replay of one solve step (forward + backward + the host<->device copies around it).
 
 At the reference's shapes (D = H = 16, a few thousand trajectories) one fused solve is tens of microseconds of GPU
-time, so the host-side cost of *issuing* it (Python, autograd bookkeeping, two launches, two memsets, the copies)
+time, so the host-side cost of *issuing* it (Python, autograd bookkeeping, two launches, the copies)
 dominates unless the whole step is replayed from a graph.  `GraphedSolveStep` captures, once:
 
     H2D   y0 (pinned host)  ->  device

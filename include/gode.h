@@ -21,10 +21,12 @@
  *    never synchronises the device, and allocates nothing: outputs and workspaces come from
  *    the caller (PyTorch's caching allocator on the Python side).
  *  - WORKSPACES ARE PERSISTENT (v0.2): the first GODE_SYNC_REGION_BYTES of every `workspace`
- *    argument are the grid-synchronisation region.  The owner zero-fills it ONCE after allocation
- *    (gode_workspace_init) and may then pass the same workspace to any number of calls that are
- *    ordered on one stream; kernels leave it ready for the next launch (tags keep counting across
- *    launches), so no memset is enqueued per call.  Never share one workspace between launches
+ *    argument are the persistent region: grid-synchronisation words (counters, tagged all-reduce
+ *    slots) and the tagged rows through which the backward kernels and the continuous adjoint sum
+ *    parameter gradients over the grid without a barrier.  Only kernels of this library write there,
+ *    always as {value | tag} words whose tags keep counting across launches.  The owner zero-fills
+ *    it ONCE after allocation (gode_workspace_init) and may then pass the same workspace to any
+ *    number of calls that are ordered on one stream, so no memset is enqueued per call.  Never share one workspace between launches
  *    that can run concurrently (different streams, concurrently replayed graphs).
  *  - return value: 0 OK; <0 argument / capability error (gode_strerror); launch failures are
  *    returned as -(1000 + cudaError_t).  Solver conditions that are only known on the device
