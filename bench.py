@@ -13,8 +13,11 @@ backward of that batch.  trajectory-steps = B x ATTEMPTED dopri5 steps (accepted
 
 value     inputs resident in HBM; the step (2 kernels; the grid-sync workspace is persistent, so there are no memsets)
           replayed from CUDA graphs, K steps back to back over 20 distinct resident batches (together larger than L2, so
-          no flush kernel is needed and consecutive steps pipeline as in a training loop); one CUDA-event pair around the
-          K steps.  The isolated-step time (flush + event pair per step) is reported as run.latency_ms_per_step.
+          no flush kernel is needed); the graphs hold --steps-per-graph (10) consecutive steps each, as a training loop
+          that replays its inner loop from a graph would (inside a graph the kernel -> kernel gap is ~2 us, between two
+          graph launches ~6 us); one CUDA-event pair around the K steps.  Beside it: run.one_step_per_graph_ms_per_step
+          (the same K steps from single-step graphs, the round-1 definition) and run.latency_ms_per_step (isolated steps:
+          L2 flush + event pair per step).
 e2e       the same metric through the public replay API (gan_ode_b200.GraphedSolvePipeline, two steps in flight) with the
           batch's noise y0 in pinned HOST memory: H2D copy of y0, forward + backward and D2H read of the parameter
           gradients are inside the timed region, every step; e2e.serial_* is one step at a time (GraphedSolveStep run +
@@ -494,20 +497,56 @@ def run_gpu(args):
             sets = []
         gode.config.pdl = False
 
-    def throughput_region(k):
-        """K replays over the rotating batches, one event pair; returns (max-over-ranks ms, trajectory-steps of ALL ranks)."""
+    # The same steps captured SEVERAL PER GRAPH (a training loop that replays its inner loop from a graph does this): between two
+    # kernels of one graph the launch gap is ~2 us, between two graph launches on a stream ~6 us (scripts/
+    # multistep_graph_probe.py: 51.0 / 47.8 / 47.2 / 46.1 us per step at 1 / 2 / 4 / 8 steps per graph).  Group g replays the
+    # steps of batches g*S .. g*S+S-1; a K that is not a multiple of S finishes on the single-step graphs.
+    STEPS_PER_GRAPH = max(1, args.steps_per_graph)
+    groups = []   # (graph, attempted steps of its S batches)
+    if sets and STEPS_PER_GRAPH > 1:
+        try:
+            gode.config.pdl = args.pdl
+            for g0 in range(0, len(sets) - STEPS_PER_GRAPH + 1, STEPS_PER_GRAPH):
+                members = sets[g0:g0 + STEPS_PER_GRAPH]
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    torch.autograd.grad(gode.odeint(f, members[0][3], t, **kw), [members[0][3]] + params, members[0][4])
+                torch.cuda.current_stream().wait_stream(s_)
+                torch.cuda.synchronize()
+                gg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gg):
+                    keep_g = [torch.autograd.grad(gode.odeint(f, m[3], t, **kw), [m[3]] + params, m[4]) for m in members]
+                gg.replay()
+                torch.cuda.synchronize()
+                assert all(torch.equal(a_, b_) for kg, m in zip(keep_g, members) for a_, b_ in zip(kg, m[2])), \
+                    "multi-step graph disagrees with the single-step graphs"
+                groups.append((gg, sum(m[1] for m in members), keep_g))
+        except Exception as e:  # noqa: BLE001
+            sys.stderr.write("[bench] multi-step graphs unavailable ({}); one step per graph\n".format(str(e)[:200]))
+            groups = []
+        gode.config.pdl = False
+
+    def throughput_region(k, grouped=True):
+        """K steps over the rotating batches, one event pair; returns (max-over-ranks ms, trajectory-steps of ALL ranks)."""
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        use = groups if grouped else []
+        n_group_launches = (k // STEPS_PER_GRAPH) if use else 0
+        rest = k - n_group_launches * STEPS_PER_GRAPH
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         a.record()
-        for j in range(k):
+        for j in range(n_group_launches):
+            use[j % len(use)][0].replay()
+        for j in range(rest):
             sets[j % len(sets)][0].replay()
         b.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        units = float(B_PER_GPU * sum(sets[j % len(sets)][1] for j in range(k)))
+        units = float(B_PER_GPU * (sum(use[j % len(use)][1] for j in range(n_group_launches)) +
+                                   sum(sets[j % len(sets)][1] for j in range(rest))))
         tt = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
         uu = torch.tensor([units], device=dev, dtype=torch.float64)
         if world > 1:
@@ -519,9 +558,12 @@ def run_gpu(args):
         run_step()
     sampler = ClockSampler(local) if rank == 0 else None
     latency_ms = timed_region(run_step, args.steps)
+    single_ms = None
     if sets:
-        throughput_region(max(3, args.warmup))
+        throughput_region(max(3, args.warmup) * STEPS_PER_GRAPH)
         total_ms, total_units = throughput_region(args.steps)
+        if groups:
+            single_ms, _ = throughput_region(args.steps, grouped=False)
     else:
         total_ms, total_units = latency_ms, None
     eager_ms = timed_region(step, args.steps) if graph is not None else latency_ms
@@ -558,17 +600,18 @@ def run_gpu(args):
                     alone[j % len(alone)][0].replay()
                 b.record()
                 torch.cuda.synchronize()
+            with_x = single_ms if single_ms is not None else total_ms    # like for like: one step per graph on both sides
             mine = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
             every = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(every, mine)
             per_rank = [float(x.item()) for x in every]
-            skew = {"what": "same {} replays over the same batches WITHOUT the gradient exchange, every rank alone; "
-                            "ms per step".format(args.steps),
+            skew = {"what": "same {} single-step graph replays over the same batches WITHOUT the gradient exchange, every rank "
+                            "alone; ms per step".format(args.steps),
                     "no_exchange_ms_per_step_per_rank": per_rank,
                     "no_exchange_slowest_rank_ms": max(per_rank), "no_exchange_fastest_rank_ms": min(per_rank),
-                    "with_exchange_ms_per_step": total_ms / args.steps,
+                    "with_exchange_ms_per_step": with_x / args.steps,
                     "rank_skew_us": (max(per_rank) - min(per_rank)) * 1e3,
-                    "exchange_cost_over_slowest_rank_us": (total_ms / args.steps - max(per_rank)) * 1e3}
+                    "exchange_cost_over_slowest_rank_us": (with_x / args.steps - max(per_rank)) * 1e3}
             del alone
         except Exception as e:  # noqa: BLE001
             skew = {"error": str(e)[:200]}
@@ -837,8 +880,14 @@ def run_gpu(args):
         "data": "synthetic", "config": config_for(n_gpus),
         "run": {"cuda_graph": graphed, "attempted_steps": n_att, "accepted_steps": n_acc,
                 "timing": ("{} steps replayed back to back over {} distinct resident batches (no flush kernel; one CUDA-event "
-                           "pair around all steps)".format(args.steps, len(sets)) if sets else
+                           "pair around all steps); {}".format(
+                               args.steps, len(sets),
+                               "CUDA graphs of {} consecutive steps each ({} graph launches + {} single-step graphs)".format(
+                                   STEPS_PER_GRAPH, args.steps // STEPS_PER_GRAPH, args.steps % STEPS_PER_GRAPH)
+                               if groups else "one CUDA graph per step") if sets else
                            "isolated steps: L2 flush + one CUDA-event pair per step"),
+                "steps_per_graph": STEPS_PER_GRAPH if groups else 1,
+                "one_step_per_graph_ms_per_step": (single_ms / args.steps) if single_ms is not None else None,
                 "attempted_steps_per_batch": [x[1] for x in sets] if sets else [n_att],
                 "latency_ms_per_step": latency_ms / args.steps,
                 "latency_value": units / (latency_ms / args.steps * 1e-3),
@@ -878,6 +927,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
     ap.add_argument("--grad-exchange", choices=("fused", "p2p", "nccl"), default="fused",
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
+    ap.add_argument("--steps-per-graph", type=int, default=10, help="value: consecutive steps captured per CUDA graph "
+                    "(1: one graph per step, the round-1 definition; reported beside the value either way)")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one step at a time (GraphedSolveStep run + sync) "
                     "instead of two steps in flight")
     ap.add_argument("--require-grad-exchange", action="store_true", help="N>1: fail instead of falling back when the "
