@@ -519,6 +519,56 @@ def test_graphed_pipeline_returns_every_step_in_order():
         assert torch.equal(gy, wy) and torch.equal(gp, wp)
 
 
+def test_round2_kernels_replay_from_cuda_graphs():
+    """The kernels added in round 2 under graph replay, bit-equal to the eager calls: wide-field dopri5 (its backward workspace
+    holds the gradient rows: larger than the pooled workspaces, so it is created inside the capture), the persistent ODE-RNN
+    forward with its per-frame backward, and the continuous adjoint with its barrier-free reduction (tags keep counting
+    across replays)."""
+    _need_gpu()
+    t = _t16()
+    f = clone_to(make_field(64, 256, seed=0), DEV)
+    B = 96
+    kw = dict(method="dopri5", rtol=1e-5, atol=1e-5, options={"ckpt_capacity": 16})
+    gs = gode.GraphedSolveStep(f, B, t, adjoint=False, read_back=("param_grads", "grad_y0", "traj"), **kw)
+    for seed in (0, 1):
+        torch.manual_seed(seed)
+        y0, g = torch.randn(B, 64), torch.randn(16, B, 64)
+        gs.grad_traj.copy_(g)
+        gs.run(y0)
+        host = gs.sync()
+        y = y0.to(DEV).requires_grad_(True)
+        sol = gode.odeint(f, y, t, **kw)
+        grads = torch.autograd.grad(sol, [y] + list(f.parameters()), g.to(DEV))
+        assert torch.equal(host["traj"], sol.detach().cpu()) and torch.equal(host["grad_y0"], grads[0].cpu())
+        assert torch.equal(host["param_grads"], torch.cat([x.reshape(-1) for x in grads[1:]]).cpu())
+
+    def replayed(fn):
+        ref = fn()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            out = fn()
+        for _ in range(3):
+            gr.replay()
+        torch.cuda.synchronize()
+        return all(torch.equal(a, b) for a, b in zip(out, ref))
+
+    f16 = clone_to(make_field(seed=1), DEV)
+    gru = torch.nn.GRUCell(16, 16).to(DEV)
+    h0 = torch.randn(512, 16, device=DEV, requires_grad=True)
+    eps, w = torch.randn(8, 512, 16, device=DEV), torch.randn(8, 512, 16, device=DEV)
+    params = list(f16.parameters()) + list(gru.parameters())
+    assert replayed(lambda: torch.autograd.grad(gode.odernn_codes(f16, gru, h0, eps), [h0] + params, w))
+    y0 = torch.randn(300, 16, device=DEV, requires_grad=True)
+    gg, t2 = torch.randn(2, 300, 16, device=DEV), torch.tensor([0.0, 1.0])
+    assert replayed(lambda: torch.autograd.grad(gode.odeint_adjoint(f16, y0, t2), [y0] + list(f16.parameters()), gg))
+
+
 # ---- drop-in: the reference's call pattern through the torchdiffeq shim ------------------------------------------------
 def test_dropin_shim_caller_forward_backward(monkeypatch):
     """`from torchdiffeq import odeint_adjoint as odeint` (models/mocogan_ode.py:4) resolved by install_shims();
