@@ -711,6 +711,14 @@ def run_gpu(args):
         return res_host
 
     e2e_eager_s = e2e_time(e2e_eager_step, args.steps)
+    # the same call with autograd's worker threads off (torch.autograd.set_multithreading_enabled(False)): the CUDA backward
+    # node then runs on the calling thread instead of being handed to the engine's device thread and back
+    e2e_eager_st_s = None
+    try:
+        with torch.autograd.set_multithreading_enabled(False):
+            e2e_eager_st_s = e2e_time(e2e_eager_step, args.steps)
+    except Exception:  # noqa: BLE001
+        pass
     if e2e_s is None:
         e2e_s, e2e_api = e2e_eager_s, "gan_ode_b200.odeint (eager, pinned host y0)"
     clocks = sampler.stop() if sampler else None
@@ -906,7 +914,8 @@ def run_gpu(args):
                 "serial_ms_per_step": (e2e_serial_s / args.steps * 1e3) if e2e_serial_s else None,
                 "serial_value": (units / (e2e_serial_s / args.steps)) if e2e_serial_s else None,
                 "serial_api": "gan_ode_b200.GraphedSolveStep.run() + .sync() per step (no overlap between steps)",
-                "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3},
+                "eager_api_value": units / (e2e_eager_s / args.steps), "eager_api_ms_per_step": e2e_eager_s / args.steps * 1e3,
+                "eager_api_autograd_single_thread_ms_per_step": (e2e_eager_st_s / args.steps * 1e3) if e2e_eager_st_s else None},
         "gpu_launches": (2 + (1 if n_gpus > 1 and gode.config.grad_exchange is None and callable(gode.config.grad_allreduce)
                               else 0)) * args.steps,
         "eager_ms_per_step": eager_ms / args.steps,

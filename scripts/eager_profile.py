@@ -60,6 +60,16 @@ for _ in range(N):
 print("issue H2D %.1f | odeint %.1f | autograd.grad %.1f | cat + D2H %.1f | final sync wait %.1f  (us)" %
       tuple(x / N * 1e6 for x in acc))
 
+# the same with autograd's worker threads off: the CUDA backward node then runs on the calling thread (no hand-off to the
+# engine's device thread and back)
+with torch.autograd.set_multithreading_enabled(False):
+    for _ in range(20):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(N):
+        step()
+    print("eager step, torch.autograd.set_multithreading_enabled(False): %.1f us" % ((time.perf_counter() - t0) / N * 1e6))
+
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(N):
