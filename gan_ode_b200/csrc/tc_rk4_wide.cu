@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t tcw2_hcol(int c) { return 8u * c; }
 #define GODE_TANH_FMA_EVERY 1000
 #endif
 // Measured (round 2, scripts/tanh_poly_probe.py; B = 18 944 / 151 552): all MUFU 184.7 / 817.5 us, one pair in 4 on the FMA pipe
-// 176.5 / 797.1 us, one in 3: 176.7 / 806.3 us, one in 2: 182.5 / 870.8 us; error against the FP32 solve unchanged (3.5e-4).
+// 176.5 / 797.1 us, one in 3 (also two of a chunk's eight pairs): 176.7 / 806.3 us, one in 2: 182.5 / 870.8 us; error against the FP32 solve unchanged (3.5e-4).
 // The epilogue is not bound by MUFU throughput alone: with two epilogue warps per scheduler the twelve extra issue slots of
 // a polynomial pair are only partly hidden, so a quarter is the most that pays.
 constexpr int kTanhPolyDefault = 4;   // GODE_TANH_POLY_EVERY default (0: every tanh on the MUFU pipe)
