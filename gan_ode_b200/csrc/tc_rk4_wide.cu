@@ -71,17 +71,18 @@ __device__ __forceinline__ uint32_t tcw2_hcol(int c) { return 8u * c; }
 #ifndef GODE_TANH_FMA_EVERY
 #define GODE_TANH_FMA_EVERY 1000
 #endif
-// Measured (round 2, scripts/tanh_poly_probe.py; B = 18 944 / 151 552): all MUFU 184.7 / 817.5 us, one pair in 4 on the FMA pipe
-// 176.5 / 797.1 us, one in 3 (also two of a chunk's eight pairs): 176.7 / 806.3 us, one in 2: 182.5 / 870.8 us; error against the FP32 solve unchanged (3.5e-4).
-// The epilogue is not bound by MUFU throughput alone: with two epilogue warps per scheduler the twelve extra issue slots of
-// a polynomial pair are only partly hidden, so a quarter is the most that pays.
-constexpr int kTanhPolyDefault = 4;   // GODE_TANH_POLY_EVERY default (0: every tanh on the MUFU pipe)
+// Measured (round 2, scripts/tanh_poly_probe.py, two runs; B = 18 944 / 151 552, us): pairs of every eight on the FMA pipe
+//   0: 182.7 / 815.5    1: 178.2 / 784.8    2: 176.6 / 798.2    3: 174.4 / 836.0    4: 180.7 / 870.8
+// error against the FP32 solve 3.4e-4 -> 3.5e-4 (N = 1).  The epilogue is not bound by MUFU throughput alone: with two epilogue
+// warps per scheduler the twelve extra issue slots of a polynomial pair are only partly hidden; one pair in eight is the best
+// trade in the throughput regime (759 TFLOP/s = 0.56 of the sustained BF16 GEMM rate), three at one tile per SM.
+constexpr int kTanhPolyDefault = 1;   // GODE_TANH_POLY_N default: pairs of every eight on the FMA pipe (0: none)
 constexpr int kTanhFmaEvery = GODE_TANH_FMA_EVERY;  // one pair in every kTanhFmaEvery goes to the FMA pipe (1000: none).
 // Measured (B = 151 552): none 844 us, every 4th pair 858 us, every 2nd pair 930 us -- the extra ~11 issue slots per pair
 // cost more than the MUFU cycles they free with only two epilogue warps per scheduler, so the default is OFF.
 
-// POLY_EVERY: one pair of tanh in every POLY_EVERY is evaluated by tc::tanh_pair_poly on the FMA pipe (no MUFU op); 1000: none
-template <int D, int H, int POLY_EVERY>
+// POLY_N: of the eight tanh pairs of a 16-column chunk, this many are evaluated by tc::tanh_pair_poly on the FMA pipe (no MUFU op)
+template <int D, int H, int POLY_N>
 __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_constant__ TcWideArgs p) {
   using S = TcWide2Shape<D, H>;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(512, 1) tc_rk4_fwd_wide2_kernel(const __grid_c
       if ((i / 2) % kTanhFmaEvery == kTanhFmaEvery - 1) {  // this pair on the FMA pipe + one MUFU.RCP (tc_common.cuh)
         const float2 th = tc::tanh_pair_fma(__uint_as_float(z[i]), __uint_as_float(z[i + 1]));
         q[i / 2] = tc::pack_bf16x2(th.x, th.y);
-      } else if ((i / 2) % POLY_EVERY == POLY_EVERY - 1) {  // this pair on the FMA pipe alone (polynomial)
+      } else if ((i / 2) % 2 == 1 ? (i / 4) < POLY_N : (i / 4) + 4 < POLY_N) {  // this pair on the FMA pipe alone (polynomial):
+        // the odd pairs first, so that polynomial and MUFU pairs alternate in the instruction stream
         const float2 th = tc::tanh_pair_poly(__uint_as_float(z[i]), __uint_as_float(z[i + 1]));
         q[i / 2] = tc::pack_bf16x2(th.x, th.y);
       } else {
@@ -346,17 +348,18 @@ int tc_rk4_fwd_wide(const float* y0, const float* W1, const float* b1, const flo
   const int ntiles = (B + S2::TILE - 1) / S2::TILE;
   int grid = sm_count();
   if (grid > ntiles) grid = ntiles;
-  // share of the tanh evaluations moved from the MUFU pipe to the FMA pipe (polynomial): developer switch GODE_TANH_POLY_EVERY
-  // = 2 / 3 / 4 (one pair in every 2 / 3 / 4) or 0 (none); default: see profiles/README.md round 2
-  static int poly_every = -1;
-  if (poly_every < 0) {
-    const char* pe = getenv("GODE_TANH_POLY_EVERY");
-    poly_every = pe ? atoi(pe) : kTanhPolyDefault;
+  // share of the tanh evaluations moved from the MUFU pipe to the FMA pipe (polynomial): developer switch GODE_TANH_POLY_N =
+  // 0..4 pairs of every eight; default: see profiles/README.md round 2
+  static int poly_n = -1;
+  if (poly_n < 0) {
+    const char* pe = getenv("GODE_TANH_POLY_N");
+    poly_n = pe ? atoi(pe) : kTanhPolyDefault;
   }
-  auto kern = poly_every == 2 ? tc_rk4_fwd_wide2_kernel<64, 256, 2>
-              : poly_every == 3 ? tc_rk4_fwd_wide2_kernel<64, 256, 3>
-              : poly_every == 4 ? tc_rk4_fwd_wide2_kernel<64, 256, 4>
-                                : tc_rk4_fwd_wide2_kernel<64, 256, 1000>;
+  auto kern = poly_n == 1 ? tc_rk4_fwd_wide2_kernel<64, 256, 1>
+              : poly_n == 2 ? tc_rk4_fwd_wide2_kernel<64, 256, 2>
+              : poly_n == 3 ? tc_rk4_fwd_wide2_kernel<64, 256, 3>
+              : poly_n == 4 ? tc_rk4_fwd_wide2_kernel<64, 256, 4>
+                            : tc_rk4_fwd_wide2_kernel<64, 256, 0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::BYTES);
   if (e != cudaSuccess) return -(1000 + (int)e);
 #ifdef GODE_TCW_TIMING

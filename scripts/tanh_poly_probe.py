@@ -1,4 +1,4 @@
-"""Wide tensor-core forward with a share of the tanh evaluations on the FMA pipe (GODE_TANH_POLY_EVERY, read once per process):
+"""Wide tensor-core forward with a share of the tanh evaluations on the FMA pipe (GODE_TANH_POLY_N = pairs of every eight, read once per process):
 time at two batch sizes and error against the FP32 wide forward.   python scripts/tanh_poly_probe.py"""
 import json
 import os
@@ -7,8 +7,8 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 if len(sys.argv) == 1:
-    for pe in ("0", "4", "3", "2"):
-        env = dict(os.environ, GODE_TANH_POLY_EVERY=pe)
+    for pe in ("0", "1", "2", "3", "4"):
+        env = dict(os.environ, GODE_TANH_POLY_N=pe)
         r = subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True)
         print(pe, r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-400:])
     sys.exit(0)
