@@ -489,6 +489,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
   // return NaN gradients instead of silently truncated ones (the host does not sync to look at the status).
   const float poison = log_status != 0 ? __int_as_float(0x7fc00000) : 0.f;
   acc.fill(poison);
+  GODE_TP(1, 52);
   const int stride = gridDim.x * WARPS * S::G;
   for (int base = (blockIdx.x * WARPS + warp) * S::G; base < p.B; base += stride) {
     const int b = base + g;
@@ -514,6 +515,7 @@ __global__ void __launch_bounds__(WARPS * 32) dopri5_backprop_bwd_kernel(const _
       t0n = p.acc_t0[n_acc - 1]; dtn = p.acc_dt[n_acc - 1];
       if (valid) load_frag<S::DL>(p.ckpt + ((size_t)(n_acc - 1) * p.B + b) * D + l * S::DL, y0n);
     }
+    GODE_TP(1, 53);
     if (staged) {
       cp_async_wait_all();
       __syncwarp();

@@ -68,7 +68,7 @@ for pdl in (False, True):
         names_f[5 + 3 * a] = "att%d reduced" % a
         names_f[6 + 3 * a] = "att%d end" % a
     names_b = {0: "entry", 1: "row weights loaded", 2: "griddep_wait + log read", 50: "grad copies issued", 51: "column weights staged",
-               3: "CTA barrier", 4: "grads staged", 30: "replay done", 32: "reduce: warp sums in smem", 33: "reduce: CTA partial stored", 36: "reduce: LAST CTA's partial stored",
+               3: "CTA barrier", 52: "accumulators cleared", 53: "first checkpoint load issued", 4: "grads staged", 30: "replay done", 32: "reduce: warp sums in smem", 33: "reduce: CTA partial stored", 36: "reduce: LAST CTA's partial stored",
                34: "reduce: grid barrier passed", 31: "exit"}
     for st in range(4):
         names_b[5 + 2 * st] = "step%d begin" % st
