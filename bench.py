@@ -18,7 +18,8 @@ value     inputs resident in HBM; the step (2 kernels; the grid-sync workspace i
           graph launches ~6 us); one CUDA-event pair around the K steps.  Beside it: run.one_step_per_graph_ms_per_step
           (the same K steps from single-step graphs, the round-1 definition) and run.latency_ms_per_step (isolated steps:
           L2 flush + event pair per step).
-e2e       the same metric through the public replay API (gan_ode_b200.GraphedSolvePipeline, two steps in flight) with the
+e2e       the same metric through the public replay API (gan_ode_b200.GraphedSolvePipeline, two slots in flight, five steps
+          per slot / graph launch; e2e.one_step_per_slot_ms_per_step beside it) with the
           batch's noise y0 in pinned HOST memory: H2D copy of y0, forward + backward and D2H read of the parameter
           gradients are inside the timed region, every step; e2e.serial_* is one step at a time (GraphedSolveStep run +
           sync), e2e.eager_api_* the plain eager odeint + autograd call the reference makes.
@@ -640,6 +641,7 @@ def run_gpu(args):
     y0_host = y0.cpu().pin_memory()
     n_param = sum(p.numel() for p in params)
     e2e_serial_s = None
+    e2e_one_s = None
     e2e_api = "gan_ode_b200.GraphedSolveStep (H2D y0 + odeint fwd + backprop + D2H param grads, one graph launch, sync)"
     try:
         if args.no_graph:
@@ -670,19 +672,41 @@ def run_gpu(args):
             chk = pipe.result()["param_grads"].to(dev)
             assert torch.allclose(chk, ref_flat, rtol=1e-4, atol=1e-6), "pipelined e2e step disagrees with the eager step"
 
-            def e2e_pipelined(k):
-                n_read = 0
-                for _ in range(k):
-                    if len(pipe._inflight) == len(pipe.slots):
-                        pipe.result()
-                        n_read += 1
-                    pipe.submit()
-                while pipe._inflight:
-                    pipe.result()
-                    n_read += 1
-                assert n_read == k
+            # ... and with E2E_S steps per slot (one graph launch carries E2E_S steps, each with its own input batch in the
+            # pinned block and its own gradient read back): the launch gap between graphs is amortised as in `value`
+            E2E_S = max(1, args.e2e_steps_per_slot)
+            pipe_s = None
+            if E2E_S > 1:
+                pipe_s = gode.GraphedSolvePipeline(f, B_PER_GPU, t, depth=2, adjoint=False, read_back=("param_grads",),
+                                                   pdl=args.pdl, steps=E2E_S, **kw)
+                for sl in pipe_s.slots:
+                    for k_ in range(E2E_S):
+                        sl.y0_host[k_].copy_(y0_host)
+                        sl.grad_traj[k_].copy_(grad)
+                pipe_s.submit()
+                chk = pipe_s.result()["param_grads"].to(dev)
+                assert all(torch.allclose(chk[k_], ref_flat, rtol=1e-4, atol=1e-6) for k_ in range(E2E_S)), \
+                    "multi-step pipelined e2e disagrees with the eager step"
 
-            e2e_pipelined(6)
+            def drive(pp, n_submit):
+                n_read = 0
+                for _ in range(n_submit):
+                    if len(pp._inflight) == len(pp.slots):
+                        pp.result()
+                        n_read += 1
+                    pp.submit()
+                while pp._inflight:
+                    pp.result()
+                    n_read += 1
+                assert n_read == n_submit
+
+            def e2e_pipelined(k):
+                n_groups = (k // E2E_S) if pipe_s is not None else 0
+                if n_groups:
+                    drive(pipe_s, n_groups)
+                drive(pipe, k - n_groups * E2E_S)
+
+            e2e_pipelined(3 * E2E_S + 2)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
@@ -693,9 +717,23 @@ def run_gpu(args):
             if world > 1:
                 dist.all_reduce(te, op=dist.ReduceOp.MAX)
             e2e_s = float(te.item())
-            e2e_api = ("gan_ode_b200.GraphedSolvePipeline, 2 steps in flight (per step: H2D y0 from pinned host, odeint fwd + "
-                       "backprop as one graph launch, D2H param grads, result read on the host; step i+1's H2D overlaps "
-                       "step i's kernels)")
+            e2e_api = ("gan_ode_b200.GraphedSolvePipeline, 2 slots in flight, {} step(s) per slot (per step: H2D of its y0 from "
+                       "pinned host, odeint fwd + backprop, D2H of its param grads, result read on the host; a slot's H2D "
+                       "overlaps the previous slot's kernels; {} slot launches + {} single-step launches)".format(
+                           E2E_S if pipe_s is not None else 1, (args.steps // E2E_S) if pipe_s is not None else 0,
+                           args.steps - ((args.steps // E2E_S) * E2E_S if pipe_s is not None else 0)))
+            # the single-step-per-slot figure beside it
+            e2e_one_s = None
+            if pipe_s is not None:
+                drive(pipe, 6)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                drive(pipe, args.steps)
+                torch.cuda.synchronize()
+                te = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+                e2e_one_s = float(te.item())
     except Exception as e:  # noqa: BLE001
         sys.stderr.write("[bench] GraphedSolveStep unavailable ({}); e2e falls back to the eager API\n".format(str(e)[:200]))
         e2e_s = None
@@ -911,6 +949,7 @@ def run_gpu(args):
         "parity_check": parity,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s / args.steps * 1e3, "api": e2e_api,
+                "one_step_per_slot_ms_per_step": (e2e_one_s / args.steps * 1e3) if e2e_one_s else None,
                 "serial_ms_per_step": (e2e_serial_s / args.steps * 1e3) if e2e_serial_s else None,
                 "serial_value": (units / (e2e_serial_s / args.steps)) if e2e_serial_s else None,
                 "serial_api": "gan_ode_b200.GraphedSolveStep.run() + .sync() per step (no overlap between steps)",
@@ -938,6 +977,8 @@ def main():
                     help="N>1: how the parameter gradient is summed over ranks (default: inside the backward kernel)")
     ap.add_argument("--steps-per-graph", type=int, default=10, help="value: consecutive steps captured per CUDA graph "
                     "(1: one graph per step, the round-1 definition; reported beside the value either way)")
+    ap.add_argument("--e2e-steps-per-slot", type=int, default=5, help="e2e: steps carried by one pipeline slot / graph launch "
+                    "(each with its own H2D input and D2H result); 1: one step per launch")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: one step at a time (GraphedSolveStep run + sync) "
                     "instead of two steps in flight")
     ap.add_argument("--require-grad-exchange", action="store_true", help="N>1: fail instead of falling back when the "

@@ -45,7 +45,10 @@ class GraphedSolveStep:
     def __init__(self, func, batch: int, t: torch.Tensor, *, method: Optional[str] = None, rtol=1e-7, atol=1e-9,
                  adjoint: bool = True, options: Optional[dict] = None, device=None,
                  read_back: Sequence[str] = ("param_grads",), warmup: int = 3, pdl: bool = False,
-                 copies_in_graph: bool = True):
+                 copies_in_graph: bool = True, steps: int = 1):
+        """steps = S > 1: ONE graph holds S consecutive steps, each with its own input batch, upstream gradient and results
+        (buffers get a leading S dimension: y0_host (S,B,D), grad_traj (S,T,B,D), host[...] (S,...)).  Between two kernels of
+        one graph the launch gap is ~2 us, between two graph launches ~6 us, so S steps per launch amortise it."""
         W1, _, _, _ = _api.recognise_field(func)
         D = W1.shape[1]
         dev = torch.device(device) if device is not None else W1.device
@@ -61,17 +64,26 @@ class GraphedSolveStep:
             if name not in ("param_grads", "grad_y0", "traj"):
                 raise ValueError("read_back entries must be 'param_grads', 'grad_y0' or 'traj'")
 
-        # static buffers: pinned host side and device side
-        self.y0_host = torch.zeros(batch, D, dtype=torch.float32).pin_memory()
-        self.y0 = torch.zeros(batch, D, dtype=torch.float32, device=dev, requires_grad=True)
-        self.grad_traj = torch.zeros(T, batch, D, dtype=torch.float32, device=dev)
-        self.host = {}
+        # static buffers: pinned host side and device side (a leading `steps` dimension, dropped for steps == 1)
+        S = self.steps = int(steps)
+        assert S >= 1
+
+        def lead(x):
+            return x[0] if S == 1 else x
+
+        self._y0_host_all = torch.zeros(S, batch, D, dtype=torch.float32).pin_memory()
+        self._y0_all = torch.zeros(S, batch, D, dtype=torch.float32, device=dev)      # one H2D fills every step's input
+        self._y0_steps = [self._y0_all[k].detach().requires_grad_(True) for k in range(S)]   # leaves sharing that storage
+        self._grad_traj_all = torch.zeros(S, T, batch, D, dtype=torch.float32, device=dev)
+        self.y0_host, self.y0, self.grad_traj = lead(self._y0_host_all), self._y0_steps[0], lead(self._grad_traj_all)
+        self._host_all = {}
         if "param_grads" in self.read_back:
-            self.host["param_grads"] = torch.zeros(n_param, dtype=torch.float32).pin_memory()
+            self._host_all["param_grads"] = torch.zeros(S, n_param, dtype=torch.float32).pin_memory()
         if "grad_y0" in self.read_back:
-            self.host["grad_y0"] = torch.zeros(batch, D, dtype=torch.float32).pin_memory()
+            self._host_all["grad_y0"] = torch.zeros(S, batch, D, dtype=torch.float32).pin_memory()
         if "traj" in self.read_back:
-            self.host["traj"] = torch.zeros(T, batch, D, dtype=torch.float32).pin_memory()
+            self._host_all["traj"] = torch.zeros(S, T, batch, D, dtype=torch.float32).pin_memory()
+        self.host = {k: lead(v) for k, v in self._host_all.items()}
         self.traj = None
         self.grads = None
         self.log = None
@@ -102,24 +114,26 @@ class GraphedSolveStep:
     def _body(self):
         if self.copies_in_graph:
             self.copy_in()
-        sol = self._solve(self.func, self.y0, self.t, **self._kw)
-        self.log = _api.last_step_log() if (self._kw["method"] in (None, "dopri5")) else None
-        grads = torch.autograd.grad(sol, [self.y0] + self.params, self.grad_traj)
-        self.traj, self.grads = sol.detach(), grads
         self._d2h = []
-        if "param_grads" in self.host:
-            self._d2h.append((self.host["param_grads"], _flat_param_grads(grads[1:])))
-        if "grad_y0" in self.host:
-            self._d2h.append((self.host["grad_y0"], grads[0]))
-        if "traj" in self.host:
-            self._d2h.append((self.host["traj"], sol.detach()))
+        for k in range(self.steps):
+            y0 = self._y0_steps[k]
+            sol = self._solve(self.func, y0, self.t, **self._kw)
+            self.log = _api.last_step_log() if (self._kw["method"] in (None, "dopri5")) else None
+            grads = torch.autograd.grad(sol, [y0] + self.params, self._grad_traj_all[k])
+            self.traj, self.grads = sol.detach(), grads      # (of the last step)
+            if "param_grads" in self._host_all:
+                self._d2h.append((self._host_all["param_grads"][k], _flat_param_grads(grads[1:])))
+            if "grad_y0" in self._host_all:
+                self._d2h.append((self._host_all["grad_y0"][k], grads[0]))
+            if "traj" in self._host_all:
+                self._d2h.append((self._host_all["traj"][k], sol.detach()))
         if self.copies_in_graph:
             self.copy_out()
 
     def copy_in(self):
         """H2D of the pinned input on the current stream (a graph node when captured)."""
         with torch.no_grad():
-            self.y0.copy_(self.y0_host, non_blocking=True)
+            self._y0_all.copy_(self._y0_host_all, non_blocking=True)
 
     def copy_out(self):
         """D2H of the requested results on the current stream (graph nodes when captured)."""

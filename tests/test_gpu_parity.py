@@ -519,6 +519,46 @@ def test_graphed_pipeline_returns_every_step_in_order():
         assert torch.equal(gy, wy) and torch.equal(gp, wp)
 
 
+def test_graphed_step_with_several_steps_per_graph():
+    """GraphedSolveStep(steps=S): one graph carries S consecutive steps, each with its own input, upstream gradient and
+    results; every step equals the eager call bit for bit, also through the pipeline."""
+    _need_gpu()
+    f = clone_to(make_field(seed=12), DEV)
+    t = _t16()
+    B, S = 512, 3
+    kw = dict(method="dopri5", rtol=1e-5, atol=1e-5)
+    torch.manual_seed(8)
+    ys, gs_ = torch.randn(S, B, 16), torch.randn(S, 16, B, 16)
+
+    def eager(k):
+        y = ys[k].to(DEV).requires_grad_(True)
+        sol = gode.odeint(f, y, t, **kw)
+        g = torch.autograd.grad(sol, [y] + list(f.parameters()), gs_[k].to(DEV))
+        return sol.detach().cpu(), g[0].cpu(), torch.cat([x.reshape(-1) for x in g[1:]]).cpu()
+
+    want = [eager(k) for k in range(S)]
+    step = gode.GraphedSolveStep(f, B, t, adjoint=False, read_back=("param_grads", "grad_y0", "traj"), steps=S, **kw)
+    assert step.y0_host.shape == (S, B, 16) and step.host["param_grads"].shape[0] == S
+    step.grad_traj.copy_(gs_)
+    step.run(ys)
+    host = step.sync()
+    for k in range(S):
+        assert torch.equal(host["traj"][k], want[k][0]) and torch.equal(host["grad_y0"][k], want[k][1])
+        assert torch.equal(host["param_grads"][k], want[k][2])
+    pipe = gode.GraphedSolvePipeline(f, B, t, depth=2, adjoint=False, read_back=("param_grads",), steps=S, **kw)
+    for sl in pipe.slots:
+        sl.grad_traj.copy_(gs_)
+    pipe.submit(ys)
+    pipe.submit(ys.flip(0))
+    a, b = pipe.result()["param_grads"].clone(), pipe.result()["param_grads"].clone()
+    for k in range(S):
+        assert torch.equal(a[k], want[k][2])
+    # second submission: inputs reversed, upstream gradients not -> compare with eager on those pairs
+    y = ys[S - 1].to(DEV).requires_grad_(True)
+    g = torch.autograd.grad(gode.odeint(f, y, t, **kw), list(f.parameters()), gs_[0].to(DEV))
+    assert torch.equal(b[0], torch.cat([x.reshape(-1) for x in g]).cpu())
+
+
 def test_round2_kernels_replay_from_cuda_graphs():
     """The kernels added in round 2 under graph replay, bit-equal to the eager calls: wide-field dopri5 (its backward workspace
     holds the gradient rows: larger than the pooled workspaces, so it is created inside the capture), the persistent ODE-RNN
